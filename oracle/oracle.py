@@ -1,0 +1,435 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/oracle.c + oracle/_ref/libsimd_utils.so).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs — never from qdrant_b200/ (the product).
+
+`ensure_built()` compiles liboracle.so with gcc when it is missing; the reference's own C kernels
+(`_ref/libsimd_utils.so`) are compiled from /root/reference only when that tree exists (this
+container) and otherwise used prebuilt (GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+COSINE, EUCLID, DOT, MANHATTAN = 0, 1, 2, 3          # lib/segment/src/types.rs:313-322
+QD_COSINE, QD_DOT, QD_L1, QD_L2 = 0, 1, 2, 3          # lib/quantization/src/encoded_vectors.rs:13
+BQ_ONE, BQ_TWO, BQ_ONE_AND_HALF = 0, 1, 2             # encoded_vectors_binary.rs:34-39
+BQQ_SAME, BQQ_SCALAR4, BQQ_SCALAR8 = 0, 1, 2          # encoded_vectors_binary.rs:48-54
+
+SCORED = np.dtype([("idx", np.uint32), ("score", np.float32)])  # #[repr(C)] ScoredPointOffset
+
+
+def ensure_built() -> None:
+    need = not os.path.exists(os.path.join(_HERE, "liboracle.so")) or (
+        os.path.getmtime(os.path.join(_HERE, "liboracle.so")) < os.path.getmtime(os.path.join(_HERE, "oracle.c"))
+    )
+    need_ref = not os.path.exists(os.path.join(_HERE, "_ref", "libsimd_utils.so")) and os.path.isdir(
+        "/root/reference/lib/quantization/cpp"
+    )
+    if need or need_ref:
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+
+
+class SQ8Meta(C.Structure):
+    _fields_ = [
+        ("dim", C.c_uint32),
+        ("actual_dim", C.c_uint32),
+        ("alpha", C.c_float),
+        ("offset", C.c_float),
+        ("multiplier", C.c_float),
+        ("distance_type", C.c_int32),
+        ("invert", C.c_int32),
+    ]
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        ensure_built()
+        L = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        f32p, u8p, u32p, u64p = (C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64))
+        for name in ("dot", "euclid", "manhattan"):
+            for tier in ("avx", "sse", "scalar"):
+                fn = getattr(L, f"qo_{name}_{tier}")
+                fn.restype, fn.argtypes = C.c_float, [f32p, f32p, C.c_size_t]
+        for tier in ("avx", "sse", "scalar"):
+            fn = getattr(L, f"qo_cosine_preprocess_{tier}")
+            fn.restype, fn.argtypes = None, [f32p, f32p, C.c_size_t]
+        L.qo_similarity_f32.restype, L.qo_similarity_f32.argtypes = C.c_float, [C.c_int, f32p, f32p, C.c_size_t]
+        L.qo_preprocess_f32.restype, L.qo_preprocess_f32.argtypes = None, [C.c_int, f32p, f32p, C.c_size_t]
+        L.qo_postprocess_f32.restype, L.qo_postprocess_f32.argtypes = C.c_float, [C.c_int, C.c_float]
+        for name in ("dot", "cosine", "euclid", "manhattan"):
+            for tier in ("avx", "scalar"):
+                fn = getattr(L, f"qo_u8_{name}_{tier}")
+                fn.restype, fn.argtypes = C.c_float, [u8p, u8p, C.c_size_t]
+        L.qo_sq8_dot_avx.restype, L.qo_sq8_dot_avx.argtypes = C.c_float, [u8p, u8p, C.c_uint32]
+        L.qo_sq8_l1_avx.restype, L.qo_sq8_l1_avx.argtypes = C.c_float, [u8p, u8p, C.c_uint32]
+        mp = C.POINTER(SQ8Meta)
+        L.qo_sq8_get_shift.restype, L.qo_sq8_get_shift.argtypes = C.c_float, [mp]
+        L.qo_sq8_make_meta.restype, L.qo_sq8_make_meta.argtypes = None, [f32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, mp]
+        L.qo_sq8_encode.restype, L.qo_sq8_encode.argtypes = None, [mp, f32p, C.c_uint64, u8p]
+        L.qo_sq8_encode_query.restype, L.qo_sq8_encode_query.argtypes = C.c_float, [mp, f32p, u8p]
+        L.qo_sq8_score.restype, L.qo_sq8_score.argtypes = C.c_float, [mp, u8p, C.c_float, u8p]
+        L.qo_sq8_score_internal.restype, L.qo_sq8_score_internal.argtypes = C.c_float, [mp, u8p, u8p]
+        L.qo_pq_encode.restype, L.qo_pq_encode.argtypes = None, [f32p, C.c_uint64, C.c_uint32, C.c_uint32, f32p, C.c_uint32, u8p]
+        L.qo_pq_encode_query.restype, L.qo_pq_encode_query.argtypes = None, [f32p, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_int, C.c_int, f32p]
+        L.qo_pq_score.restype, L.qo_pq_score.argtypes = C.c_float, [f32p, C.c_uint32, u8p, C.c_uint32]
+        L.qo_pq_score_internal.restype, L.qo_pq_score_internal.argtypes = C.c_float, [u8p, u8p, C.c_uint32, C.c_uint32, f32p, C.c_int, C.c_int]
+        L.qo_bq_row_bytes.restype, L.qo_bq_row_bytes.argtypes = C.c_uint32, [C.c_uint32, C.c_int]
+        L.qo_bq_encode.restype, L.qo_bq_encode.argtypes = None, [f32p, C.c_uint32, C.c_int, f32p, u8p]
+        L.qo_bq_encode_scalar_query.restype, L.qo_bq_encode_scalar_query.argtypes = C.c_uint32, [f32p, C.c_uint32, C.c_int, C.c_uint32, u8p]
+        L.qo_bq_score.restype, L.qo_bq_score.argtypes = C.c_float, [u8p, u8p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_int]
+        L.qo_topk.restype, L.qo_topk.argtypes = C.c_uint32, [u32p, f32p, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.qo_scan_f32.restype = None
+        L.qo_scan_f32.argtypes = [C.c_int, f32p, C.c_uint64, C.c_uint64, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, C.c_void_p, u32p]
+        L.qo_scan_sq8.restype = None
+        L.qo_scan_sq8.argtypes = [mp, u8p, C.c_uint64, C.c_uint64, u8p, f32p, C.c_uint32, C.c_uint32, u64p, C.c_void_p, u32p]
+        L.qo_scan_pq.restype = None
+        L.qo_scan_pq.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, C.c_void_p, u32p]
+        L.qo_scan_bq.restype = None
+        L.qo_scan_bq.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_int, u8p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_void_p, u32p]
+        L.qo_score_points_f32.restype = None
+        L.qo_score_points_f32.argtypes = [C.c_int, f32p, C.c_uint32, f32p, u32p, C.c_uint64, f32p]
+        L.qo_score_rows_f32.restype = None
+        L.qo_score_rows_f32.argtypes = [C.c_int, f32p, C.c_uint64, C.c_uint32, f32p, f32p]
+        L.qo_preprocess_rows_f32.restype = None
+        L.qo_preprocess_rows_f32.argtypes = [C.c_int, f32p, f32p, C.c_uint64, C.c_uint32]
+        _LIB = L
+    return _LIB
+
+
+def ref():
+    """The reference's own C kernels compiled verbatim (None when the prebuilt .so is absent)."""
+    global _REF
+    if _REF is None:
+        ensure_built()
+        path = os.path.join(_HERE, "_ref", "libsimd_utils.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        u8p = C.POINTER(C.c_uint8)
+        for n in ("impl_score_dot_avx", "impl_score_l1_avx", "impl_score_dot_sse", "impl_score_l1_sse"):
+            fn = getattr(R, n)
+            fn.restype, fn.argtypes = C.c_float, [u8p, u8p, C.c_uint32]
+        for n in ("impl_xor_popcnt_scalar8_avx_uint128", "impl_xor_popcnt_scalar4_avx_uint128",
+                  "impl_xor_popcnt_sse_uint128", "impl_xor_popcnt_scalar8_sse_uint128",
+                  "impl_xor_popcnt_scalar4_sse_uint128"):
+            fn = getattr(R, n)
+            fn.restype, fn.argtypes = C.c_uint32, [u8p, u8p, C.c_uint32]
+        _REF = R
+    return _REF
+
+
+# ------------------------------------------------------------------ f32 metrics
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def similarity_f32(distance: int, q, v) -> np.float32:
+    q, v = _f32(q), _f32(v)
+    return np.float32(lib().qo_similarity_f32(distance, _p(q, C.c_float), _p(v, C.c_float), q.size))
+
+
+def preprocess_f32(distance: int, v) -> np.ndarray:
+    v = _f32(v)
+    out = np.empty_like(v)
+    lib().qo_preprocess_f32(distance, _p(v, C.c_float), _p(out, C.c_float), v.size)
+    return out
+
+
+def preprocess_rows_f32(distance: int, rows) -> np.ndarray:
+    rows = _f32(rows)
+    out = np.empty_like(rows)
+    lib().qo_preprocess_rows_f32(distance, _p(rows, C.c_float), _p(out, C.c_float), rows.shape[0], rows.shape[1])
+    return out
+
+
+def postprocess_f32(distance: int, s) -> np.float32:
+    return np.float32(lib().qo_postprocess_f32(distance, float(s)))
+
+
+def raw_f32(name: str, tier: str, a, b) -> np.float32:
+    a, b = _f32(a), _f32(b)
+    return np.float32(getattr(lib(), f"qo_{name}_{tier}")(_p(a, C.c_float), _p(b, C.c_float), a.size))
+
+
+def raw_cosine_preprocess(tier: str, v) -> np.ndarray:
+    v = _f32(v)
+    out = np.empty_like(v)
+    getattr(lib(), f"qo_cosine_preprocess_{tier}")(_p(v, C.c_float), _p(out, C.c_float), v.size)
+    return out
+
+
+def raw_u8(name: str, tier: str, a, b) -> np.float32:
+    a, b = _u8(a), _u8(b)
+    return np.float32(getattr(lib(), f"qo_u8_{name}_{tier}")(_p(a, C.c_uint8), _p(b, C.c_uint8), a.size))
+
+
+def similarity_u8(distance: int, q, v) -> np.float32:
+    """Metric<u8>::similarity dispatch (metric_uint/simple_*.rs): avx2 for dim>=32, else integer-exact tiers."""
+    name = {COSINE: "cosine", EUCLID: "euclid", DOT: "dot", MANHATTAN: "manhattan"}[distance]
+    q = _u8(q)
+    return raw_u8(name, "avx" if q.size >= 32 else "scalar", q, v)
+
+
+def score_rows_f32(distance: int, rows, q_pre) -> np.ndarray:
+    rows, q_pre = _f32(rows), _f32(q_pre)
+    out = np.empty(rows.shape[0], dtype=np.float32)
+    lib().qo_score_rows_f32(distance, _p(rows, C.c_float), rows.shape[0], rows.shape[1], _p(q_pre, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def score_points_f32(distance: int, base, q_pre, ids) -> np.ndarray:
+    base, q_pre = _f32(base), _f32(q_pre)
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    out = np.empty(ids.size, dtype=np.float32)
+    lib().qo_score_points_f32(distance, _p(base, C.c_float), base.shape[1], _p(q_pre, C.c_float), _p(ids, C.c_uint32), ids.size, _p(out, C.c_float))
+    return out
+
+
+def _bitmap_ptr(deleted):
+    if deleted is None:
+        return None, None
+    d = np.ascontiguousarray(deleted, dtype=np.uint64)
+    return d, _p(d, C.c_uint64)
+
+
+def scan_f32(distance: int, base, queries_pre, top: int, deleted=None, row_begin=0, row_end=None):
+    """peek_top_iter over rows [row_begin,row_end) -> list of SCORED arrays (one per query, descending)."""
+    base, queries_pre = _f32(base), np.atleast_2d(_f32(queries_pre))
+    nq = queries_pre.shape[0]
+    row_end = base.shape[0] if row_end is None else row_end
+    out = np.zeros((nq, max(top, 1)), dtype=SCORED)
+    counts = np.zeros(nq, dtype=np.uint32)
+    keep, dp = _bitmap_ptr(deleted)
+    lib().qo_scan_f32(distance, _p(base, C.c_float), row_begin, row_end, base.shape[1], _p(queries_pre, C.c_float), nq, top,
+                      dp, out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+    return [out[i, : counts[i]].copy() for i in range(nq)]
+
+
+def topk(scores, top: int, ids=None) -> np.ndarray:
+    scores = _f32(scores)
+    out = np.zeros(max(top, 1), dtype=SCORED)
+    idp = None
+    if ids is not None:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        idp = _p(ids, C.c_uint32)
+    n = lib().qo_topk(idp, _p(scores, C.c_float), scores.size, top, out.ctypes.data_as(C.c_void_p))
+    return out[:n].copy()
+
+
+# ------------------------------------------------------------------ SQ8
+@dataclass
+class SQ8:
+    meta: SQ8Meta
+    rows: np.ndarray  # [count, 4 + actual_dim] u8
+
+    @property
+    def row_bytes(self) -> int:
+        return 4 + self.meta.actual_dim
+
+    @staticmethod
+    def encode(data, distance_type: int, invert: bool) -> "SQ8":
+        """EncodedVectorsU8::encode with quantile=None (encoded_vectors_u8.rs:143-316)."""
+        data = _f32(data)
+        m = SQ8Meta()
+        lib().qo_sq8_make_meta(_p(data, C.c_float), data.shape[0], data.shape[1], distance_type, int(invert), C.byref(m))
+        rows = np.zeros((data.shape[0], 4 + m.actual_dim), dtype=np.uint8)
+        lib().qo_sq8_encode(C.byref(m), _p(data, C.c_float), data.shape[0], _p(rows, C.c_uint8))
+        return SQ8(m, rows)
+
+    def encode_query(self, q):
+        q = _f32(q)
+        code = np.zeros(self.meta.actual_dim, dtype=np.uint8)
+        off = lib().qo_sq8_encode_query(C.byref(self.meta), _p(q, C.c_float), _p(code, C.c_uint8))
+        return code, np.float32(off)
+
+    def score(self, q_code, q_off, row_id: int) -> np.float32:
+        row = np.ascontiguousarray(self.rows[row_id])
+        return np.float32(lib().qo_sq8_score(C.byref(self.meta), _p(_u8(q_code), C.c_uint8), C.c_float(float(q_off)), _p(row, C.c_uint8)))
+
+    def score_internal(self, i: int, j: int) -> np.float32:
+        ri, rj = np.ascontiguousarray(self.rows[i]), np.ascontiguousarray(self.rows[j])
+        return np.float32(lib().qo_sq8_score_internal(C.byref(self.meta), _p(ri, C.c_uint8), _p(rj, C.c_uint8)))
+
+    def score_all(self, q_code, q_off) -> np.ndarray:
+        return np.array([self.score(q_code, q_off, i) for i in range(self.rows.shape[0])], dtype=np.float32)
+
+    def scan(self, q_codes, q_offs, top: int, deleted=None):
+        q_codes = np.atleast_2d(_u8(q_codes))
+        q_offs = np.atleast_1d(_f32(q_offs))
+        nq = q_codes.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED)
+        counts = np.zeros(nq, dtype=np.uint32)
+        keep, dp = _bitmap_ptr(deleted)
+        rows = np.ascontiguousarray(self.rows)
+        lib().qo_scan_sq8(C.byref(self.meta), _p(rows, C.c_uint8), 0, rows.shape[0], _p(q_codes, C.c_uint8), _p(q_offs, C.c_float),
+                          nq, top, dp, out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
+
+
+# ------------------------------------------------------------------ PQ
+def kmeans_pq_centroids(data, chunk: int, n_centroids: int = 256, iters: int = 8, seed: int = 7, sample: int = 10_000) -> np.ndarray:
+    """OUR k-means (the reference's training is RNG-dependent and unpinned): per-chunk Lloyd
+    on a seeded sample; returns centroids as n_centroids full-dim vectors (Metadata.centroids layout,
+    encoded_vectors_pq.rs:47-51)."""
+    data = _f32(data)
+    rng = np.random.default_rng(seed)
+    n, dim = data.shape
+    samp = data[rng.choice(n, size=min(sample, n), replace=False)]
+    cents = np.zeros((n_centroids, dim), dtype=np.float32)
+    for s in range(0, dim, chunk):
+        e = min(s + chunk, dim)
+        x = samp[:, s:e]
+        c = x[rng.choice(x.shape[0], size=n_centroids, replace=x.shape[0] < n_centroids)].copy()
+        for _ in range(iters):
+            d = (x * x).sum(1)[:, None] - 2.0 * x @ c.T + (c * c).sum(1)[None, :]
+            a = d.argmin(1)
+            for k in range(n_centroids):
+                sel = x[a == k]
+                if len(sel):
+                    c[k] = sel.mean(0)
+        cents[:, s:e] = c
+    return cents
+
+
+@dataclass
+class PQ:
+    dim: int
+    chunk: int
+    centroids: np.ndarray  # [n_centroids, dim] f32
+    codes: np.ndarray      # [count, m] u8
+    distance_type: int
+    invert: bool
+
+    @property
+    def m(self) -> int:
+        return (self.dim + self.chunk - 1) // self.chunk
+
+    @staticmethod
+    def encode(data, chunk: int, centroids, distance_type: int, invert: bool) -> "PQ":
+        data, centroids = _f32(data), _f32(centroids)
+        dim = data.shape[1]
+        m = (dim + chunk - 1) // chunk
+        codes = np.zeros((data.shape[0], m), dtype=np.uint8)
+        lib().qo_pq_encode(_p(data, C.c_float), data.shape[0], dim, chunk, _p(centroids, C.c_float), centroids.shape[0], _p(codes, C.c_uint8))
+        return PQ(dim, chunk, centroids, codes, distance_type, invert)
+
+    def encode_query(self, q) -> np.ndarray:
+        q = _f32(q)
+        lut = np.zeros((self.m, self.centroids.shape[0]), dtype=np.float32)
+        lib().qo_pq_encode_query(_p(q, C.c_float), self.dim, self.chunk, _p(self.centroids, C.c_float), self.centroids.shape[0],
+                                 self.distance_type, int(self.invert), _p(lut, C.c_float))
+        return lut
+
+    def score(self, lut, row_id: int) -> np.float32:
+        code = np.ascontiguousarray(self.codes[row_id])
+        lut = _f32(lut)
+        return np.float32(lib().qo_pq_score(_p(lut, C.c_float), self.centroids.shape[0], _p(code, C.c_uint8), self.m))
+
+    def score_internal(self, i: int, j: int) -> np.float32:
+        ci, cj = np.ascontiguousarray(self.codes[i]), np.ascontiguousarray(self.codes[j])
+        return np.float32(lib().qo_pq_score_internal(_p(ci, C.c_uint8), _p(cj, C.c_uint8), self.dim, self.chunk,
+                                                     _p(self.centroids, C.c_float), self.distance_type, int(self.invert)))
+
+    def scan(self, luts, top: int, deleted=None):
+        luts = _f32(luts)
+        if luts.ndim == 2:
+            luts = luts[None]
+        nq = luts.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED)
+        counts = np.zeros(nq, dtype=np.uint32)
+        keep, dp = _bitmap_ptr(deleted)
+        codes = np.ascontiguousarray(self.codes)
+        lib().qo_scan_pq(_p(codes, C.c_uint8), 0, codes.shape[0], self.m, self.centroids.shape[0], _p(luts, C.c_float), nq, top, dp,
+                         out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
+
+
+# ------------------------------------------------------------------ BQ
+def bq_row_bytes(dim: int, encoding: int) -> int:
+    return int(lib().qo_bq_row_bytes(dim, encoding))
+
+
+def bq_mean_std(data) -> np.ndarray:
+    """Per-coordinate (mean, stddev) for the 2-bit / 1.5-bit encodings.  The reference computes them with a
+    streaming estimator (vector_stats.rs); training parity is unpinned, so tests feed the SAME stats to both sides."""
+    data = _f32(data)
+    return np.stack([data.mean(0), data.std(0)], axis=1).astype(np.float32)
+
+
+@dataclass
+class BQ:
+    dim: int
+    encoding: int
+    query_encoding: int
+    rows: np.ndarray  # [count, row_bytes] u8
+    distance_type: int
+    invert: bool
+    mean_std: np.ndarray | None = None
+
+    @property
+    def query_bits(self) -> int:
+        return {BQQ_SAME: 1, BQQ_SCALAR4: 4, BQQ_SCALAR8: 8}[self.query_encoding]
+
+    @staticmethod
+    def encode(data, encoding: int, query_encoding: int, distance_type: int, invert: bool, mean_std=None) -> "BQ":
+        data = _f32(data)
+        dim = data.shape[1]
+        rb = bq_row_bytes(dim, encoding)
+        rows = np.zeros((data.shape[0], rb), dtype=np.uint8)
+        ms = None if mean_std is None else _f32(mean_std)
+        for i in range(data.shape[0]):
+            lib().qo_bq_encode(_p(data[i], C.c_float), dim, encoding, None if ms is None else _p(ms, C.c_float),
+                               rows[i].ctypes.data_as(C.POINTER(C.c_uint8)))
+        return BQ(dim, encoding, query_encoding, rows, distance_type, invert, ms)
+
+    @property
+    def query_bytes(self) -> int:
+        return self.rows.shape[1] * self.query_bits
+
+    def encode_query(self, q) -> np.ndarray:
+        q = _f32(q)
+        if self.query_encoding == BQQ_SAME:
+            out = np.zeros(self.rows.shape[1], dtype=np.uint8)
+            lib().qo_bq_encode(_p(q, C.c_float), self.dim, self.encoding, None if self.mean_std is None else _p(self.mean_std, C.c_float),
+                               _p(out, C.c_uint8))
+            return out
+        out = np.zeros(self.query_bytes, dtype=np.uint8)
+        n = lib().qo_bq_encode_scalar_query(_p(q, C.c_float), self.dim, self.encoding, self.query_bits, _p(out, C.c_uint8))
+        assert n == out.size, (n, out.size)
+        return out
+
+    def score(self, q_enc, row_id: int) -> np.float32:
+        row = np.ascontiguousarray(self.rows[row_id])
+        q_enc = _u8(q_enc)
+        return np.float32(lib().qo_bq_score(_p(row, C.c_uint8), _p(q_enc, C.c_uint8), self.dim, self.encoding, self.query_bits,
+                                            self.distance_type, int(self.invert)))
+
+    def scan(self, q_encs, top: int, deleted=None):
+        q_encs = np.atleast_2d(_u8(q_encs))
+        nq = q_encs.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED)
+        counts = np.zeros(nq, dtype=np.uint32)
+        keep, dp = _bitmap_ptr(deleted)
+        rows = np.ascontiguousarray(self.rows)
+        lib().qo_scan_bq(_p(rows, C.c_uint8), 0, rows.shape[0], self.dim, self.encoding, self.query_bits, self.distance_type, int(self.invert),
+                         _p(q_encs, C.c_uint8), q_encs.shape[1], nq, top, dp, out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+        return [out[i, : counts[i]].copy() for i in range(nq)]

@@ -1,0 +1,173 @@
+"""Pins the CPU oracle against the reference's own known-answer tests.
+
+Each case re-types the fixed vectors of a reference unit test and asserts what that test asserts
+(SIMD tier == scalar tier, exactly), plus the hand-computable value.  Sources:
+  f32 : lib/segment/src/spaces/simple_avx.rs:218-256, simple_sse.rs:206-..., simple.rs:248-277
+  u8  : lib/segment/src/spaces/metric_uint/avx2/{dot.rs:77-106,cosine.rs:112-170,euclid.rs,manhattan.rs}
+  topk: lib/segment/src/spaces/tools.rs:64-75
+  SQ8/BQ inner loops: the reference's C kernels compiled verbatim (oracle/_ref/libsimd_utils.so)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def f32_kat():
+    base = list(range(10, 26))
+    v1 = base * 4 + [26, 27, 28, 29, 30, 31]
+    v2 = list(range(40, 56)) + base * 3 + [56, 57, 58, 59, 60, 61]
+    return np.array(v1, np.float32), np.array(v2, np.float32)
+
+
+def u8_kat():
+    a = [255, 255, 0] + list(range(1, 18))
+    v1 = a * 5
+    b0 = [255, 255, 0] + list(range(254, 237, -1))
+    b = [255, 255, 255] + list(range(254, 237, -1))
+    v2 = b0 + b * 4
+    assert len(v1) == 100 and len(v2) == 100
+    return np.array(v1, np.uint8), np.array(v2, np.uint8)
+
+
+def test_f32_avx_equals_scalar_kat(oracle):
+    v1, v2 = f32_kat()
+    assert v1.size == 70
+    for name in ("euclid", "manhattan", "dot"):
+        assert oracle.raw_f32(name, "avx", v1, v2) == oracle.raw_f32(name, "scalar", v1, v2), name
+    # hand-computable: first 16 differ by 30, last 6 by 30 -> 22 * 900 ; manhattan 22 * 30
+    assert oracle.raw_f32("euclid", "avx", v1, v2) == np.float32(-22 * 900)
+    assert oracle.raw_f32("manhattan", "avx", v1, v2) == np.float32(-22 * 30)
+    assert oracle.raw_f32("dot", "avx", v1, v2) == np.float32(np.dot(v1.astype(np.float64), v2.astype(np.float64)))
+    np.testing.assert_array_equal(oracle.raw_cosine_preprocess("avx", v1), oracle.raw_cosine_preprocess("scalar", v1))
+
+
+def test_f32_sse_equals_scalar_kat(oracle):
+    v1, v2 = f32_kat()
+    for name in ("euclid", "manhattan", "dot"):
+        assert oracle.raw_f32(name, "sse", v1, v2) == oracle.raw_f32(name, "scalar", v1, v2), name
+    np.testing.assert_array_equal(oracle.raw_cosine_preprocess("sse", v1), oracle.raw_cosine_preprocess("scalar", v1))
+
+
+def test_cosine_preprocess_zero_and_stable(oracle):
+    # simple.rs:248-252
+    z = np.zeros(4, np.float32)
+    np.testing.assert_array_equal(oracle.preprocess_f32(oracle.COSINE, z), z)
+    # simple.rs:256-277: re-normalising a normalised vector is a fixed point (100 x 1500-d)
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        v = rng.uniform(-1, 1, 1500).astype(np.float32)
+        p1 = oracle.preprocess_f32(oracle.COSINE, v)
+        p2 = oracle.preprocess_f32(oracle.COSINE, p1)
+        np.testing.assert_array_equal(p1, p2)
+
+
+def test_dispatch_tiers(oracle):
+    rng = np.random.default_rng(5)
+    for dim, tier in ((8, "scalar"), (15, "scalar"), (16, "sse"), (31, "sse"), (32, "avx"), (70, "avx"), (768, "avx")):
+        a, b = rng.standard_normal(dim).astype(np.float32), rng.standard_normal(dim).astype(np.float32)
+        assert oracle.similarity_f32(oracle.DOT, a, b) == oracle.raw_f32("dot", tier, a, b)
+        assert oracle.similarity_f32(oracle.COSINE, a, b) == oracle.raw_f32("dot", tier, a, b)
+        assert oracle.similarity_f32(oracle.EUCLID, a, b) == oracle.raw_f32("euclid", tier, a, b)
+        assert oracle.similarity_f32(oracle.MANHATTAN, a, b) == oracle.raw_f32("manhattan", tier, a, b)
+
+
+def test_postprocess(oracle):
+    assert oracle.postprocess_f32(oracle.EUCLID, -9.0) == np.float32(3.0)
+    assert oracle.postprocess_f32(oracle.MANHATTAN, -9.0) == np.float32(9.0)
+    assert oracle.postprocess_f32(oracle.DOT, -9.0) == np.float32(-9.0)
+
+
+def test_u8_avx_equals_scalar_kat(oracle):
+    v1, v2 = u8_kat()
+    for name in ("dot", "cosine", "euclid", "manhattan"):
+        assert oracle.raw_u8(name, "avx", v1, v2) == oracle.raw_u8(name, "scalar", v1, v2), name
+    d = int(np.dot(v1.astype(np.int64), v2.astype(np.int64)))
+    assert oracle.raw_u8("dot", "avx", v1, v2) == np.float32(d)
+
+
+def test_u8_cosine_zero(oracle):
+    # metric_uint/avx2/cosine.rs:148-166 and simple_cosine.rs:80-87
+    v1 = np.zeros(8, np.uint8)
+    v2 = np.array([255, 255, 0, 254, 253, 252, 251, 250], np.uint8)
+    for tier in ("avx", "scalar"):
+        assert oracle.raw_u8("cosine", tier, v1, v2) == 0.0
+        assert oracle.raw_u8("cosine", tier, v2, v1) == 0.0
+        assert oracle.raw_u8("cosine", tier, v1, v1) == 0.0
+
+
+def test_peek_top_kat(oracle):
+    # tools.rs:64-75
+    data = np.array([10, 20, 40, 5, 100, 33, 84, 65, 20, 43, 44, 42], np.float32)
+    res = oracle.topk(data, 3)
+    assert list(res["score"]) == [100.0, 84.0, 65.0]
+    assert list(res["idx"]) == [4, 6, 7]
+    res = oracle.topk(-data, 3)
+    assert list(-res["score"]) == [5.0, 10.0, 20.0]
+    assert oracle.topk(data, 0).size == 0
+    assert oracle.topk(data, 100).size == data.size  # fewer points than top
+
+
+def test_topk_matches_sort(oracle):
+    rng = np.random.default_rng(3)
+    s = rng.standard_normal(5000).astype(np.float32)
+    res = oracle.topk(s, 17)
+    order = np.argsort(-s, kind="stable")[:17]
+    np.testing.assert_array_equal(res["score"], s[order])
+    np.testing.assert_array_equal(res["idx"], order.astype(np.uint32))
+
+
+def test_sq8_inner_loops_match_reference_c(oracle):
+    """oracle restatement == the reference's own avx2.c / sse.c compiled verbatim, on random + extreme codes."""
+    R = oracle.ref()
+    if R is None:
+        pytest.skip("oracle/_ref/libsimd_utils.so not built (no /root/reference and no prebuilt)")
+    L = oracle.lib()
+    u8p = C.POINTER(C.c_uint8)
+    rng = np.random.default_rng(42)
+    for dim in (16, 32, 48, 64, 80, 768, 784, 1536, 4096):
+        for trial in range(20):
+            q = rng.integers(0, 128, dim, dtype=np.uint8)
+            v = rng.integers(0, 128, dim, dtype=np.uint8)
+            if trial == 0:
+                q[:] = 127; v[:] = 127
+            if trial == 1:
+                q[:] = 0
+            qp, vp = q.ctypes.data_as(u8p), v.ctypes.data_as(u8p)
+            assert L.qo_sq8_dot_avx(qp, vp, dim) == R.impl_score_dot_avx(qp, vp, dim)
+            assert L.qo_sq8_l1_avx(qp, vp, dim) == R.impl_score_l1_avx(qp, vp, dim)
+            # the SSE tier is the same integers for dims whose sums stay < 2^24 (exactness window)
+            if dim <= 1040:
+                assert R.impl_score_dot_sse(qp, vp, dim) == R.impl_score_dot_avx(qp, vp, dim)
+                assert R.impl_score_dot_avx(qp, vp, dim) == np.float32(int(np.dot(q.astype(np.int64), v.astype(np.int64))))
+
+
+def test_bq_popcount_matches_reference_c(oracle):
+    R = oracle.ref()
+    if R is None:
+        pytest.skip("oracle/_ref/libsimd_utils.so not built")
+    rng = np.random.default_rng(9)
+    u8p = C.POINTER(C.c_uint8)
+    for dim in (1, 127, 128, 129, 768, 1000, 1536):
+        data = rng.standard_normal((4, dim)).astype(np.float32)
+        q = rng.standard_normal(dim).astype(np.float32)
+        for qenc, bits, fn in ((oracle.BQQ_SCALAR8, 8, R.impl_xor_popcnt_scalar8_avx_uint128),
+                               (oracle.BQQ_SCALAR4, 4, R.impl_xor_popcnt_scalar4_avx_uint128)):
+            bq = oracle.BQ.encode(data, oracle.BQ_ONE, qenc, oracle.QD_DOT, False)
+            qe = bq.encode_query(q)
+            words = bq.rows.shape[1] // 16
+            for i in range(data.shape[0]):
+                row = np.ascontiguousarray(bq.rows[i])
+                x = fn(qe.ctypes.data_as(u8p), row.ctypes.data_as(u8p), words)
+                xf = np.float32(x) / np.float32((1 << bits) - 1)
+                zeros = np.float32(dim) - xf
+                assert bq.score(qe, i) == zeros - xf
+        bq = oracle.BQ.encode(data, oracle.BQ_ONE, oracle.BQQ_SAME, oracle.QD_DOT, False)
+        qe = bq.encode_query(q)
+        for i in range(data.shape[0]):
+            row = np.ascontiguousarray(bq.rows[i])
+            x = R.impl_xor_popcnt_sse_uint128(qe.ctypes.data_as(u8p), row.ctypes.data_as(u8p), bq.rows.shape[1] // 16)
+            assert bq.score(qe, i) == np.float32(dim - x) - np.float32(x)
+            bits_q = (q > 0)
+            bits_v = (data[i] > 0)
+            assert x == int(np.sum(bits_q != bits_v))
