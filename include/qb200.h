@@ -1,0 +1,189 @@
+/*
+ * qb200.h — C ABI of libqdrant_b200.so: Qdrant's vector-scoring hot path on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference has no FFI seam for scorers; its seam is the Rust trait
+ * object `RawScorer` (lib/segment/src/vector_storage/raw_scorer.rs:39-54) built by `RawScorerBuilder`
+ * (:122-128) / `QuantizedVectorsRead::raw_scorer` (quantized_vectors/read_access.rs:26-34) and driven by
+ * `BatchFilteredSearcher::peek_top_iter` (lib/segment/src/index/hnsw_index/point_scorer.rs:423-472) and
+ * `FilteredScorer::score_points` (:265-295).  Each entry point below names the reference interface it
+ * replaces.  INTEGRATION.md shows the Rust `extern "C"` block + `impl RawScorer` adapter a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns qb_status (0 = ok, < 0 = error); qb_last_error() gives the thread-local text.
+ *     No exception crosses the ABI.  Scoring calls on valid handles fail only on CUDA errors, which the Rust
+ *     adapter `expect`s exactly like the reference's `.expect("read vectors")` (metric_query_scorer.rs:91).
+ *   - handles are opaque and owned by the library; host buffers are borrowed for the duration of a call;
+ *     outputs are caller-allocated.
+ *   - any thread may call any function.  One qb_scorer must not be used from two threads at once (the Rust
+ *     `&mut FilteredScorer`), but many scorers / searches over one qb_storage may run concurrently
+ *     (segments_searcher.rs:255): each scorer and each search context owns a CUDA stream.
+ *   - there is NO CPU fallback: without a CUDA device every create call returns QB_ERR_NO_DEVICE.
+ *   - "greater score = closer" everywhere, exactly as Metric::similarity (spaces/metric.rs:8-17).
+ */
+#ifndef QB200_H
+#define QB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define QB_API __attribute__((visibility("default")))
+#else
+#define QB_API
+#endif
+
+typedef int32_t qb_status;
+enum {
+    QB_OK = 0,
+    QB_ERR_INVALID = -1,      /* bad argument (null, dim mismatch, id out of range, top == 0 ...) */
+    QB_ERR_CUDA = -2,         /* CUDA runtime / driver error, text in qb_last_error() */
+    QB_ERR_UNSUPPORTED = -3,  /* e.g. internal scorer on PQ (encode_internal_vector = None, encoded_vectors_pq.rs:624) */
+    QB_ERR_OOM = -4,
+    QB_ERR_CANCELLED = -5,    /* *is_stopped became non-zero (check_process_stopped, point_scorer.rs:433) */
+    QB_ERR_NO_DEVICE = -6
+};
+
+/* Distance — same order as lib/segment/src/types.rs:313-322 */
+typedef enum { QB_DIST_COSINE = 0, QB_DIST_EUCLID = 1, QB_DIST_DOT = 2, QB_DIST_MANHATTAN = 3 } qb_distance;
+/* VectorStorageDatatype (types.rs) of a dense storage */
+typedef enum { QB_DT_F32 = 0, QB_DT_F16 = 1, QB_DT_U8 = 2 } qb_dtype;
+/* quantization::DistanceType — lib/quantization/src/encoded_vectors.rs:13 */
+typedef enum { QB_QD_COSINE = 0, QB_QD_DOT = 1, QB_QD_L1 = 2, QB_QD_L2 = 3 } qb_qdistance;
+/* BQ Encoding / QueryEncoding — lib/quantization/src/encoded_vectors_binary.rs:34-54 */
+typedef enum { QB_BQ_ONE_BIT = 0, QB_BQ_TWO_BITS = 1, QB_BQ_ONE_AND_HALF_BITS = 2 } qb_bq_encoding;
+typedef enum { QB_BQQ_SAME_AS_STORAGE = 0, QB_BQQ_SCALAR4 = 1, QB_BQQ_SCALAR8 = 2 } qb_bq_query_encoding;
+
+/* #[repr(C)] ScoredPointOffset — lib/common/common/src/types.rs:12-17 */
+typedef struct { uint32_t idx; float score; } qb_scored_point;
+
+/* HardwareCounterCell deltas a drop-in scorer must keep reporting (metric_query_scorer.rs:43-49,84-85;
+ * encoded_vectors_u8.rs:785-787).  Values are already multiplied by the reference's multipliers. */
+typedef struct { uint64_t cpu; uint64_t vector_io_read; } qb_hw_counters;
+
+typedef struct qb_storage qb_storage;  /* one segment's vectors (dense or quantized) resident in HBM */
+typedef struct qb_scorer qb_scorer;    /* Box<dyn RawScorer>: a preprocessed/encoded query bound to a storage */
+
+/* ---------------------------------------------------------------- library / device ------------------ */
+QB_API const char* qb_last_error(void);
+QB_API int32_t qb_abi_version(void);
+QB_API qb_status qb_device_count(int32_t* out);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+QB_API uint64_t qb_kernel_launch_count(void);
+
+/* ---------------------------------------------------------------- storages -------------------------- */
+/* Dense vectors as the reference stores them: row-major, `dim` elements of `dt`, rows `row_stride_bytes`
+ * apart (dense/immutable_dense_vectors.rs:100-113).  Cosine rows must already be normalised the way
+ * Distance::preprocess_vector does at insert time (types.rs:334-347) — see qb_metric_preprocess.
+ * host_rows may be NULL to allocate an empty storage filled later with qb_storage_write_rows*. */
+QB_API qb_status qb_storage_create_dense(int32_t device, qb_dtype dt, qb_distance distance, uint32_t dim, uint64_t count,
+                                  const void* host_rows, uint64_t row_stride_bytes, qb_storage** out);
+/* chunked upload (the reference uploads in chunks too, UPLOAD_CHUNK_SIZE, gpu_vector_storage/mod.rs) */
+QB_API qb_status qb_storage_write_rows(qb_storage* s, uint64_t first_row, uint64_t n_rows, const void* host_rows, uint64_t row_stride_bytes);
+QB_API qb_status qb_storage_write_rows_device(qb_storage* s, uint64_t first_row, uint64_t n_rows, const void* dev_rows, uint64_t row_stride_bytes);
+/* read back stored rows (dense storages; used by rescoring and by the full-size parity tests) */
+QB_API qb_status qb_storage_read_rows(const qb_storage* s, const uint32_t* ids, uint64_t n, void* host_out);
+
+/* Quantized storages.  `dt` + `invert` are the quantizer's VectorParameters (construct_vector_parameters,
+ * quantized_vectors.rs:205-234: Cosine is stored as Dot, invert = Euclid || Manhattan); `metric` is the segment's
+ * Distance and only decides Metric::preprocess of incoming queries (QuantizedQueryScorer::new,
+ * quantized_query_scorer.rs:29-55).
+ *
+ * SQ8: rows exactly as `quantized.data` holds them — [f32 v_off][actual_dim u8], stride row_bytes =
+ * 4 + ceil(dim/16)*16 (encoded_vectors_u8.rs:22,240-283,622-629) — plus MetadataInt8 (:84-91). */
+QB_API qb_status qb_storage_create_sq8(int32_t device, uint32_t dim, uint64_t count, const uint8_t* rows, uint32_t row_bytes,
+                                float alpha, float offset, float multiplier, qb_qdistance dt, int32_t invert,
+                                qb_distance metric, qb_storage** out);
+/* PQ: codes [count x m] u8, centroids as 256 (n_centroids) full-dim vectors and the chunk division
+ * (Metadata, encoded_vectors_pq.rs:46-51); division = 2*m uint32 {start,end}. */
+QB_API qb_status qb_storage_create_pq(int32_t device, uint32_t dim, uint32_t m, const uint32_t* div_start_end,
+                               const float* centroids, uint32_t n_centroids, const uint8_t* codes, uint64_t count,
+                               qb_qdistance dt, int32_t invert, qb_distance metric, qb_storage** out);
+/* BQ (u128 words): rows of row_bytes = ceil(bits/128)*16 (encoded_vectors_binary.rs:829-839);
+ * mean_std = dim x {mean, stddev} for the 2-bit / 1.5-bit encodings (VectorStats), or NULL. */
+QB_API qb_status qb_storage_create_bq(int32_t device, uint32_t dim, qb_bq_encoding enc, qb_bq_query_encoding qenc,
+                               const uint8_t* rows, uint32_t row_bytes, uint64_t count, qb_qdistance dt, int32_t invert,
+                               const float* mean_std, qb_distance metric, qb_storage** out);
+QB_API void qb_storage_destroy(qb_storage* s);
+
+QB_API qb_status qb_storage_info(const qb_storage* s, uint32_t* dim, uint64_t* count, uint64_t* hbm_bytes);
+/* Resident soft-delete flags (bit i = 1 => point i deleted): the storage-level `deleted` BitSlice that
+ * ScorerFilters / not_deleted_checker consult (point_scorer.rs:351-352).  NULL clears. */
+QB_API qb_status qb_storage_set_deleted(qb_storage* s, const uint64_t* bitmap_words, uint64_t n_words);
+/* CUDA stream (cudaStream_t) the storage's default search context launches on — for event timing */
+QB_API void* qb_storage_stream(qb_storage* s);
+
+/* Metric::preprocess for `n` vectors (spaces/metric.rs:14; cosine = cosine_preprocess_avx arithmetic,
+ * simple_avx.rs:127-165).  in/out are host buffers of n*dim f32 (may alias). */
+QB_API qb_status qb_metric_preprocess(int32_t device, qb_distance distance, uint32_t dim, uint64_t n, const float* in, float* out);
+/* same, in place on device memory (synthetic data generated on the GPU) */
+QB_API qb_status qb_metric_preprocess_device(int32_t device, qb_distance distance, uint32_t dim, uint64_t n, float* dev_rows, uint64_t row_stride_bytes);
+/* MetricPostProcessing::postprocess applied by the caller at shard level (local_shard/search.rs:150-170) */
+QB_API float qb_metric_postprocess(qb_distance distance, float score);
+
+/* ---------------------------------------------------------------- RawScorer ------------------------- */
+/* RawScorerBuilder::build_raw_scorer / QuantizedVectorsRead::raw_scorer for QueryVector::Nearest:
+ * runs Metric::preprocess + (quantized) EncodedVectors::encode_query on the device. query = dim raw f32. */
+QB_API qb_status qb_scorer_create(qb_storage* s, const float* query, qb_scorer** out);
+/* QuantizedVectorsRead::raw_internal_scorer / FilteredScorer::new_internal: the stored point is the query.
+ * QB_ERR_UNSUPPORTED for PQ (encoded_vectors_pq.rs:624-627), as in the reference. */
+QB_API qb_status qb_scorer_create_internal(qb_storage* s, uint32_t point_id, qb_scorer** out);
+QB_API void qb_scorer_destroy(qb_scorer* sc);
+/* RawScorer::score_points(&[PointOffsetType], &mut [ScoreType]) — raw_scorer.rs:40 */
+QB_API qb_status qb_score_points(qb_scorer* sc, const uint32_t* ids, size_t n, float* scores);
+/* RawScorer::score_point — raw_scorer.rs:43 */
+QB_API qb_status qb_score_point(qb_scorer* sc, uint32_t id, float* score);
+/* RawScorer::score_internal — raw_scorer.rs:50 (QB_ERR_INVALID when an id is out of range; Rust adapter panics) */
+QB_API qb_status qb_score_internal(qb_scorer* sc, uint32_t a, uint32_t b, float* score);
+/* read and reset the hardware-counter deltas accumulated by this scorer */
+QB_API qb_status qb_scorer_take_counters(qb_scorer* sc, qb_hw_counters* out);
+
+/* ---------------------------------------------------------------- brute-force scan ------------------ */
+/* BatchFilteredSearcher::{new, peek_top_iter} fused: scores every candidate point against every query and
+ * keeps the `top` best per query, sorted by descending score (FixedLengthPriorityQueue::into_sorted_vec).
+ *   queries        n_queries x dim raw f32 (preprocessed + encoded on the device)
+ *   deleted_bitmap optional per-call soft-delete bits (bit=1 deleted), OR-ed with the resident flags
+ *   id_list/n_ids  optional explicit candidate ids (a payload filter's result); NULL = all rows
+ *   is_stopped     optional cancellation flag, polled between kernel launches
+ *   out            n_queries x top; out_counts[q] = number of valid entries (< top when fewer candidates)
+ * Ties: ScoredPointOffset orders by score only, so which of several equal-score points survives at the
+ * k-th boundary is unspecified in the reference; this library orders by (score desc, id asc). */
+QB_API qb_status qb_search_batch(qb_storage* s, const float* queries, uint32_t n_queries, uint32_t top,
+                          const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids,
+                          const volatile int32_t* is_stopped, qb_scored_point* out, uint32_t* out_counts,
+                          qb_hw_counters* counters /* optional */);
+/* Same scan with queries and outputs already resident in HBM; enqueued on qb_storage_stream(s), no host
+ * synchronisation (bench.py's kernel-only `value`). */
+QB_API qb_status qb_search_batch_device(qb_storage* s, const float* dev_queries, uint32_t n_queries, uint32_t top,
+                                 qb_scored_point* dev_out, uint32_t* dev_counts);
+
+/* Oversampling + rescoring contract (index/vector_index_search_common.rs:27-91): rescore `n` candidate ids of
+ * one query with the ORIGINAL-vector scorer `orig`, sort descending, truncate to `top`. */
+QB_API qb_status qb_rescore(qb_scorer* orig, const uint32_t* ids, size_t n, uint32_t top, qb_scored_point* out, uint32_t* out_count);
+
+/* ---------------------------------------------------------------- sharded segments (multi-GPU) ------- */
+/* Rows of a sharded data set live on several GPUs (one process per GPU); ids reported by searches on this shard
+ * are `local row + id_base`. */
+QB_API qb_status qb_storage_set_id_base(qb_storage* s, uint32_t id_base);
+/* BatchResultAggregator (lib/shard/src/search_result_aggregator.rs:50-117) on the device: merge `n_lists` per-shard
+ * top-k lists per query — as all-gathered over NVLink by the caller: dev_lists[n_lists][n_queries][top],
+ * dev_counts[n_lists][n_queries] — into dev_out[n_queries][top].  dev_scratch >= n_queries*n_lists*top*8 bytes.
+ * Enqueued on `stream` (cudaStream_t), no host synchronisation. */
+QB_API qb_status qb_topk_merge_device(int32_t device, const qb_scored_point* dev_lists, const uint32_t* dev_counts, uint32_t n_lists,
+                                      uint32_t n_queries, uint32_t top, qb_scored_point* dev_out, uint32_t* dev_out_counts,
+                                      void* dev_scratch, uint64_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------- profiling hooks ------------------- */
+/* When enabled, the dominant scan kernel of every search on this storage is bracketed by CUDA events on its
+ * launch stream; qb_profile_read returns the number of bracketed launches and their summed duration. */
+QB_API qb_status qb_profile_enable(qb_storage* s, int32_t on);
+QB_API qb_status qb_profile_read(qb_storage* s, uint64_t* launches, double* total_ms, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QB200_H */

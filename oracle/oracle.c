@@ -960,3 +960,60 @@ API void qo_score_rows_f32(int distance, const float* rows, uint64_t n, uint32_t
 API void qo_preprocess_rows_f32(int distance, const float* in, float* out, uint64_t n, uint32_t dim) {
     for (uint64_t i = 0; i < n; i++) qo_preprocess_f32(distance, in + i * dim, out + i * dim, dim);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * f16-datatype metrics — lib/segment/src/spaces/metric_f16/{avx,sse}/ *.rs, simple_*.rs
+ * (`half` 2.7.1 f16::to_f32 / from_f32 are IEEE-exact conversions; F16C gives the same values)
+ * ---------------------------------------------------------------------------------------- */
+static inline float h2f(uint16_t h) { return _cvtsh_ss(h); }
+
+/* metric_f16/avx/{dot.rs:13-69, euclid.rs:13-70, manhattan.rs:13-75}; kind 0 dot, 1 euclid, 2 manhattan */
+static float f16_avx(int kind, const uint16_t* v1, const uint16_t* v2, size_t n) {
+    const __m256 mask = _mm256_set1_ps(-0.0f);
+    size_t m = n - (n % 32);
+    __m256 s[4] = { _mm256_setzero_ps(), _mm256_setzero_ps(), _mm256_setzero_ps(), _mm256_setzero_ps() };
+    const __m128i* p1 = (const __m128i*)v1; const __m128i* p2 = (const __m128i*)v2;
+    for (size_t i = 0; i < m; i += 32) {
+        for (int a = 0; a < 4; a++) {
+            __m256 x = _mm256_cvtph_ps(_mm_loadu_si128(p1 + a));
+            __m256 y = _mm256_cvtph_ps(_mm_loadu_si128(p2 + a));
+            if (kind == 0) s[a] = _mm256_fmadd_ps(x, y, s[a]);
+            else {
+                __m256 d = _mm256_sub_ps(x, y);
+                if (kind == 1) s[a] = _mm256_fmadd_ps(d, d, s[a]);
+                else s[a] = _mm256_add_ps(_mm256_andnot_ps(mask, d), s[a]);
+            }
+        }
+        p1 += 4; p2 += 4;
+    }
+    const uint16_t* t1 = (const uint16_t*)p1; const uint16_t* t2 = (const uint16_t*)p2;
+    float result = hsum256_ps_avx(s[0]) + hsum256_ps_avx(s[1]) + hsum256_ps_avx(s[2]) + hsum256_ps_avx(s[3]);
+    for (size_t i = 0; i < n - m; i++) {
+        float a = h2f(t1[i]), b = h2f(t2[i]);
+        if (kind == 0) result += a * b;
+        else if (kind == 1) { float d = a - b; result += d * d; }
+        else result += fabsf(a - b);
+    }
+    return kind == 0 ? result : -result;
+}
+API float qo_f16_dot_avx(const uint16_t* a, const uint16_t* b, size_t n) { return f16_avx(0, a, b, n); }
+API float qo_f16_euclid_avx(const uint16_t* a, const uint16_t* b, size_t n) { return f16_avx(1, a, b, n); }
+API float qo_f16_manhattan_avx(const uint16_t* a, const uint16_t* b, size_t n) { return f16_avx(2, a, b, n); }
+
+/* Metric<f16>::similarity dispatch (metric_f16/simple_dot.rs:17-56 etc.): avx+fma+f16c for n >= 32; the SSE tier
+ * converts to f32 and calls the f32 SSE kernels (metric_f16/sse/dot.rs:10-17); scalar tier sums f32 products. */
+API float qo_similarity_f16(int distance, const uint16_t* q, const uint16_t* v, size_t n) {
+    int kind = (distance == QO_EUCLID) ? 1 : (distance == QO_MANHATTAN ? 2 : 0);
+    if (n >= MIN_DIM_SIZE_AVX) return f16_avx(kind, q, v, n);
+    float a[32], b[32];
+    for (size_t i = 0; i < n; i++) { a[i] = h2f(q[i]); b[i] = h2f(v[i]); }
+    if (n >= MIN_DIM_SIZE_SIMD)
+        return kind == 0 ? qo_dot_sse(a, b, n) : (kind == 1 ? qo_euclid_sse(a, b, n) : qo_manhattan_sse(a, b, n));
+    return kind == 0 ? qo_dot_scalar(a, b, n) : (kind == 1 ? qo_euclid_scalar(a, b, n) : qo_manhattan_scalar(a, b, n));
+}
+/* scalar f16 reference (metric_f16/simple_dot.rs:65-73) for the SIMD-vs-scalar tolerance KAT */
+API float qo_f16_dot_scalar(const uint16_t* a, const uint16_t* b, size_t n) {
+    float s = RUST_SUM_INIT;
+    for (size_t i = 0; i < n; i++) s += h2f(a[i]) * h2f(b[i]);
+    return s;
+}

@@ -75,6 +75,11 @@ def lib() -> C.CDLL:
             for tier in ("avx", "scalar"):
                 fn = getattr(L, f"qo_u8_{name}_{tier}")
                 fn.restype, fn.argtypes = C.c_float, [u8p, u8p, C.c_size_t]
+        u16p = C.POINTER(C.c_uint16)
+        for n in ("qo_f16_dot_avx", "qo_f16_euclid_avx", "qo_f16_manhattan_avx", "qo_f16_dot_scalar"):
+            fn = getattr(L, n)
+            fn.restype, fn.argtypes = C.c_float, [u16p, u16p, C.c_size_t]
+        L.qo_similarity_f16.restype, L.qo_similarity_f16.argtypes = C.c_float, [C.c_int, u16p, u16p, C.c_size_t]
         L.qo_sq8_dot_avx.restype, L.qo_sq8_dot_avx.argtypes = C.c_float, [u8p, u8p, C.c_uint32]
         L.qo_sq8_l1_avx.restype, L.qo_sq8_l1_avx.argtypes = C.c_float, [u8p, u8p, C.c_uint32]
         mp = C.POINTER(SQ8Meta)
@@ -187,6 +192,19 @@ def similarity_u8(distance: int, q, v) -> np.float32:
     name = {COSINE: "cosine", EUCLID: "euclid", DOT: "dot", MANHATTAN: "manhattan"}[distance]
     q = _u8(q)
     return raw_u8(name, "avx" if q.size >= 32 else "scalar", q, v)
+
+
+def similarity_f16(distance: int, q, v) -> np.float32:
+    """Metric<f16>::similarity; q, v are numpy float16 arrays (cosine == dot on pre-normalised vectors)."""
+    q = np.ascontiguousarray(q, dtype=np.float16).view(np.uint16)
+    v = np.ascontiguousarray(v, dtype=np.float16).view(np.uint16)
+    return np.float32(lib().qo_similarity_f16(distance, _p(q, C.c_uint16), _p(v, C.c_uint16), q.size))
+
+
+def raw_f16(name: str, a, b) -> np.float32:
+    a = np.ascontiguousarray(a, dtype=np.float16).view(np.uint16)
+    b = np.ascontiguousarray(b, dtype=np.float16).view(np.uint16)
+    return np.float32(getattr(lib(), f"qo_f16_{name}")(_p(a, C.c_uint16), _p(b, C.c_uint16), a.size))
 
 
 def score_rows_f32(distance: int, rows, q_pre) -> np.ndarray:

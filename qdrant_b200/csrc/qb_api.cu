@@ -1,0 +1,908 @@
+// qb_api.cu — the C ABI (include/qb200.h): storages in HBM, RawScorer handles, fused brute-force search.
+//
+// Host-side orchestration only; every arithmetic step runs in the CUDA kernels of qb_dense.cu / qb_quant.cu /
+// qb_topk.cu.  There is no CPU scoring path anywhere in this library.
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "qb_internal.h"
+
+// kernels' host entry points (qb_dense.cu / qb_quant.cu / qb_dtype.cu)
+qb_status qb_dense_f32_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
+qb_status qb_dense_f32_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
+qb_status qb_dense_x_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
+qb_status qb_dense_x_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
+qb_status qb_dense_x_convert_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, void* d_out, cudaStream_t stream);
+qb_status qb_sq8_repack(const qb_storage* s, const uint8_t* d_rows_in, uint32_t row_bytes, uint64_t first, uint64_t n, cudaStream_t stream);
+qb_status qb_sq8_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, uint8_t* d_codes, float* d_q_off, cudaStream_t stream);
+qb_status qb_sq8_internal_query(const qb_storage* s, uint32_t id, uint8_t* d_code, float* d_q_off, cudaStream_t stream);
+qb_status qb_sq8_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
+qb_status qb_sq8_score_points(const qb_storage* s, const void* d_q_enc, const float* d_q_off, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
+qb_status qb_pq_build_luts(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, float* d_luts, cudaStream_t stream);
+qb_status qb_pq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
+qb_status qb_pq_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
+qb_status qb_pq_score_internal(const qb_storage* s, uint32_t a, uint32_t b, float* d_out, cudaStream_t stream);
+qb_status qb_bq_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, int force_binary, void* d_out, cudaStream_t stream);
+qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
+qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+std::atomic<uint64_t> g_qb_launches{0};
+
+void qb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* qb_last_error(void) { return g_err; }
+extern "C" int32_t qb_abi_version(void) { return QB200_ABI_VERSION; }
+extern "C" uint64_t qb_kernel_launch_count(void) { return g_qb_launches.load(); }
+
+extern "C" qb_status qb_device_count(int32_t* out) {
+    QB_CHECK(out, QB_ERR_INVALID, "qb_device_count: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        *out = 0;
+        qb_set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+        cudaGetLastError();
+        return QB_ERR_NO_DEVICE;
+    }
+    *out = n;
+    return QB_OK;
+}
+
+static qb_status use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        qb_set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+        cudaGetLastError();
+        return QB_ERR_NO_DEVICE;
+    }
+    QB_CHECK(device >= 0 && device < n, QB_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    QB_CUDA(cudaSetDevice(device));
+    return QB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ buffers
+qb_status qb_ensure_device(void** p, size_t* have, size_t need_bytes) {
+    if (*have >= need_bytes && *p) return QB_OK;
+    if (*p) { QB_CUDA(cudaFree(*p)); *p = nullptr; *have = 0; }
+    size_t sz = std::max<size_t>(need_bytes, 256);
+    QB_CUDA(cudaMalloc(p, sz));
+    *have = sz;
+    return QB_OK;
+}
+qb_status qb_ensure_pinned(void** p, size_t* have, size_t need_bytes) {
+    if (*have >= need_bytes && *p) return QB_OK;
+    if (*p) { QB_CUDA(cudaFreeHost(*p)); *p = nullptr; *have = 0; }
+    size_t sz = std::max<size_t>(need_bytes, 4096);
+    QB_CUDA(cudaMallocHost(p, sz));
+    *have = sz;
+    return QB_OK;
+}
+template <typename T>
+static qb_status ensure_dev_elems(T** p, size_t* have_elems, size_t need_elems) {
+    size_t have_b = *have_elems * sizeof(T);
+    void* vp = *p;
+    QB_TRY(qb_ensure_device(&vp, &have_b, need_elems * sizeof(T)));
+    *p = reinterpret_cast<T*>(vp);
+    *have_elems = have_b / sizeof(T);
+    return QB_OK;
+}
+
+qb_status qb_ctx_acquire(qb_storage* s, QbSearchCtx** out) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (QbSearchCtx* c : s->ctxs)
+        if (!c->in_use) { c->in_use = true; *out = c; return QB_OK; }
+    QbSearchCtx* c = new QbSearchCtx();
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; qb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return QB_ERR_CUDA; }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    c->in_use = true;
+    s->ctxs.push_back(c);
+    *out = c;
+    return QB_OK;
+}
+void qb_ctx_release(qb_storage* s, QbSearchCtx* c) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    c->in_use = false;
+}
+static void ctx_destroy(QbSearchCtx* c) {
+    if (!c) return;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_queries_raw); cudaFree(c->d_queries_enc); cudaFree(c->d_q_off); cudaFree(c->d_thr); cudaFree(c->d_cnt);
+    cudaFree(c->d_cand); cudaFree(c->d_out); cudaFree(c->d_out_counts); cudaFree(c->d_deleted2); cudaFree(c->d_ids);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------ storages
+static qb_storage* new_storage(int device, QbKind kind, uint32_t dim, uint64_t count) {
+    qb_storage* s = new qb_storage();
+    s->device = device; s->kind = kind; s->dim = dim; s->count = count;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    return s;
+}
+
+static uint32_t elem_size_of(qb_dtype dt) { return dt == QB_DT_F32 ? 4 : (dt == QB_DT_F16 ? 2 : 1); }
+
+extern "C" qb_status qb_storage_create_dense(int32_t device, qb_dtype dt, qb_distance distance, uint32_t dim, uint64_t count,
+                                             const void* host_rows, uint64_t row_stride_bytes, qb_storage** out) {
+    QB_CHECK(out, QB_ERR_INVALID, "create_dense: null out");
+    *out = nullptr;
+    QB_CHECK(dim >= 1 && dim <= 65536, QB_ERR_INVALID, "create_dense: dim %u outside [1,65536]", dim);
+    QB_CHECK((int)dt >= 0 && (int)dt <= 2, QB_ERR_INVALID, "create_dense: bad dtype %d", (int)dt);
+    QB_CHECK((int)distance >= 0 && (int)distance <= 3, QB_ERR_INVALID, "create_dense: bad distance %d", (int)distance);
+    QB_CHECK(count <= 0xFFFFFFFFull, QB_ERR_INVALID, "create_dense: count exceeds PointOffsetType (u32)");
+    QB_TRY(use_device(device));
+    qb_storage* s = new_storage(device, QB_KIND_DENSE, dim, count);
+    s->dtype = dt; s->distance = distance; s->elem_size = elem_size_of(dt);
+    s->row_stride = (uint32_t)round_up_u64((uint64_t)dim * s->elem_size, 16);
+    const size_t bytes = std::max<size_t>((size_t)count * s->row_stride, 256);
+    cudaError_t e = cudaMalloc(&s->d_rows, bytes);
+    if (e != cudaSuccess) { delete s; qb_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return QB_ERR_OOM; }
+    s->hbm_bytes = bytes;
+    if (s->row_stride != dim * s->elem_size) cudaMemset(s->d_rows, 0, bytes);
+    *out = s;
+    if (host_rows && count) {
+        qb_status st = qb_storage_write_rows(s, 0, count, host_rows, row_stride_bytes);
+        if (st != QB_OK) { qb_storage_destroy(s); *out = nullptr; return st; }
+    }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_storage_write_rows(qb_storage* s, uint64_t first_row, uint64_t n_rows, const void* host_rows, uint64_t row_stride_bytes) {
+    QB_CHECK(s && host_rows, QB_ERR_INVALID, "write_rows: null argument");
+    QB_CHECK(s->kind == QB_KIND_DENSE, QB_ERR_UNSUPPORTED, "write_rows: dense storages only");
+    QB_CHECK(first_row + n_rows <= s->count, QB_ERR_INVALID, "write_rows: range beyond count");
+    const size_t rb = (size_t)s->dim * s->elem_size;
+    if (row_stride_bytes == 0) row_stride_bytes = rb;
+    QB_CHECK(row_stride_bytes >= rb, QB_ERR_INVALID, "write_rows: stride smaller than a row");
+    QB_TRY(use_device(s->device));
+    QB_CUDA(cudaMemcpy2D(reinterpret_cast<uint8_t*>(s->d_rows) + first_row * s->row_stride, s->row_stride, host_rows, row_stride_bytes, rb, n_rows,
+                         cudaMemcpyHostToDevice));
+    return QB_OK;
+}
+
+extern "C" qb_status qb_storage_write_rows_device(qb_storage* s, uint64_t first_row, uint64_t n_rows, const void* dev_rows, uint64_t row_stride_bytes) {
+    QB_CHECK(s && dev_rows, QB_ERR_INVALID, "write_rows_device: null argument");
+    QB_CHECK(s->kind == QB_KIND_DENSE, QB_ERR_UNSUPPORTED, "write_rows_device: dense storages only");
+    QB_CHECK(first_row + n_rows <= s->count, QB_ERR_INVALID, "write_rows_device: range beyond count");
+    const size_t rb = (size_t)s->dim * s->elem_size;
+    if (row_stride_bytes == 0) row_stride_bytes = rb;
+    QB_TRY(use_device(s->device));
+    QB_CUDA(cudaMemcpy2D(reinterpret_cast<uint8_t*>(s->d_rows) + first_row * s->row_stride, s->row_stride, dev_rows, row_stride_bytes, rb, n_rows,
+                         cudaMemcpyDeviceToDevice));
+    return QB_OK;
+}
+
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ rows, uint32_t stride, uint32_t row_bytes, const uint32_t* __restrict__ ids, uint64_t n,
+                                   uint8_t* __restrict__ out) {
+    for (uint64_t r = blockIdx.x; r < n; r += gridDim.x) {
+        const uint8_t* src = rows + (size_t)ids[r] * stride;
+        uint8_t* dst = out + r * row_bytes;
+        for (uint32_t i = threadIdx.x; i < row_bytes; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+extern "C" qb_status qb_storage_read_rows(const qb_storage* s, const uint32_t* ids, uint64_t n, void* host_out) {
+    QB_CHECK(s && ids && host_out, QB_ERR_INVALID, "read_rows: null argument");
+    QB_CHECK(s->kind == QB_KIND_DENSE, QB_ERR_UNSUPPORTED, "read_rows: dense storages only");
+    if (n == 0) return QB_OK;
+    for (uint64_t i = 0; i < n; ++i) QB_CHECK(ids[i] < s->count, QB_ERR_INVALID, "read_rows: id %u out of range", ids[i]);
+    QB_TRY(use_device(s->device));
+    const uint32_t rb = s->dim * s->elem_size;
+    uint32_t* d_ids = nullptr; uint8_t* d_out = nullptr;
+    QB_CUDA(cudaMalloc(&d_ids, n * 4));
+    cudaError_t e = cudaMalloc(&d_out, n * rb);
+    if (e != cudaSuccess) { cudaFree(d_ids); qb_set_error("read_rows: cudaMalloc: %s", cudaGetErrorString(e)); return QB_ERR_OOM; }
+    cudaMemcpy(d_ids, ids, n * 4, cudaMemcpyHostToDevice);
+    gather_rows_kernel<<<(unsigned)std::min<uint64_t>(n, 4096), 128>>>(reinterpret_cast<const uint8_t*>(s->d_rows), s->row_stride, rb, d_ids, n, d_out);
+    QB_LAUNCHED();
+    e = cudaMemcpy(host_out, d_out, n * rb, cudaMemcpyDeviceToHost);
+    cudaFree(d_ids); cudaFree(d_out);
+    if (e != cudaSuccess) { qb_set_error("read_rows: %s", cudaGetErrorString(e)); return QB_ERR_CUDA; }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_storage_create_sq8(int32_t device, uint32_t dim, uint64_t count, const uint8_t* rows, uint32_t row_bytes, float alpha,
+                                           float offset, float multiplier, qb_qdistance dt, int32_t invert, qb_distance metric, qb_storage** out) {
+    QB_CHECK(out, QB_ERR_INVALID, "create_sq8: null out");
+    *out = nullptr;
+    QB_CHECK(dim >= 1 && dim <= 65536, QB_ERR_INVALID, "create_sq8: dim %u outside [1,65536]", dim);
+    const uint32_t ad = dim + (16 - dim % 16) % 16;  // get_actual_dim, encoded_vectors_u8.rs:622-624
+    QB_CHECK(row_bytes == ad + 4, QB_ERR_INVALID, "create_sq8: row_bytes %u != 4 + actual_dim %u (load validation, encoded_vectors_u8.rs:328)", row_bytes, ad);
+    QB_CHECK(count == 0 || rows, QB_ERR_INVALID, "create_sq8: null rows");
+    QB_CHECK(count <= 0xFFFFFFFFull, QB_ERR_INVALID, "create_sq8: count exceeds u32");
+    QB_TRY(use_device(device));
+    qb_storage* s = new_storage(device, QB_KIND_SQ8, dim, count);
+    s->actual_dim = ad; s->alpha = alpha; s->offset = offset; s->multiplier = multiplier; s->qdist = dt; s->invert = invert ? 1 : 0;
+    s->distance = metric;
+    const size_t cb = std::max<size_t>((size_t)count * ad, 256), ob = std::max<size_t>((size_t)count * 4, 256);
+    if (cudaMalloc(&s->d_codes, cb) != cudaSuccess || cudaMalloc(&s->d_voff, ob) != cudaSuccess) {
+        qb_set_error("create_sq8: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        qb_storage_destroy(s);
+        return QB_ERR_OOM;
+    }
+    s->hbm_bytes = cb + ob;
+    // upload in chunks through a device staging buffer, repacking 772-B rows into a 768-B code plane + f32 plane
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / row_bytes);
+    uint8_t* d_stage = nullptr;
+    if (count) {
+        if (cudaMalloc(&d_stage, std::min<uint64_t>(chunk_rows, count) * row_bytes) != cudaSuccess) {
+            qb_set_error("create_sq8: staging cudaMalloc failed"); qb_storage_destroy(s); return QB_ERR_OOM;
+        }
+        for (uint64_t r = 0; r < count; r += chunk_rows) {
+            const uint64_t n = std::min<uint64_t>(chunk_rows, count - r);
+            cudaError_t e = cudaMemcpy(d_stage, rows + r * row_bytes, n * row_bytes, cudaMemcpyHostToDevice);
+            qb_status st = (e == cudaSuccess) ? qb_sq8_repack(s, d_stage, row_bytes, r, n, 0) : QB_ERR_CUDA;
+            if (st == QB_OK && cudaDeviceSynchronize() != cudaSuccess) st = QB_ERR_CUDA;
+            if (st != QB_OK) { qb_set_error("create_sq8: upload failed: %s", cudaGetErrorString(cudaGetLastError())); cudaFree(d_stage); qb_storage_destroy(s); return st; }
+        }
+        cudaFree(d_stage);
+    }
+    *out = s;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_storage_create_pq(int32_t device, uint32_t dim, uint32_t m, const uint32_t* div_start_end, const float* centroids,
+                                          uint32_t n_centroids, const uint8_t* codes, uint64_t count, qb_qdistance dt, int32_t invert,
+                                          qb_distance metric, qb_storage** out) {
+    QB_CHECK(out, QB_ERR_INVALID, "create_pq: null out");
+    *out = nullptr;
+    QB_CHECK(dim >= 1 && m >= 1 && div_start_end && centroids, QB_ERR_INVALID, "create_pq: bad arguments");
+    QB_CHECK(n_centroids >= 1 && n_centroids <= 256, QB_ERR_INVALID, "create_pq: n_centroids %u outside [1,256]", n_centroids);
+    QB_CHECK(count == 0 || codes, QB_ERR_INVALID, "create_pq: null codes");
+    QB_CHECK(count <= 0xFFFFFFFFull, QB_ERR_INVALID, "create_pq: count exceeds u32");
+    for (uint32_t j = 0; j < m; ++j)
+        QB_CHECK(div_start_end[2 * j] < div_start_end[2 * j + 1] && div_start_end[2 * j + 1] <= dim, QB_ERR_INVALID, "create_pq: bad division %u", j);
+    QB_TRY(use_device(device));
+    qb_storage* s = new_storage(device, QB_KIND_PQ, dim, count);
+    s->pq_m = m; s->pq_stride = (uint32_t)round_up_u64(m, 16); s->n_centroids = n_centroids; s->qdist = dt; s->invert = invert ? 1 : 0;
+    s->distance = metric;
+    s->pq_div.assign(div_start_end, div_start_end + 2 * m);
+    const size_t cb = std::max<size_t>((size_t)count * s->pq_stride, 256);
+    bool ok = cudaMalloc(&s->d_pq_codes, cb) == cudaSuccess && cudaMalloc(&s->d_centroids, (size_t)n_centroids * dim * 4) == cudaSuccess &&
+              cudaMalloc(&s->d_pq_div, (size_t)2 * m * 4) == cudaSuccess;
+    if (!ok) { qb_set_error("create_pq: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); qb_storage_destroy(s); return QB_ERR_OOM; }
+    s->hbm_bytes = cb + (size_t)n_centroids * dim * 4;
+    cudaMemset(s->d_pq_codes, 0, cb);
+    cudaError_t e = cudaMemcpy(s->d_centroids, centroids, (size_t)n_centroids * dim * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_pq_div, div_start_end, (size_t)2 * m * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && count) e = cudaMemcpy2D(s->d_pq_codes, s->pq_stride, codes, m, m, count, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { qb_set_error("create_pq: upload: %s", cudaGetErrorString(e)); qb_storage_destroy(s); return QB_ERR_CUDA; }
+    *out = s;
+    return QB_OK;
+}
+
+static uint32_t bq_row_bytes_for(uint32_t dim, qb_bq_encoding enc) {  // get_quantized_vector_size_from_params :829-839
+    uint64_t ext = dim;
+    if (enc == QB_BQ_TWO_BITS) ext = (uint64_t)dim * 2;
+    else if (enc == QB_BQ_ONE_AND_HALF_BITS) ext = ((uint64_t)dim * 3 + 1) / 2;
+    if (ext < 1) ext = 1;
+    return (uint32_t)(((ext + 127) / 128) * 16);
+}
+
+extern "C" qb_status qb_storage_create_bq(int32_t device, uint32_t dim, qb_bq_encoding enc, qb_bq_query_encoding qenc, const uint8_t* rows,
+                                          uint32_t row_bytes, uint64_t count, qb_qdistance dt, int32_t invert, const float* mean_std,
+                                          qb_distance metric, qb_storage** out) {
+    QB_CHECK(out, QB_ERR_INVALID, "create_bq: null out");
+    *out = nullptr;
+    QB_CHECK(dim >= 1 && dim <= 65536, QB_ERR_INVALID, "create_bq: dim %u outside [1,65536]", dim);
+    QB_CHECK(row_bytes == bq_row_bytes_for(dim, enc), QB_ERR_INVALID, "create_bq: row_bytes %u != expected %u", row_bytes, bq_row_bytes_for(dim, enc));
+    QB_CHECK(count == 0 || rows, QB_ERR_INVALID, "create_bq: null rows");
+    QB_CHECK(count <= 0xFFFFFFFFull, QB_ERR_INVALID, "create_bq: count exceeds u32");
+    QB_TRY(use_device(device));
+    qb_storage* s = new_storage(device, QB_KIND_BQ, dim, count);
+    s->bq_enc = enc; s->bq_qenc = qenc; s->bq_row_bytes = row_bytes; s->qdist = dt; s->invert = invert ? 1 : 0; s->distance = metric;
+    const size_t rb = std::max<size_t>((size_t)count * row_bytes, 256);
+    bool ok = cudaMalloc(&s->d_bq_rows, rb) == cudaSuccess;
+    if (ok && mean_std) ok = cudaMalloc(&s->d_mean_std, (size_t)dim * 8) == cudaSuccess;
+    if (!ok) { qb_set_error("create_bq: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); qb_storage_destroy(s); return QB_ERR_OOM; }
+    s->hbm_bytes = rb;
+    cudaError_t e = count ? cudaMemcpy(s->d_bq_rows, rows, (size_t)count * row_bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    if (e == cudaSuccess && mean_std) e = cudaMemcpy(s->d_mean_std, mean_std, (size_t)dim * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { qb_set_error("create_bq: upload: %s", cudaGetErrorString(e)); qb_storage_destroy(s); return QB_ERR_CUDA; }
+    *out = s;
+    return QB_OK;
+}
+
+extern "C" void qb_storage_destroy(qb_storage* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (QbSearchCtx* c : s->ctxs) ctx_destroy(c);
+    for (auto& pr : s->prof_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    cudaFree(s->d_rows); cudaFree(s->d_codes); cudaFree(s->d_voff); cudaFree(s->d_pq_div); cudaFree(s->d_centroids); cudaFree(s->d_pq_codes);
+    cudaFree(s->d_bq_rows); cudaFree(s->d_mean_std); cudaFree(s->d_deleted);
+    cudaGetLastError();
+    delete s;
+}
+
+extern "C" qb_status qb_storage_info(const qb_storage* s, uint32_t* dim, uint64_t* count, uint64_t* hbm_bytes) {
+    QB_CHECK(s, QB_ERR_INVALID, "storage_info: null storage");
+    if (dim) *dim = s->dim;
+    if (count) *count = s->count;
+    if (hbm_bytes) *hbm_bytes = s->hbm_bytes;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_storage_set_deleted(qb_storage* s, const uint64_t* bitmap_words, uint64_t n_words) {
+    QB_CHECK(s, QB_ERR_INVALID, "set_deleted: null storage");
+    QB_TRY(use_device(s->device));
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!bitmap_words) { if (s->d_deleted) { cudaDeviceSynchronize(); cudaFree(s->d_deleted); s->d_deleted = nullptr; } return QB_OK; }
+    const uint64_t need = ceil_div_u64(s->count, 64);
+    QB_CHECK(n_words >= need, QB_ERR_INVALID, "set_deleted: bitmap has %llu words, need %llu", (unsigned long long)n_words, (unsigned long long)need);
+    if (!s->d_deleted) QB_CUDA(cudaMalloc(&s->d_deleted, std::max<uint64_t>(need, 1) * 8));
+    QB_CUDA(cudaMemcpy(s->d_deleted, bitmap_words, need * 8, cudaMemcpyHostToDevice));
+    return QB_OK;
+}
+
+extern "C" void* qb_storage_stream(qb_storage* s) {
+    if (!s) return nullptr;
+    if (cudaSetDevice(s->device) != cudaSuccess) return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->ctxs.empty()) return s->ctxs[0]->stream;
+    }
+    QbSearchCtx* c = nullptr;
+    if (qb_ctx_acquire(s, &c) != QB_OK) return nullptr;
+    qb_ctx_release(s, c);
+    return c->stream;
+}
+
+// ------------------------------------------------------------------------------------------------ Metric::preprocess
+extern "C" qb_status qb_metric_preprocess(int32_t device, qb_distance distance, uint32_t dim, uint64_t n, const float* in, float* out) {
+    QB_CHECK(in && out && dim >= 1, QB_ERR_INVALID, "metric_preprocess: bad arguments");
+    QB_TRY(use_device(device));
+    if (n == 0) return QB_OK;
+    float* d = nullptr;
+    QB_CUDA(cudaMalloc(&d, n * dim * 4));
+    cudaError_t e = cudaMemcpy(d, in, n * dim * 4, cudaMemcpyHostToDevice);
+    qb_status st = (e == cudaSuccess) ? qb_launch_preprocess_rows(distance, dim, n, d, dim, d, dim, 0) : QB_ERR_CUDA;
+    if (st == QB_OK) e = cudaMemcpy(out, d, n * dim * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (st != QB_OK || e != cudaSuccess) { qb_set_error("metric_preprocess: %s", cudaGetErrorString(e)); return st != QB_OK ? st : QB_ERR_CUDA; }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_metric_preprocess_device(int32_t device, qb_distance distance, uint32_t dim, uint64_t n, float* dev_rows, uint64_t row_stride_bytes) {
+    QB_CHECK(dev_rows && dim >= 1, QB_ERR_INVALID, "metric_preprocess_device: bad arguments");
+    QB_TRY(use_device(device));
+    if (row_stride_bytes == 0) row_stride_bytes = (uint64_t)dim * 4;
+    QB_CHECK(row_stride_bytes % 4 == 0, QB_ERR_INVALID, "metric_preprocess_device: stride must be a multiple of 4");
+    QB_TRY(qb_launch_preprocess_rows(distance, dim, n, dev_rows, row_stride_bytes / 4, dev_rows, row_stride_bytes / 4, 0));
+    QB_CUDA(cudaStreamSynchronize(0));
+    return QB_OK;
+}
+
+extern "C" float qb_metric_postprocess(qb_distance distance, float score) {
+    // MetricPostProcessing::postprocess, spaces/simple.rs:74-78,118-122 (host arithmetic on one scalar per result)
+    if (distance == QB_DIST_EUCLID) return sqrtf(fabsf(score));
+    if (distance == QB_DIST_MANHATTAN) return fabsf(score);
+    return score;
+}
+
+// ------------------------------------------------------------------------------------------------ queries
+size_t qb_encoded_query_bytes(const qb_storage* s) {
+    switch (s->kind) {
+        case QB_KIND_DENSE: return s->row_stride;
+        case QB_KIND_SQ8: return s->actual_dim;
+        case QB_KIND_PQ: return (size_t)s->pq_m * s->n_centroids * 4;
+        default: return (size_t)s->bq_row_bytes * (s->bq_qenc == QB_BQQ_SCALAR4 ? 4 : (s->bq_qenc == QB_BQQ_SCALAR8 ? 8 : 1));
+    }
+}
+
+// f32 stride (floats) of the preprocessed-query staging rows
+static uint32_t pre_stride_f(const qb_storage* s) { return (uint32_t)round_up_u64(s->dim, 4); }
+
+// Metric::preprocess then (for quantized storages) EncodedVectors::encode_query, all on the device.
+// d_pre: scratch of nq * pre_stride_f floats (ignored for dense f32 where the output IS the preprocessed query)
+static qb_status prepare_queries(const qb_storage* s, const float* d_q_raw, uint32_t nq, float* d_pre, void* d_q_enc, float* d_q_off, cudaStream_t stream) {
+    if (nq == 0) return QB_OK;
+    if (s->kind == QB_KIND_DENSE && s->dtype == QB_DT_F32) {
+        return qb_launch_preprocess_rows(s->distance, s->dim, nq, d_q_raw, s->dim, reinterpret_cast<float*>(d_q_enc), s->row_stride / 4, stream);
+    }
+    const uint32_t ps = pre_stride_f(s);
+    // u8 / f16 storages: only CosineMetric<f32>-style preprocess applies to f32/f16 (metric_f16/simple_cosine.rs); u8 cosine has none
+    qb_distance pre_dist = s->distance;
+    if (s->kind == QB_KIND_DENSE && s->dtype == QB_DT_U8) pre_dist = QB_DIST_DOT;
+    QB_TRY(qb_launch_preprocess_rows(pre_dist, s->dim, nq, d_q_raw, s->dim, d_pre, ps, stream));
+    switch (s->kind) {
+        case QB_KIND_DENSE: return qb_dense_x_convert_queries(s, d_pre, ps, nq, d_q_enc, stream);
+        case QB_KIND_SQ8: return qb_sq8_encode_queries(s, d_pre, ps, nq, reinterpret_cast<uint8_t*>(d_q_enc), d_q_off, stream);
+        case QB_KIND_PQ: return qb_pq_build_luts(s, d_pre, ps, nq, reinterpret_cast<float*>(d_q_enc), stream);
+        default: return qb_bq_encode_queries(s, d_pre, ps, nq, 0, d_q_enc, stream);
+    }
+}
+
+qb_status qb_launch_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream) {
+    switch (s->kind) {
+        case QB_KIND_DENSE: return s->dtype == QB_DT_F32 ? qb_dense_f32_scan(s, a, stream) : qb_dense_x_scan(s, a, stream);
+        case QB_KIND_SQ8: return qb_sq8_scan(s, a, stream);
+        case QB_KIND_PQ: return qb_pq_scan(s, a, stream);
+        default: return qb_bq_scan(s, a, stream);
+    }
+}
+
+qb_status qb_launch_score_points(const qb_storage* s, const void* d_q_enc, const float* d_q_off, const uint32_t* d_ids, uint64_t n, float* d_scores,
+                                 cudaStream_t stream) {
+    switch (s->kind) {
+        case QB_KIND_DENSE:
+            return s->dtype == QB_DT_F32 ? qb_dense_f32_score_points(s, d_q_enc, d_ids, n, d_scores, stream)
+                                         : qb_dense_x_score_points(s, d_q_enc, d_ids, n, d_scores, stream);
+        case QB_KIND_SQ8: return qb_sq8_score_points(s, d_q_enc, d_q_off, d_ids, n, d_scores, stream);
+        case QB_KIND_PQ: return qb_pq_score_points(s, d_q_enc, d_ids, n, d_scores, stream);
+        default: return QB_ERR_INVALID;  // BQ goes through the scorer (needs bits)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ search
+struct SearchPlan {
+    uint64_t n_cand;       // candidates per query (rows or listed ids)
+    bool direct;           // one dense pass + select
+    uint64_t sample;       // sample prefix length (two-pass)
+    uint64_t cap;          // per-query candidate capacity of the filter pass
+    uint32_t q_chunk;      // queries per pass
+};
+
+static SearchPlan make_plan(uint64_t n_cand, uint32_t nq, uint32_t top, bool force_direct) {
+    SearchPlan p{};
+    p.n_cand = n_cand;
+    const uint64_t kDirectRows = 65536;
+    const uint64_t kCandBudgetBytes = 2ull << 30;  // candidate buffer budget per pass
+    if (force_direct || n_cand <= kDirectRows) {
+        p.direct = true;
+        p.cap = std::max<uint64_t>(n_cand, 1);
+    } else {
+        p.direct = false;
+        // minimise sample + expected survivors (N*k/S): S ~ sqrt(N*k); x2 keeps the survivor list short
+        uint64_t sgoal = (uint64_t)(2.0 * sqrt((double)n_cand * (double)top));
+        sgoal = round_up_u64(std::max<uint64_t>(sgoal, 8192), 1024);
+        p.sample = std::min<uint64_t>(sgoal, n_cand / 2);
+        const uint64_t expect = (uint64_t)((double)n_cand * (double)top / (double)p.sample);
+        p.cap = std::max<uint64_t>(p.sample, 8 * expect + 4096);
+        p.cap = std::min<uint64_t>(p.cap, n_cand);
+    }
+    uint64_t qc = kCandBudgetBytes / (p.cap * 8);
+    if (qc < 1) qc = 1;
+    p.q_chunk = (uint32_t)std::min<uint64_t>(qc, nq);
+    return p;
+}
+
+static void profile_begin(qb_storage* s, QbSearchCtx* c, cudaStream_t stream, cudaEvent_t* e0, cudaEvent_t* e1) {
+    *e0 = *e1 = nullptr;
+    if (!s->profile) return;
+    cudaEventCreate(e0);
+    cudaEventCreate(e1);
+    cudaEventRecord(*e0, stream);
+}
+static void profile_end(qb_storage* s, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
+    if (!e0) return;
+    cudaEventRecord(e1, stream);
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->prof_pending.emplace_back(e0, e1);
+}
+
+// Core of the fused scan: queries already encoded in c->d_queries_enc (+ c->d_q_off).  Results to d_out/d_counts
+// (device).  Sets *overflow_possible when the filter pass is used (caller checks c->d_cnt overflow flag at [nq]).
+static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t top, const uint32_t* d_ids, uint64_t n_ids, const uint32_t* d_deleted2,
+                            const volatile int32_t* is_stopped, bool force_direct, qb_scored_point* d_out, uint32_t* d_counts, unsigned int* d_overflow) {
+    const uint64_t n_cand = d_ids ? n_ids : s->count;
+    cudaStream_t stream = c->stream;
+    if (n_cand == 0) { QB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, stream)); return QB_OK; }
+    const SearchPlan plan = make_plan(n_cand, nq, top, force_direct);
+    QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)plan.q_chunk * plan.cap));
+    QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)nq));
+    QB_TRY(ensure_dev_elems(&c->d_cnt, &c->cnt_elems, (size_t)nq + 1));
+    const size_t enc_bytes = qb_encoded_query_bytes(s);
+
+    for (uint32_t q0 = 0; q0 < nq; q0 += plan.q_chunk) {
+        if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+        const uint32_t qn = std::min<uint32_t>(plan.q_chunk, nq - q0);
+        QbScanArgs a{};
+        a.d_q_enc = reinterpret_cast<const uint8_t*>(c->d_queries_enc) + (size_t)q0 * enc_bytes;
+        a.d_q_off = c->d_q_off ? c->d_q_off + q0 : nullptr;
+        a.nq = qn;
+        a.d_ids = d_ids;
+        a.emit.deleted = s->d_deleted;
+        a.emit.deleted2 = d_deleted2;
+        a.emit.id_base = s->id_base;
+        a.emit.cand = c->d_cand;
+        a.emit.cap = plan.cap;
+        cudaEvent_t e0, e1;
+        if (plan.direct) {
+            a.row_begin = 0; a.row_end = n_cand;
+            a.emit.dense = 1; a.emit.dense_base = 0;
+            profile_begin(s, c, stream, &e0, &e1);
+            QB_TRY(qb_launch_scan(s, a, stream));
+            profile_end(s, stream, e0, e1);
+            QB_TRY(qb_launch_select(c->d_cand, nullptr, plan.cap, n_cand, qn, top, 0, d_out + (size_t)q0 * top, d_counts + q0, nullptr, nullptr, stream));
+        } else {
+            // pass 1: sample prefix, materialised densely -> per-query threshold = k-th best of the sample
+            a.row_begin = 0; a.row_end = plan.sample;
+            a.emit.dense = 1; a.emit.dense_base = 0;
+            QB_TRY(qb_launch_scan(s, a, stream));
+            QB_TRY(qb_launch_select(c->d_cand, nullptr, plan.cap, plan.sample, qn, top, 1, nullptr, nullptr, c->d_thr + q0, nullptr, stream));
+            // pass 2: everything, keeping only score >= threshold
+            QB_CUDA(cudaMemsetAsync(c->d_cnt + q0, 0, (size_t)qn * 4, stream));
+            a.row_begin = 0; a.row_end = n_cand;
+            a.emit.dense = 0; a.emit.thr = c->d_thr + q0; a.emit.cnt = c->d_cnt + q0;
+            if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+            profile_begin(s, c, stream, &e0, &e1);
+            QB_TRY(qb_launch_scan(s, a, stream));
+            profile_end(s, stream, e0, e1);
+            QB_TRY(qb_launch_select(c->d_cand, c->d_cnt + q0, plan.cap, 0, qn, top, 0, d_out + (size_t)q0 * top, d_counts + q0, nullptr, d_overflow, stream));
+        }
+    }
+    return QB_OK;
+}
+
+static uint64_t cpu_units_per_point(const qb_storage* s) {
+    switch (s->kind) {
+        case QB_KIND_DENSE: return (uint64_t)s->dim * s->elem_size;  // set_cpu_multiplier(dim * size_of::<TElement>()), metric_query_scorer.rs:43
+        case QB_KIND_SQ8: return s->dim;                             // encoded_vectors_u8.rs:785-787
+        case QB_KIND_PQ: return s->pq_m;                             // encoded_vectors_pq.rs:693-695
+        default: return s->bq_row_bytes;                             // encoded_vectors_binary.rs:999
+    }
+}
+
+extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32_t n_queries, uint32_t top, const uint64_t* deleted_bitmap,
+                                     const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped, qb_scored_point* out,
+                                     uint32_t* out_counts, qb_hw_counters* counters) {
+    QB_CHECK(s && out && out_counts, QB_ERR_INVALID, "search_batch: null argument");
+    QB_CHECK(n_queries == 0 || queries, QB_ERR_INVALID, "search_batch: null queries");
+    QB_CHECK(top >= 1, QB_ERR_INVALID, "search_batch: top must be >= 1 (FixedLengthPriorityQueue::new panics on 0)");
+    QB_CHECK(top <= QB_MAX_TOP, QB_ERR_UNSUPPORTED, "search_batch: top %u > %u not supported by the fused selection", top, QB_MAX_TOP);
+    if (n_queries == 0) return QB_OK;
+    if (id_list) for (uint64_t i = 0; i < n_ids; ++i) QB_CHECK(id_list[i] < s->count, QB_ERR_INVALID, "search_batch: id %u out of range", id_list[i]);
+    if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+    QB_TRY(use_device(s->device));
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_acquire(s, &c));
+    struct Rel { qb_storage* s; QbSearchCtx* c; ~Rel() { qb_ctx_release(s, c); } } rel{s, c};
+    cudaStream_t stream = c->stream;
+
+    const size_t raw_bytes = (size_t)n_queries * s->dim * 4;
+    const size_t res_bytes = (size_t)n_queries * top * sizeof(qb_scored_point);
+    const size_t cnt_bytes = (size_t)n_queries * 4;
+    // pinned staging: [queries | results | counts | overflow flag]
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + cnt_bytes + 16));
+    uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
+    memcpy(hs, queries, raw_bytes);
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, raw_bytes + (size_t)n_queries * pre_stride_f(s) * 4));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, (size_t)n_queries * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
+    QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)n_queries * top));
+    QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)n_queries + 4));
+    QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
+    float* d_pre = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + raw_bytes);
+    QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), n_queries, d_pre, c->d_queries_enc, c->d_q_off, stream));
+
+    const uint32_t* d_del2 = nullptr;
+    if (deleted_bitmap) {
+        const uint64_t words64 = ceil_div_u64(s->count, 64);
+        QB_TRY(ensure_dev_elems(&c->d_deleted2, &c->deleted2_words, (size_t)words64 * 2));
+        QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_bitmap, words64 * 8, cudaMemcpyHostToDevice, stream));
+        d_del2 = c->d_deleted2;
+    }
+    const uint32_t* d_ids = nullptr;
+    if (id_list) {
+        QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)std::max<uint64_t>(n_ids, 1)));
+        QB_CUDA(cudaMemcpyAsync(c->d_ids, id_list, n_ids * 4, cudaMemcpyHostToDevice, stream));
+        d_ids = c->d_ids;
+    }
+    unsigned int* d_overflow = reinterpret_cast<unsigned int*>(c->d_out_counts + n_queries);
+    QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
+    QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, false, c->d_out, c->d_out_counts, d_overflow));
+    uint8_t* h_res = hs + raw_bytes;
+    uint8_t* h_cnt = h_res + res_bytes;
+    QB_CUDA(cudaMemcpyAsync(h_res, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaMemcpyAsync(h_cnt, c->d_out_counts, cnt_bytes + 4, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaStreamSynchronize(stream));
+    unsigned int overflow = 0;
+    memcpy(&overflow, h_cnt + cnt_bytes, 4);
+    if (overflow) {
+        // the threshold admitted more candidates than the buffer holds (adversarial data, e.g. mass ties or a
+        // mostly-deleted sample): redo with full materialisation, which cannot overflow
+        QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, true, c->d_out, c->d_out_counts, d_overflow));
+        QB_CUDA(cudaMemcpyAsync(h_res, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaMemcpyAsync(h_cnt, c->d_out_counts, cnt_bytes, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaStreamSynchronize(stream));
+    }
+    memcpy(out, h_res, res_bytes);
+    memcpy(out_counts, h_cnt, cnt_bytes);
+    if (counters) {
+        const uint64_t n_cand = id_list ? n_ids : s->count;
+        counters->cpu += n_cand * (uint64_t)n_queries * cpu_units_per_point(s);
+        counters->vector_io_read += 0;  // HBM-resident storage is "not on disk": multiplier 0 (metric_query_scorer.rs:44-48)
+    }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_search_batch_device(qb_storage* s, const float* dev_queries, uint32_t n_queries, uint32_t top, qb_scored_point* dev_out,
+                                            uint32_t* dev_counts) {
+    QB_CHECK(s && dev_queries && dev_out && dev_counts, QB_ERR_INVALID, "search_batch_device: null argument");
+    QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "search_batch_device: top %u outside [1,%u]", top, QB_MAX_TOP);
+    if (n_queries == 0) return QB_OK;
+    QB_TRY(use_device(s->device));
+    QbSearchCtx* c = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->ctxs.empty()) c = s->ctxs[0];
+    }
+    if (!c) { QB_TRY(qb_ctx_acquire(s, &c)); qb_ctx_release(s, c); }
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, (size_t)n_queries * pre_stride_f(s) * 4 + 256));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, (size_t)n_queries * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
+    QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)n_queries + 4));
+    QB_TRY(prepare_queries(s, dev_queries, n_queries, reinterpret_cast<float*>(c->d_queries_raw), c->d_queries_enc, c->d_q_off, c->stream));
+    unsigned int* d_overflow = reinterpret_cast<unsigned int*>(c->d_out_counts + n_queries);
+    return run_search(s, c, n_queries, top, nullptr, 0, nullptr, nullptr, false, dev_out, dev_counts, d_overflow);
+}
+
+// ------------------------------------------------------------------------------------------------ RawScorer
+static qb_status scorer_alloc(qb_storage* s, qb_scorer** out) {
+    qb_scorer* sc = new qb_scorer();
+    sc->st = s;
+    if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete sc; qb_set_error("scorer: cudaStreamCreate failed"); return QB_ERR_CUDA;
+    }
+    sc->query_bytes = std::max<size_t>(qb_encoded_query_bytes(s), s->bq_row_bytes);
+    if (cudaMalloc(&sc->d_query, std::max<size_t>(sc->query_bytes, 256)) != cudaSuccess || cudaMalloc(&sc->d_q_off, 256) != cudaSuccess) {
+        qb_set_error("scorer: cudaMalloc failed"); qb_scorer_destroy(sc); return QB_ERR_OOM;
+    }
+    *out = sc;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_scorer_create(qb_storage* s, const float* query, qb_scorer** out) {
+    QB_CHECK(s && query && out, QB_ERR_INVALID, "scorer_create: null argument");
+    *out = nullptr;
+    QB_TRY(use_device(s->device));
+    qb_scorer* sc = nullptr;
+    QB_TRY(scorer_alloc(s, &sc));
+    float* d_raw = nullptr;
+    const size_t raw = (size_t)s->dim * 4, pre = (size_t)pre_stride_f(s) * 4;
+    if (cudaMalloc(&d_raw, raw + pre + 256) != cudaSuccess) { qb_scorer_destroy(sc); qb_set_error("scorer_create: cudaMalloc failed"); return QB_ERR_OOM; }
+    cudaError_t e = cudaMemcpyAsync(d_raw, query, raw, cudaMemcpyHostToDevice, sc->stream);
+    qb_status st = e == cudaSuccess ? prepare_queries(s, d_raw, 1, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_raw) + round_up_u64(raw, 16)),
+                                                      sc->d_query, sc->d_q_off, sc->stream)
+                                    : QB_ERR_CUDA;
+    if (st == QB_OK && cudaStreamSynchronize(sc->stream) != cudaSuccess) st = QB_ERR_CUDA;
+    cudaFree(d_raw);
+    if (st != QB_OK) { qb_set_error("scorer_create: %s", cudaGetErrorString(cudaGetLastError())); qb_scorer_destroy(sc); return st; }
+    *out = sc;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_scorer_create_internal(qb_storage* s, uint32_t point_id, qb_scorer** out) {
+    QB_CHECK(s && out, QB_ERR_INVALID, "scorer_create_internal: null argument");
+    *out = nullptr;
+    QB_CHECK(point_id < s->count, QB_ERR_INVALID, "scorer_create_internal: id %u out of range", point_id);
+    QB_CHECK(s->kind != QB_KIND_PQ, QB_ERR_UNSUPPORTED, "PQ has no internal query encoding (encode_internal_vector = None, encoded_vectors_pq.rs:624-627)");
+    QB_TRY(use_device(s->device));
+    qb_scorer* sc = nullptr;
+    QB_TRY(scorer_alloc(s, &sc));
+    sc->internal = true; sc->internal_id = point_id;
+    qb_status st = QB_OK;
+    cudaError_t e = cudaSuccess;
+    switch (s->kind) {
+        case QB_KIND_DENSE:
+            e = cudaMemcpyAsync(sc->d_query, reinterpret_cast<const uint8_t*>(s->d_rows) + (size_t)point_id * s->row_stride, s->row_stride,
+                                cudaMemcpyDeviceToDevice, sc->stream);
+            break;
+        case QB_KIND_SQ8: st = qb_sq8_internal_query(s, point_id, reinterpret_cast<uint8_t*>(sc->d_query), sc->d_q_off, sc->stream); break;
+        default:
+            e = cudaMemcpyAsync(sc->d_query, s->d_bq_rows + (size_t)point_id * s->bq_row_bytes, s->bq_row_bytes, cudaMemcpyDeviceToDevice, sc->stream);
+            break;
+    }
+    if (e != cudaSuccess) st = QB_ERR_CUDA;
+    if (st == QB_OK && cudaStreamSynchronize(sc->stream) != cudaSuccess) st = QB_ERR_CUDA;
+    if (st != QB_OK) { qb_set_error("scorer_create_internal: %s", cudaGetErrorString(cudaGetLastError())); qb_scorer_destroy(sc); return st; }
+    *out = sc;
+    return QB_OK;
+}
+
+extern "C" void qb_scorer_destroy(qb_scorer* sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->st->device);
+    if (sc->stream) cudaStreamSynchronize(sc->stream);
+    cudaFree(sc->d_query); cudaFree(sc->d_q_off); cudaFree(sc->d_ids); cudaFree(sc->d_scores);
+    if (sc->h_ids) cudaFreeHost(sc->h_ids);
+    if (sc->h_scores) cudaFreeHost(sc->h_scores);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    cudaGetLastError();
+    delete sc;
+}
+
+static qb_status scorer_reserve(qb_scorer* sc, size_t n) {
+    if (n <= sc->cap) return QB_OK;
+    size_t cap = std::max<size_t>(n, 256);
+    cap = round_up_u64(cap, 256);
+    cudaFree(sc->d_ids); cudaFree(sc->d_scores);
+    if (sc->h_ids) cudaFreeHost(sc->h_ids);
+    if (sc->h_scores) cudaFreeHost(sc->h_scores);
+    sc->d_ids = nullptr; sc->d_scores = nullptr; sc->h_ids = nullptr; sc->h_scores = nullptr; sc->cap = 0;
+    QB_CUDA(cudaMalloc(&sc->d_ids, cap * 4));
+    QB_CUDA(cudaMalloc(&sc->d_scores, cap * 4));
+    QB_CUDA(cudaMallocHost(&sc->h_ids, cap * 4));
+    QB_CUDA(cudaMallocHost(&sc->h_scores, cap * 4));
+    sc->cap = cap;
+    return QB_OK;
+}
+
+static qb_status scorer_launch(qb_scorer* sc, const uint32_t* d_ids, uint64_t n, float* d_scores) {
+    qb_storage* s = sc->st;
+    if (s->kind == QB_KIND_BQ) {
+        const int bits = sc->internal ? 1 : (s->bq_qenc == QB_BQQ_SCALAR4 ? 4 : (s->bq_qenc == QB_BQQ_SCALAR8 ? 8 : 1));
+        return qb_bq_score_points(s, sc->d_query, bits, d_ids, n, d_scores, sc->stream);
+    }
+    return qb_launch_score_points(s, sc->d_query, sc->d_q_off, d_ids, n, d_scores, sc->stream);
+}
+
+extern "C" qb_status qb_score_points(qb_scorer* sc, const uint32_t* ids, size_t n, float* scores) {
+    QB_CHECK(sc && (n == 0 || (ids && scores)), QB_ERR_INVALID, "score_points: null argument");
+    if (n == 0) return QB_OK;
+    qb_storage* s = sc->st;
+    for (size_t i = 0; i < n; ++i) QB_CHECK(ids[i] < s->count, QB_ERR_INVALID, "score_points: id %u out of range (count %llu)", ids[i], (unsigned long long)s->count);
+    QB_TRY(use_device(s->device));
+    QB_TRY(scorer_reserve(sc, n));
+    memcpy(sc->h_ids, ids, n * 4);
+    QB_CUDA(cudaMemcpyAsync(sc->d_ids, sc->h_ids, n * 4, cudaMemcpyHostToDevice, sc->stream));
+    QB_TRY(scorer_launch(sc, sc->d_ids, n, sc->d_scores));
+    QB_CUDA(cudaMemcpyAsync(sc->h_scores, sc->d_scores, n * 4, cudaMemcpyDeviceToHost, sc->stream));
+    QB_CUDA(cudaStreamSynchronize(sc->stream));
+    memcpy(scores, sc->h_scores, n * 4);
+    sc->hw.cpu += (uint64_t)n * cpu_units_per_point(s);
+    return QB_OK;
+}
+
+extern "C" qb_status qb_score_point(qb_scorer* sc, uint32_t id, float* score) { return qb_score_points(sc, &id, 1, score); }
+
+extern "C" qb_status qb_score_internal(qb_scorer* sc, uint32_t a, uint32_t b, float* score) {
+    QB_CHECK(sc && score, QB_ERR_INVALID, "score_internal: null argument");
+    qb_storage* s = sc->st;
+    QB_CHECK(a < s->count && b < s->count, QB_ERR_INVALID, "score_internal: id out of range (the reference panics)");
+    QB_TRY(use_device(s->device));
+    QB_TRY(scorer_reserve(sc, 1));
+    if (s->kind == QB_KIND_PQ) {
+        QB_TRY(qb_pq_score_internal(s, a, b, sc->d_scores, sc->stream));
+    } else {
+        // point `a` becomes the query (MetricQueryScorer::score_internal; SQ8 encode_internal_vector; BQ binary)
+        qb_scorer* tmp = nullptr;
+        QB_TRY(qb_scorer_create_internal(s, a, &tmp));
+        qb_status st = qb_score_points(tmp, &b, 1, score);
+        qb_scorer_destroy(tmp);
+        sc->hw.cpu += cpu_units_per_point(s);
+        return st;
+    }
+    QB_CUDA(cudaMemcpyAsync(sc->h_scores, sc->d_scores, 4, cudaMemcpyDeviceToHost, sc->stream));
+    QB_CUDA(cudaStreamSynchronize(sc->stream));
+    *score = sc->h_scores[0];
+    sc->hw.cpu += (uint64_t)s->pq_m * (s->pq_div[1] - s->pq_div[0]);
+    return QB_OK;
+}
+
+extern "C" qb_status qb_scorer_take_counters(qb_scorer* sc, qb_hw_counters* out) {
+    QB_CHECK(sc && out, QB_ERR_INVALID, "take_counters: null argument");
+    *out = sc->hw;
+    sc->hw.cpu = 0; sc->hw.vector_io_read = 0;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_rescore(qb_scorer* orig, const uint32_t* ids, size_t n, uint32_t top, qb_scored_point* out, uint32_t* out_count) {
+    QB_CHECK(orig && out && out_count && (n == 0 || ids), QB_ERR_INVALID, "rescore: null argument");
+    QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "rescore: top %u outside [1,%u]", top, QB_MAX_TOP);
+    *out_count = 0;
+    if (n == 0) return QB_OK;
+    qb_storage* s = orig->st;
+    for (size_t i = 0; i < n; ++i) QB_CHECK(ids[i] < s->count, QB_ERR_INVALID, "rescore: id %u out of range", ids[i]);
+    QB_TRY(use_device(s->device));
+    QB_TRY(scorer_reserve(orig, std::max<size_t>(n, (size_t)top * 2 + 8)));
+    memcpy(orig->h_ids, ids, n * 4);
+    QB_CUDA(cudaMemcpyAsync(orig->d_ids, orig->h_ids, n * 4, cudaMemcpyHostToDevice, orig->stream));
+    // score into candidate keys, select top on the device (postprocess_search_result: sort_unstable desc + truncate)
+    unsigned long long* d_cand = nullptr;
+    QB_CUDA(cudaMalloc(&d_cand, n * 8 + top * sizeof(qb_scored_point) + 64));
+    QbScanArgs a{};
+    a.d_q_enc = orig->d_query; a.d_q_off = orig->d_q_off; a.nq = 1; a.row_begin = 0; a.row_end = n; a.d_ids = orig->d_ids;
+    a.emit.cand = d_cand; a.emit.cap = n; a.emit.dense = 1; a.emit.dense_base = 0;
+    qb_status st = QB_OK;
+    if (s->kind == QB_KIND_BQ) st = QB_ERR_UNSUPPORTED;  // rescoring always uses the original (dense) vectors
+    else st = qb_launch_scan(s, a, orig->stream);
+    qb_scored_point* d_res = reinterpret_cast<qb_scored_point*>(d_cand + n);
+    uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d_res + top);
+    if (st == QB_OK) st = qb_launch_select(d_cand, nullptr, n, n, 1, top, 0, d_res, d_cnt, nullptr, nullptr, orig->stream);
+    cudaError_t e = cudaSuccess;
+    if (st == QB_OK) {
+        e = cudaMemcpyAsync(out, d_res, (size_t)top * sizeof(qb_scored_point), cudaMemcpyDeviceToHost, orig->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_count, d_cnt, 4, cudaMemcpyDeviceToHost, orig->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(orig->stream);
+    }
+    cudaFree(d_cand);
+    if (e != cudaSuccess) { qb_set_error("rescore: %s", cudaGetErrorString(e)); return QB_ERR_CUDA; }
+    orig->hw.cpu += (uint64_t)n * cpu_units_per_point(s);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------ sharding
+extern "C" qb_status qb_storage_set_id_base(qb_storage* s, uint32_t id_base) {
+    QB_CHECK(s, QB_ERR_INVALID, "set_id_base: null storage");
+    s->id_base = id_base;
+    return QB_OK;
+}
+
+__global__ void lists_to_keys_kernel(const qb_scored_point* __restrict__ lists, const uint32_t* __restrict__ counts, uint32_t n_lists, uint32_t nq,
+                                     uint32_t top, unsigned long long* __restrict__ keys) {
+    // lists: [n_lists][nq][top], counts: [n_lists][nq]  ->  keys: [nq][n_lists*top] (0 = empty)
+    const uint64_t total = (uint64_t)n_lists * nq * top;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(i % top);
+        const uint32_t q = (uint32_t)((i / top) % nq);
+        const uint32_t l = (uint32_t)(i / ((uint64_t)top * nq));
+        const qb_scored_point sp = lists[i];
+        keys[(uint64_t)q * n_lists * top + (uint64_t)l * top + k] = (k < counts[(uint64_t)l * nq + q]) ? qb_pack_key(sp.score, sp.idx) : 0ull;
+    }
+}
+
+// BatchResultAggregator (lib/shard/src/search_result_aggregator.rs:50-117) for per-GPU shards: merge n_lists sorted
+// top-k lists per query (as gathered over NVLink) into one.  All pointers are device memory; enqueued on `stream`.
+extern "C" qb_status qb_topk_merge_device(int32_t device, const qb_scored_point* dev_lists, const uint32_t* dev_counts, uint32_t n_lists,
+                                          uint32_t n_queries, uint32_t top, qb_scored_point* dev_out, uint32_t* dev_out_counts,
+                                          void* dev_scratch, uint64_t scratch_bytes, void* stream) {
+    QB_CHECK(dev_lists && dev_counts && dev_out && dev_out_counts && dev_scratch, QB_ERR_INVALID, "topk_merge: null argument");
+    QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "topk_merge: top %u outside [1,%u]", top, QB_MAX_TOP);
+    const uint64_t need = (uint64_t)n_queries * n_lists * top * 8;
+    QB_CHECK(scratch_bytes >= need, QB_ERR_INVALID, "topk_merge: scratch %llu < %llu bytes", (unsigned long long)scratch_bytes, (unsigned long long)need);
+    if (n_queries == 0 || n_lists == 0) return QB_OK;
+    QB_TRY(use_device(device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const uint64_t total = (uint64_t)n_lists * n_queries * top;
+    lists_to_keys_kernel<<<(unsigned)std::min<uint64_t>(ceil_div_u64(total, 256), 4096), 256, 0, st>>>(
+        dev_lists, dev_counts, n_lists, n_queries, top, reinterpret_cast<unsigned long long*>(dev_scratch));
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return qb_launch_select(reinterpret_cast<unsigned long long*>(dev_scratch), nullptr, (unsigned long long)n_lists * top,
+                            (unsigned long long)n_lists * top, n_queries, top, 0, dev_out, dev_out_counts, nullptr, nullptr, st);
+}
+
+// ------------------------------------------------------------------------------------------------ profiling
+extern "C" qb_status qb_profile_enable(qb_storage* s, int32_t on) {
+    QB_CHECK(s, QB_ERR_INVALID, "profile_enable: null storage");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->profile = on != 0;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_profile_read(qb_storage* s, uint64_t* launches, double* total_ms, int32_t reset) {
+    QB_CHECK(s, QB_ERR_INVALID, "profile_read: null storage");
+    QB_TRY(use_device(s->device));
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (auto& pr : s->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            s->prof_ms += ms;
+            s->prof_launches += 1;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    s->prof_pending.clear();
+    if (launches) *launches = s->prof_launches;
+    if (total_ms) *total_ms = s->prof_ms;
+    if (reset) { s->prof_launches = 0; s->prof_ms = 0.0; }
+    return QB_OK;
+}

@@ -1,0 +1,144 @@
+// qb_internal.h — host-side objects behind the opaque C-ABI handles.
+#pragma once
+#include "qb_common.cuh"
+
+enum QbKind { QB_KIND_DENSE = 0, QB_KIND_SQ8 = 1, QB_KIND_PQ = 2, QB_KIND_BQ = 3 };
+
+constexpr uint32_t QB_MAX_TOP = 4096;          // fused top-k limit (select kernel sorts <= 4096 keys in smem)
+constexpr uint32_t QB_SELECT_THREADS = 1024;
+
+// A search context: one CUDA stream + the scratch a brute-force scan needs.  Contexts are pooled per
+// storage so that concurrent qb_search_batch calls (one blocking task per segment in the reference,
+// segments_searcher.rs:255) never share buffers.
+struct QbSearchCtx {
+    cudaStream_t stream = nullptr;
+    // device scratch
+    void* d_queries_raw = nullptr;   size_t queries_raw_bytes = 0;   // uploaded raw f32 queries
+    void* d_queries_enc = nullptr;   size_t queries_enc_bytes = 0;   // preprocessed / encoded queries
+    float* d_q_off = nullptr;        size_t q_off_elems = 0;         // SQ8 query offsets
+    float* d_thr = nullptr;          size_t thr_elems = 0;
+    unsigned int* d_cnt = nullptr;   size_t cnt_elems = 0;
+    unsigned long long* d_cand = nullptr; size_t cand_elems = 0;
+    qb_scored_point* d_out = nullptr; size_t out_elems = 0;
+    uint32_t* d_out_counts = nullptr; size_t out_counts_elems = 0;
+    uint32_t* d_deleted2 = nullptr;  size_t deleted2_words = 0;
+    uint32_t* d_ids = nullptr;       size_t ids_elems = 0;
+    // pinned host staging
+    void* h_stage = nullptr;         size_t h_stage_bytes = 0;
+    // profiling
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool in_use = false;
+};
+
+struct qb_storage {
+    int device = 0;
+    QbKind kind = QB_KIND_DENSE;
+    uint32_t dim = 0;
+    uint64_t count = 0;
+    uint64_t hbm_bytes = 0;
+
+    // ---- dense
+    qb_dtype dtype = QB_DT_F32;
+    qb_distance distance = QB_DIST_DOT;
+    void* d_rows = nullptr;          // row-major, stride padded to 16 B
+    uint32_t row_stride = 0;         // bytes
+    uint32_t elem_size = 4;
+
+    // ---- quantized common
+    qb_qdistance qdist = QB_QD_DOT;
+    int invert = 0;
+
+    // ---- SQ8 (rows repacked: code plane + offset plane; the HBM copy is a cache, SURVEY §7 hard parts)
+    uint32_t actual_dim = 0;
+    uint8_t* d_codes = nullptr;      // [count][actual_dim], actual_dim % 16 == 0
+    float* d_voff = nullptr;         // [count]
+    float alpha = 0, offset = 0, multiplier = 0;
+
+    // ---- PQ
+    uint32_t pq_m = 0, pq_stride = 0, n_centroids = 0;
+    std::vector<uint32_t> pq_div;    // 2*m {start,end}
+    uint32_t* d_pq_div = nullptr;
+    float* d_centroids = nullptr;    // [n_centroids][dim]
+    uint8_t* d_pq_codes = nullptr;   // [count][pq_stride], stride = round_up(m,16)
+
+    // ---- BQ
+    qb_bq_encoding bq_enc = QB_BQ_ONE_BIT;
+    qb_bq_query_encoding bq_qenc = QB_BQQ_SAME_AS_STORAGE;
+    uint32_t bq_row_bytes = 0;
+    uint8_t* d_bq_rows = nullptr;
+    float* d_mean_std = nullptr;
+
+    // ---- sharding: ids reported by searches are local row + id_base
+    uint32_t id_base = 0;
+
+    // ---- soft deletes
+    uint32_t* d_deleted = nullptr;   // resident bits (32-bit words), or null
+
+    // ---- contexts / profiling
+    std::mutex mu;
+    std::vector<QbSearchCtx*> ctxs;
+    bool profile = false;
+    uint64_t prof_launches = 0;
+    double prof_ms = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+    int sm_count = 148;
+};
+
+struct qb_scorer {
+    qb_storage* st = nullptr;
+    cudaStream_t stream = nullptr;
+    void* d_query = nullptr;         // preprocessed f32 / u8 / f16 query, SQ8 code, PQ LUT, BQ encoded query
+    size_t query_bytes = 0;
+    float* d_q_off = nullptr;        // SQ8 query offset (device scalar)
+    bool internal = false;
+    uint32_t internal_id = 0;
+    // staging (grown on demand)
+    uint32_t* d_ids = nullptr;  float* d_scores = nullptr;  size_t cap = 0;
+    uint32_t* h_ids = nullptr;  float* h_scores = nullptr;  size_t h_cap = 0;
+    qb_hw_counters hw = {0, 0};
+};
+
+// ---------------------------------------------------------------- helpers (qb_api.cu)
+qb_status qb_ensure_device(void** p, size_t* have, size_t need_bytes);
+qb_status qb_ensure_pinned(void** p, size_t* have, size_t need_bytes);
+qb_status qb_ctx_acquire(qb_storage* s, QbSearchCtx** out);
+void qb_ctx_release(qb_storage* s, QbSearchCtx* c);
+
+// ---------------------------------------------------------------- kernels' host launchers
+// All launchers enqueue on `stream` and never synchronise.
+
+// queries: Metric::preprocess / encode_query on device.  q_raw [nq][dim] f32 -> ctx->d_queries_enc (+ d_q_off)
+qb_status qb_launch_prepare_queries(const qb_storage* s, const float* d_q_raw, uint32_t nq, void* d_q_enc, float* d_q_off,
+                                    cudaStream_t stream);
+// size in bytes of one encoded query for this storage
+size_t qb_encoded_query_bytes(const qb_storage* s);
+
+// scan rows [row_begin,row_end) (id_list == null) or the listed ids [0,n_ids) against nq encoded queries
+struct QbScanArgs {
+    const void* d_q_enc;
+    const float* d_q_off;
+    uint32_t nq;
+    uint64_t row_begin, row_end;
+    const uint32_t* d_ids;  // optional gather list; then row_begin/row_end index into it
+    QbEmit emit;
+};
+qb_status qb_launch_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
+
+// score listed ids for ONE encoded query into d_scores (RawScorer::score_points)
+qb_status qb_launch_score_points(const qb_storage* s, const void* d_q_enc, const float* d_q_off, const uint32_t* d_ids,
+                                 uint64_t n, float* d_scores, cudaStream_t stream);
+// encoded query taken from a stored point (internal scorer)
+qb_status qb_launch_encode_internal(const qb_storage* s, uint32_t point_id, void* d_q_enc, float* d_q_off, cudaStream_t stream);
+
+// selection (qb_topk.cu)
+//  mode 0: write top-k (desc) of each query's candidate list to out/out_counts
+//  mode 1: write the score of the k-th best candidate of each query to thr (or -inf when fewer than k)
+qb_status qb_launch_select(const unsigned long long* d_cand, const unsigned int* d_cnt, unsigned long long cap,
+                           unsigned long long fixed_n /* !=0: dense lists of this length */, uint32_t nq, uint32_t top, int mode,
+                           qb_scored_point* d_out, uint32_t* d_out_counts, float* d_thr, unsigned int* d_overflow,
+                           cudaStream_t stream);
+qb_status qb_launch_fill_u32(unsigned int* p, unsigned int v, size_t n, cudaStream_t stream);
+
+// dense preprocess of rows in place (qb_dense.cu)
+qb_status qb_launch_preprocess_rows(qb_distance distance, uint32_t dim, uint64_t n, const float* in, uint64_t in_stride_f,
+                                    float* out, uint64_t out_stride_f, cudaStream_t stream);

@@ -1,0 +1,592 @@
+// qb_quant.cu — quantized scorers on B200: SQ8 (scalar), PQ (product, LUT) and BQ (binary).
+//
+// Replaces quantization::EncodedVectors::{encode_query, score, score_point, score_internal}
+// (lib/quantization/src/encoded_vectors.rs:41-117) for
+//   SQ8  EncodedVectorsU8  — lib/quantization/src/encoded_vectors_u8.rs (+ cpp/avx2.c:25-122)
+//   PQ   EncodedVectorsPQ  — lib/quantization/src/encoded_vectors_pq.rs:411-443,519-541,574-618
+//   BQ   EncodedVectorsBin<u128> — lib/quantization/src/encoded_vectors_binary.rs:558-810
+// as called from QuantizedQueryScorer::score_stored_batch (lib/segment/src/vector_storage/quantized/
+// quantized_query_scorer.rs:81-93).  All three are integer / table work bounded by HBM or shared-memory
+// gathers; none of it is reshaped into a GEMM here (the batched SQ8 tensor-core path lives in qb_sq8_mma.cu).
+//
+// Exactness notes
+//   SQ8  integer dot is exact; the CPU converts 8 i32 lanes to f32 and adds them in the HSUM256_PS tree
+//        (cpp/avx2.c:7-14).  Codes are <= 127 and non-negative, so when the total is < 2^24 every partial
+//        is exact and any order gives f32(total); beyond that (only possible for actual_dim > 1040) the
+//        LANEX variant reproduces the lane partition and the tree.  The epilogue is three separate roundings
+//        (encoded_vectors_u8.rs:101-103).
+//   PQ   four f32 lanes, lane k sums chunks j = k (mod 4) in ascending j; (s0+s2)+(s1+s3); tail sequential.
+//   BQ   popcounts are integers; the float epilogue of calculate_metric is restated literally.
+#include "qb_internal.h"
+
+namespace {
+
+// ================================================================== SQ8 ===========================
+__device__ __forceinline__ uint8_t sq8_encode_value(float v, float offset, float alpha) {  // encoded_vectors_u8.rs:95-98
+    float i = __fdiv_rn(__fsub_rn(v, offset), alpha);
+    if (i < 0.0f) i = 0.0f;          // f32::clamp keeps NaN
+    if (i > 127.0f) i = 127.0f;
+    float r = roundf(i);             // f32::round: half away from zero
+    if (r != r) return 0;            // NaN as u8 == 0
+    return (uint8_t)r;
+}
+
+// one block per query: threads encode elements, thread 0 folds the offset sequentially (f32, Rust order)
+__global__ void __launch_bounds__(256) sq8_encode_query_kernel(const float* __restrict__ q_pre, uint32_t q_stride_f, uint32_t dim,
+                                                               uint32_t actual_dim, float alpha, float offset, int qdist, int invert,
+                                                               uint8_t* __restrict__ codes, float* __restrict__ q_off) {
+    const uint32_t q = blockIdx.x;
+    const float* src = q_pre + (size_t)q * q_stride_f;
+    uint8_t* dst = codes + (size_t)q * actual_dim;
+    const bool is_dot = (qdist == QB_QD_DOT || qdist == QB_QD_COSINE);
+    const uint8_t pad = sq8_encode_value(is_dot ? 0.0f : offset, offset, alpha);  // :586-596
+    for (uint32_t i = threadIdx.x; i < actual_dim; i += blockDim.x) dst[i] = (i < dim) ? sq8_encode_value(src[i], offset, alpha) : pad;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float off;
+        if (is_dot) {
+            float s = -0.0f;
+            for (uint32_t i = 0; i < actual_dim; ++i) s = __fadd_rn(s, (float)dst[i]);
+            off = __fmul_rn(__fmul_rn(s, alpha), offset);
+        } else if (qdist == QB_QD_L1) {
+            off = 0.0f;
+        } else {
+            float s = -0.0f;
+            for (uint32_t i = 0; i < actual_dim; ++i) { float c = (float)dst[i]; s = __fadd_rn(s, __fmul_rn(c, c)); }
+            off = __fmul_rn(__fmul_rn(s, alpha), alpha);
+        }
+        q_off[q] = invert ? -off : off;
+    }
+}
+
+struct Sq8Params {
+    const uint8_t* codes;   // [count][ad]
+    const float* voff;      // [count]
+    uint32_t ad;            // actual_dim (multiple of 16)
+    float multiplier;
+    int l1;                 // 1: Manhattan on codes
+    uint64_t begin, end;
+    const uint32_t* ids;
+    const uint8_t* q_codes; // [nq][ad]
+    const float* q_off;     // [nq]
+    uint32_t nq;
+    float* scores;
+    int emit_mode;
+};
+
+// 8 lanes per candidate, 16 B per lane per step.
+template <bool LANEX>
+__global__ void __launch_bounds__(256) sq8_group_kernel(const Sq8Params p, const QbEmit emit) {
+    const int t = threadIdx.x & 7;
+    const uint64_t groups_per_grid = (uint64_t)gridDim.x * (blockDim.x >> 3);
+    const uint64_t g0 = (uint64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    const uint64_t n = p.end - p.begin;
+    const uint64_t n_iter = (n + groups_per_grid - 1) / groups_per_grid;
+    const uint32_t n_chunks = p.ad >> 4;
+    for (uint64_t it = 0; it < n_iter; ++it) {
+        const uint64_t ci = g0 + it * groups_per_grid;
+        const bool valid = ci < n;
+        const uint64_t cand = p.begin + (valid ? ci : 0);
+        const uint32_t row = p.ids ? p.ids[cand] : (uint32_t)cand;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.codes + (size_t)row * p.ad);
+        const float v_off = p.voff[row];
+        for (uint32_t q = 0; q < p.nq; ++q) {
+            const uint4* qp = reinterpret_cast<const uint4*>(p.q_codes + (size_t)q * p.ad);
+            float score;
+            if (p.l1) {
+                unsigned int acc = 0;
+                for (uint32_t c = t; c < n_chunks; c += 8) {
+                    uint4 v = __ldg(rp + c), w = __ldg(qp + c);
+                    acc += __vsadu4(v.x, w.x) + __vsadu4(v.y, w.y) + __vsadu4(v.z, w.z) + __vsadu4(v.w, w.w);
+                }
+                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+                score = (float)acc;  // impl_score_l1_avx returns (float)sum, cpp/avx2.c:117-121
+            } else if (!LANEX) {
+                int acc = 0;
+                for (uint32_t c = t; c < n_chunks; c += 8) {
+                    uint4 v = __ldg(rp + c), w = __ldg(qp + c);
+                    acc = __dp4a((int)v.x, (int)w.x, acc);
+                    acc = __dp4a((int)v.y, (int)w.y, acc);
+                    acc = __dp4a((int)v.z, (int)w.z, acc);
+                    acc = __dp4a((int)v.w, (int)w.w, acc);
+                }
+                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+                score = (float)acc;  // exact: total < 2^24 (see header)
+            } else {
+                // lane partition of impl_score_dot_avx: byte pair j of every 16-B chunk accumulates into i32 lane j
+                int ln[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (uint32_t c = t; c < n_chunks; c += 8) {
+                    uint4 v = __ldg(rp + c), w = __ldg(qp + c);
+                    ln[0] = __dp4a((int)v.x, (int)(w.x & 0x0000FFFFu), ln[0]); ln[1] = __dp4a((int)v.x, (int)(w.x & 0xFFFF0000u), ln[1]);
+                    ln[2] = __dp4a((int)v.y, (int)(w.y & 0x0000FFFFu), ln[2]); ln[3] = __dp4a((int)v.y, (int)(w.y & 0xFFFF0000u), ln[3]);
+                    ln[4] = __dp4a((int)v.z, (int)(w.z & 0x0000FFFFu), ln[4]); ln[5] = __dp4a((int)v.z, (int)(w.z & 0xFFFF0000u), ln[5]);
+                    ln[6] = __dp4a((int)v.w, (int)(w.w & 0x0000FFFFu), ln[6]); ln[7] = __dp4a((int)v.w, (int)(w.w & 0xFFFF0000u), ln[7]);
+                }
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    ln[l] += __shfl_xor_sync(0xFFFFFFFFu, ln[l], 1);
+                    ln[l] += __shfl_xor_sync(0xFFFFFFFFu, ln[l], 2);
+                    ln[l] += __shfl_xor_sync(0xFFFFFFFFu, ln[l], 4);
+                }
+                // HSUM256_PS (cpp/avx2.c:7-14): ((l0+l4)+(l2+l6)) + ((l1+l5)+(l3+l7))
+                float x0 = __fadd_rn((float)ln[4], (float)ln[0]), x1 = __fadd_rn((float)ln[5], (float)ln[1]);
+                float x2 = __fadd_rn((float)ln[6], (float)ln[2]), x3 = __fadd_rn((float)ln[7], (float)ln[3]);
+                score = __fadd_rn(__fadd_rn(x0, x2), __fadd_rn(x1, x3));
+            }
+            // postprocess_score: multiplier * score + query_offset + vector_offset (encoded_vectors_u8.rs:101-103)
+            const float sc = __fadd_rn(__fadd_rn(__fmul_rn(p.multiplier, score), p.q_off[q]), v_off);
+            if (valid && t == 0) {
+                if (p.emit_mode) qb_emit(emit, q, cand, row, sc);
+                else p.scores[(size_t)q * n + ci] = sc;
+            }
+        }
+    }
+}
+
+// encode_internal_vector (encoded_vectors_u8.rs:715-728): query code = stored code, q_off = v_off - shift
+__global__ void sq8_internal_query_kernel(const uint8_t* __restrict__ codes, const float* __restrict__ voff, uint32_t ad, uint32_t id,
+                                          float shift, uint8_t* __restrict__ q_code, float* __restrict__ q_off) {
+    for (uint32_t i = threadIdx.x; i < ad; i += blockDim.x) q_code[i] = codes[(size_t)id * ad + i];
+    if (threadIdx.x == 0) q_off[0] = __fsub_rn(voff[id], shift);
+}
+
+// repack [f32 v_off][codes] rows -> code plane + offset plane
+__global__ void sq8_repack_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes, uint32_t ad, uint64_t n, uint8_t* __restrict__ codes,
+                                  float* __restrict__ voff) {
+    const uint64_t total = n * (uint64_t)(ad >> 2);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / (ad >> 2);
+        const uint32_t w = (uint32_t)(i % (ad >> 2));
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rows + r * row_bytes);  // row_bytes = 4 + ad, 4-B aligned
+        reinterpret_cast<uint32_t*>(codes + r * ad)[w] = src[1 + w];
+        if (w == 0) voff[r] = __uint_as_float(src[0]);
+    }
+}
+
+// ================================================================== PQ ============================
+// LUT build (encode_query, encoded_vectors_pq.rs:519-541): grid (m, nq), thread c = centroid
+__global__ void __launch_bounds__(256) pq_lut_kernel(const float* __restrict__ q_pre, uint32_t q_stride_f, uint32_t dim, uint32_t m,
+                                                     const uint32_t* __restrict__ div, const float* __restrict__ centroids,
+                                                     uint32_t n_centroids, int qdist, int invert, float* __restrict__ luts) {
+    const uint32_t j = blockIdx.x, q = blockIdx.y;
+    const uint32_t s = div[2 * j], e = div[2 * j + 1];
+    const float* a = q_pre + (size_t)q * q_stride_f + s;
+    for (uint32_t c = threadIdx.x; c < n_centroids; c += blockDim.x) {
+        const float* b = centroids + (size_t)c * dim + s;
+        float acc = -0.0f;  // DistanceType::distance, encoded_vectors.rs:119-127 (sequential f32 sums)
+        if (qdist == QB_QD_DOT || qdist == QB_QD_COSINE) {
+            for (uint32_t k = 0; k < e - s; ++k) acc = __fadd_rn(acc, __fmul_rn(a[k], b[k]));
+        } else if (qdist == QB_QD_L1) {
+            for (uint32_t k = 0; k < e - s; ++k) acc = __fadd_rn(acc, fabsf(__fsub_rn(a[k], b[k])));
+        } else {
+            for (uint32_t k = 0; k < e - s; ++k) { float d = __fsub_rn(a[k], b[k]); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+        }
+        luts[((size_t)q * m + j) * n_centroids + c] = invert ? -acc : acc;
+    }
+}
+
+struct PqParams {
+    const uint8_t* codes;   // [count][stride]
+    uint32_t stride, m, n_centroids;
+    uint64_t begin, end;
+    const uint32_t* ids;
+    const float* luts;      // [nq][m][n_centroids]
+    uint32_t nq;
+    float* scores;
+    int emit_mode;
+    int lut_in_smem;
+};
+
+// score_point_sse (encoded_vectors_pq.rs:411-443): one thread per candidate, LUT of the current query in smem
+__global__ void __launch_bounds__(512) pq_scan_kernel(const PqParams p, const QbEmit emit) {
+    extern __shared__ __align__(16) float lut_s[];
+    const uint64_t n = p.end - p.begin;
+    const size_t lut_elems = (size_t)p.m * p.n_centroids;
+    const uint32_t K = p.n_centroids;
+    const uint32_t m4 = p.m & ~3u;
+    for (uint32_t q = 0; q < p.nq; ++q) {
+        const float* lut = p.luts + (size_t)q * lut_elems;
+        if (p.lut_in_smem) {
+            __syncthreads();
+            const float4* src = reinterpret_cast<const float4*>(lut);
+            float4* dst = reinterpret_cast<float4*>(lut_s);
+            for (size_t i = threadIdx.x; i < lut_elems / 4; i += blockDim.x) dst[i] = src[i];
+            for (size_t i = (lut_elems & ~(size_t)3) + threadIdx.x; i < lut_elems; i += blockDim.x) lut_s[i] = lut[i];
+            __syncthreads();
+            lut = lut_s;
+        }
+        for (uint64_t ci = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t cand = p.begin + ci;
+            const uint32_t row = p.ids ? p.ids[cand] : (uint32_t)cand;
+            const uint8_t* code = p.codes + (size_t)row * p.stride;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            uint32_t j = 0;
+            for (; j + 16 <= m4; j += 16) {
+                const uint4 cw = *reinterpret_cast<const uint4*>(code + j);
+                const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float* l = lut + (size_t)(j + 4 * k) * K;
+                    s0 = __fadd_rn(s0, l[w[k] & 255u]);
+                    s1 = __fadd_rn(s1, l[K + ((w[k] >> 8) & 255u)]);
+                    s2 = __fadd_rn(s2, l[2 * K + ((w[k] >> 16) & 255u)]);
+                    s3 = __fadd_rn(s3, l[3 * K + (w[k] >> 24)]);
+                }
+            }
+            for (; j < m4; j += 4) {
+                const float* l = lut + (size_t)j * K;
+                s0 = __fadd_rn(s0, l[code[j]]);
+                s1 = __fadd_rn(s1, l[K + code[j + 1]]);
+                s2 = __fadd_rn(s2, l[2 * K + code[j + 2]]);
+                s3 = __fadd_rn(s3, l[3 * K + code[j + 3]]);
+            }
+            float sum = __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
+            for (; j < p.m; ++j) sum = __fadd_rn(sum, lut[(size_t)j * K + code[j]]);
+            if (p.emit_mode) qb_emit(emit, q, cand, row, sum);
+            else p.scores[(size_t)q * n + ci] = sum;
+        }
+    }
+}
+
+// score_internal (encoded_vectors_pq.rs:574-618): decode both codes through the centroids; single pair
+__global__ void pq_score_internal_kernel(const uint8_t* __restrict__ codes, uint32_t stride, uint32_t m, const uint32_t* __restrict__ div,
+                                         const float* __restrict__ centroids, uint32_t dim, int qdist, int invert, uint32_t a, uint32_t b,
+                                         float* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    float total = -0.0f;
+    for (uint32_t j = 0; j < m; ++j) {
+        const uint32_t s = div[2 * j], e = div[2 * j + 1];
+        const float* x = centroids + (size_t)codes[(size_t)a * stride + j] * dim + s;
+        const float* y = centroids + (size_t)codes[(size_t)b * stride + j] * dim + s;
+        float acc = -0.0f;
+        if (qdist == QB_QD_DOT || qdist == QB_QD_COSINE) {
+            for (uint32_t k = 0; k < e - s; ++k) acc = __fadd_rn(acc, __fmul_rn(x[k], y[k]));
+        } else if (qdist == QB_QD_L1) {
+            for (uint32_t k = 0; k < e - s; ++k) acc = __fadd_rn(acc, fabsf(__fsub_rn(x[k], y[k])));
+        } else {
+            for (uint32_t k = 0; k < e - s; ++k) { float d = __fsub_rn(x[k], y[k]); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+        }
+        total = __fadd_rn(total, acc);
+    }
+    out[0] = invert ? -total : total;
+}
+
+// ================================================================== BQ ============================
+__device__ __forceinline__ void bq_two_bits(float value, const float* ms, bool& b1, bool& b2) {  // :636-671
+    if (!ms) { b1 = b2 = value > 0.0f; return; }
+    const float mean = ms[0], sd = ms[1];
+    if (sd < 1.1920929e-07f) { b1 = value > 0.0f; b2 = false; return; }
+    const float vz = __fdiv_rn(__fsub_rn(value, mean), sd);
+    const float SIG = 2.0f / 3.0f;
+    if (vz <= -SIG) { b1 = false; b2 = false; }
+    else if (vz < SIG) { b1 = true; b2 = false; }
+    else { b1 = true; b2 = true; }
+}
+
+// one block per query.  Binary query (SameAsStorage) or transposed scalar query (4 / 8 bits).
+__global__ void __launch_bounds__(256) bq_encode_query_kernel(const float* __restrict__ q_pre, uint32_t q_stride_f, uint32_t dim, int enc,
+                                                              int bits, const float* __restrict__ mean_std, uint32_t row_bytes,
+                                                              uint32_t* __restrict__ out /* [nq][row_bytes*bits/4] */) {
+    __shared__ float s_max[256];
+    const uint32_t q = blockIdx.x;
+    const float* src = q_pre + (size_t)q * q_stride_f;
+    const uint32_t words = row_bytes * (uint32_t)bits / 4;
+    uint32_t* dst = out + (size_t)q * words;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = 0u;
+    __syncthreads();
+    if (bits == 1) {
+        for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+            const float v = src[i];
+            if (enc == QB_BQ_ONE_BIT) {
+                if (v > 0.0f) atomicOr(&dst[i >> 5], 1u << (i & 31));
+            } else {
+                bool b1, b2;
+                bq_two_bits(v, mean_std ? mean_std + 2 * (size_t)i : nullptr, b1, b2);
+                if (b1) atomicOr(&dst[i >> 5], 1u << (i & 31));
+                if (b2) {
+                    const uint32_t jx = (enc == QB_BQ_TWO_BITS) ? dim + i : dim + i / 2;
+                    atomicOr(&dst[jx >> 5], 1u << (jx & 31));
+                }
+            }
+        }
+        return;
+    }
+    // extended query (encode_scalar_query_vector :692-720)
+    uint32_t ext = dim;
+    if (enc == QB_BQ_TWO_BITS) ext = 2 * dim;
+    else if (enc == QB_BQ_ONE_AND_HALF_BITS) ext = dim + (dim + 1) / 2;
+    auto ext_value = [&](uint32_t i) -> float {
+        if (i < dim) return src[i];
+        if (enc == QB_BQ_TWO_BITS) return src[i - dim];
+        const uint32_t k = 2 * (i - dim);
+        return (k + 1 < dim) ? fmaxf(src[k], src[k + 1]) : src[k];
+    };
+    float mx = 0.0f;
+    for (uint32_t i = threadIdx.x; i < ext; i += blockDim.x) mx = fmaxf(mx, fabsf(ext_value(i)));
+    s_max[threadIdx.x] = mx;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + st]);
+        __syncthreads();
+    }
+    const float max_abs = s_max[0];
+    const float mn = -max_abs;
+    const unsigned long long ranges = (1ull << bits) - 1ull;
+    const float delta = __fdiv_rn(__fsub_rn(max_abs, mn), (float)ranges);
+    for (uint32_t i = threadIdx.x; i < ext; i += blockDim.x) {
+        const float shifted = __fsub_rn(ext_value(i), mn);
+        const float delted = (delta > 1.1920929e-07f) ? __fdiv_rn(shifted, delta) : 0.0f;
+        const float rv = roundf(delted);
+        unsigned long long rounded = (rv != rv || rv <= 0.0f) ? 0ull : (rv >= 1.8446744e19f ? 0xFFFFFFFFFFFFFFFFull : (unsigned long long)rv);
+        const unsigned long long quantized = rounded % (ranges + 1ull);
+        const uint32_t chunk = i >> 7, shift = i & 127;
+        for (int b = 0; b < bits; ++b)
+            if ((quantized >> b) & 1ull) {
+                const uint32_t word32 = ((uint32_t)bits * chunk + (uint32_t)b) * 4 + (shift >> 5);
+                atomicOr(&dst[word32], 1u << (shift & 31));
+            }
+    }
+}
+
+struct BqParams {
+    const uint8_t* rows;    // [count][row_bytes]
+    uint32_t row_bytes, dim;
+    int bits;               // 1, 4, 8
+    int is_dot, invert;
+    uint64_t begin, end;
+    const uint32_t* ids;
+    const uint8_t* q_enc;   // [nq][row_bytes*bits]
+    uint32_t nq;
+    float* scores;
+    int emit_mode;
+};
+
+__device__ __forceinline__ unsigned int popc128(uint4 a, uint4 b) {
+    return __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+}
+
+// calculate_metric (encoded_vectors_binary.rs:766-810): 8 lanes per candidate, one u128 word per lane per step
+__global__ void __launch_bounds__(256) bq_group_kernel(const BqParams p, const QbEmit emit) {
+    const int t = threadIdx.x & 7;
+    const uint64_t groups_per_grid = (uint64_t)gridDim.x * (blockDim.x >> 3);
+    const uint64_t g0 = (uint64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    const uint64_t n = p.end - p.begin;
+    const uint64_t n_iter = (n + groups_per_grid - 1) / groups_per_grid;
+    const uint32_t n_words = p.row_bytes >> 4;
+    const float dimf = (float)p.dim;
+    for (uint64_t it = 0; it < n_iter; ++it) {
+        const uint64_t ci = g0 + it * groups_per_grid;
+        const bool valid = ci < n;
+        const uint64_t cand = p.begin + (valid ? ci : 0);
+        const uint32_t row = p.ids ? p.ids[cand] : (uint32_t)cand;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.rows + (size_t)row * p.row_bytes);
+        for (uint32_t q = 0; q < p.nq; ++q) {
+            const uint4* qp = reinterpret_cast<const uint4*>(p.q_enc + (size_t)q * p.row_bytes * p.bits);
+            unsigned int acc = 0;
+            if (p.bits == 1) {
+                for (uint32_t w = t; w < n_words; w += 8) acc += popc128(__ldg(rp + w), __ldg(qp + w));
+            } else {
+                for (uint32_t w = t; w < n_words; w += 8) {
+                    const uint4 v = __ldg(rp + w);
+                    for (int b = 0; b < p.bits; ++b) acc += popc128(v, __ldg(qp + (size_t)w * p.bits + b)) << b;
+                }
+            }
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+            float xr = (float)acc;
+            if (p.bits != 1) xr = __fdiv_rn(xr, (float)((1 << p.bits) - 1));
+            const float zeros = __fsub_rn(dimf, xr);
+            // (Dot, invert) -> xor - zeros ; (Dot, !invert) -> zeros - xor ; (L1/L2, invert) -> zeros - xor ; else xor - zeros
+            const bool zeros_minus_xor = p.is_dot ? !p.invert : (p.invert != 0);
+            const float sc = zeros_minus_xor ? __fsub_rn(zeros, xr) : __fsub_rn(xr, zeros);
+            if (valid && t == 0) {
+                if (p.emit_mode) qb_emit(emit, q, cand, row, sc);
+                else p.scores[(size_t)q * n + ci] = sc;
+            }
+        }
+    }
+}
+
+unsigned grid_for_groups(uint64_t n, int sm_count) {
+    uint64_t blocks = ceil_div_u64(n, 256 / 8);
+    uint64_t maxb = (uint64_t)sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks == 0) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- SQ8 host launchers
+qb_status qb_sq8_repack(const qb_storage* s, const uint8_t* d_rows_in, uint32_t row_bytes, uint64_t first, uint64_t n, cudaStream_t stream) {
+    if (n == 0) return QB_OK;
+    uint64_t total = n * (uint64_t)(s->actual_dim >> 2);
+    uint64_t blocks = ceil_div_u64(total, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    sq8_repack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_rows_in, row_bytes, s->actual_dim, n, s->d_codes + first * s->actual_dim,
+                                                            s->d_voff + first);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+qb_status qb_sq8_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, uint8_t* d_codes, float* d_q_off,
+                                cudaStream_t stream) {
+    if (nq == 0) return QB_OK;
+    sq8_encode_query_kernel<<<nq, 256, 0, stream>>>(d_q_pre, q_stride_f, s->dim, s->actual_dim, s->alpha, s->offset, (int)s->qdist, s->invert,
+                                                    d_codes, d_q_off);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+static float sq8_shift_host(const qb_storage* s) {  // get_shift, encoded_vectors_u8.rs:116-134
+    float shift = 0.0f;
+    if (s->qdist == QB_QD_DOT || s->qdist == QB_QD_COSINE) {
+        volatile float a = (float)s->actual_dim * s->offset;
+        shift = a * s->offset;
+    }
+    return s->invert ? -shift : shift;
+}
+
+qb_status qb_sq8_internal_query(const qb_storage* s, uint32_t id, uint8_t* d_code, float* d_q_off, cudaStream_t stream) {
+    sq8_internal_query_kernel<<<1, 256, 0, stream>>>(s->d_codes, s->d_voff, s->actual_dim, id, sq8_shift_host(s), d_code, d_q_off);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+static qb_status sq8_launch(const qb_storage* s, Sq8Params& p, const QbEmit& e, cudaStream_t stream) {
+    const uint64_t n = p.end - p.begin;
+    if (n == 0 || p.nq == 0) return QB_OK;
+    p.codes = s->d_codes; p.voff = s->d_voff; p.ad = s->actual_dim; p.multiplier = s->multiplier;
+    p.l1 = (s->qdist == QB_QD_L1) ? 1 : 0;
+    const bool lanex = (uint64_t)s->actual_dim * 127ull * 127ull >= (1ull << 24);
+    if (lanex) sq8_group_kernel<true><<<grid_for_groups(n, s->sm_count), 256, 0, stream>>>(p, e);
+    else sq8_group_kernel<false><<<grid_for_groups(n, s->sm_count), 256, 0, stream>>>(p, e);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+qb_status qb_sq8_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream) {
+    Sq8Params p{};
+    p.begin = a.row_begin; p.end = a.row_end; p.ids = a.d_ids;
+    p.q_codes = reinterpret_cast<const uint8_t*>(a.d_q_enc); p.q_off = a.d_q_off; p.nq = a.nq;
+    p.scores = nullptr; p.emit_mode = 1;
+    return sq8_launch(s, p, a.emit, stream);
+}
+
+qb_status qb_sq8_score_points(const qb_storage* s, const void* d_q_enc, const float* d_q_off, const uint32_t* d_ids, uint64_t n, float* d_scores,
+                              cudaStream_t stream) {
+    Sq8Params p{};
+    p.begin = 0; p.end = n; p.ids = d_ids;
+    p.q_codes = reinterpret_cast<const uint8_t*>(d_q_enc); p.q_off = d_q_off; p.nq = 1;
+    p.scores = d_scores; p.emit_mode = 0;
+    QbEmit e{};
+    return sq8_launch(s, p, e, stream);
+}
+
+// ---------------------------------------------------------------- PQ host launchers
+qb_status qb_pq_build_luts(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, float* d_luts, cudaStream_t stream) {
+    if (nq == 0) return QB_OK;
+    dim3 grid(s->pq_m, nq);
+    pq_lut_kernel<<<grid, 256, 0, stream>>>(d_q_pre, q_stride_f, s->dim, s->pq_m, s->d_pq_div, s->d_centroids, s->n_centroids, (int)s->qdist,
+                                            s->invert, d_luts);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cudaStream_t stream) {
+    const uint64_t n = p.end - p.begin;
+    if (n == 0 || p.nq == 0) return QB_OK;
+    p.codes = s->d_pq_codes; p.stride = s->pq_stride; p.m = s->pq_m; p.n_centroids = s->n_centroids;
+    const size_t lut_bytes = (size_t)s->pq_m * s->n_centroids * sizeof(float);
+    p.lut_in_smem = (lut_bytes <= 200 * 1024 && n >= 4096) ? 1 : 0;
+    const size_t smem = p.lut_in_smem ? lut_bytes : 0;
+    if (smem > 48 * 1024) QB_CUDA(cudaFuncSetAttribute(pq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    uint64_t blocks = ceil_div_u64(n, 512);
+    uint64_t maxb = p.lut_in_smem ? (uint64_t)s->sm_count * (smem > 100 * 1024 ? 1 : 2) : (uint64_t)s->sm_count * 4;
+    if (blocks > maxb) blocks = maxb;
+    pq_scan_kernel<<<(unsigned)blocks, 512, smem, stream>>>(p, e);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+qb_status qb_pq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream) {
+    PqParams p{};
+    p.begin = a.row_begin; p.end = a.row_end; p.ids = a.d_ids;
+    p.luts = reinterpret_cast<const float*>(a.d_q_enc); p.nq = a.nq;
+    p.scores = nullptr; p.emit_mode = 1;
+    return pq_launch(s, p, a.emit, stream);
+}
+
+qb_status qb_pq_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream) {
+    PqParams p{};
+    p.begin = 0; p.end = n; p.ids = d_ids;
+    p.luts = reinterpret_cast<const float*>(d_q_enc); p.nq = 1;
+    p.scores = d_scores; p.emit_mode = 0;
+    QbEmit e{};
+    return pq_launch(s, p, e, stream);
+}
+
+qb_status qb_pq_score_internal(const qb_storage* s, uint32_t a, uint32_t b, float* d_out, cudaStream_t stream) {
+    pq_score_internal_kernel<<<1, 32, 0, stream>>>(s->d_pq_codes, s->pq_stride, s->pq_m, s->d_pq_div, s->d_centroids, s->dim, (int)s->qdist,
+                                                   s->invert, a, b, d_out);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+// ---------------------------------------------------------------- BQ host launchers
+static int bq_bits(const qb_storage* s) { return s->bq_qenc == QB_BQQ_SCALAR4 ? 4 : (s->bq_qenc == QB_BQQ_SCALAR8 ? 8 : 1); }
+
+qb_status qb_bq_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, int force_binary, void* d_out,
+                               cudaStream_t stream) {
+    if (nq == 0) return QB_OK;
+    const int bits = force_binary ? 1 : bq_bits(s);
+    bq_encode_query_kernel<<<nq, 256, 0, stream>>>(d_q_pre, q_stride_f, s->dim, (int)s->bq_enc, bits, s->d_mean_std, s->bq_row_bytes,
+                                                   reinterpret_cast<uint32_t*>(d_out));
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+static qb_status bq_launch(const qb_storage* s, BqParams& p, const QbEmit& e, cudaStream_t stream) {
+    const uint64_t n = p.end - p.begin;
+    if (n == 0 || p.nq == 0) return QB_OK;
+    p.rows = s->d_bq_rows; p.row_bytes = s->bq_row_bytes; p.dim = s->dim;
+    p.is_dot = (s->qdist == QB_QD_DOT || s->qdist == QB_QD_COSINE) ? 1 : 0;
+    p.invert = s->invert;
+    bq_group_kernel<<<grid_for_groups(n, s->sm_count), 256, 0, stream>>>(p, e);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream) {
+    BqParams p{};
+    p.bits = bq_bits(s);
+    p.begin = a.row_begin; p.end = a.row_end; p.ids = a.d_ids;
+    p.q_enc = reinterpret_cast<const uint8_t*>(a.d_q_enc); p.nq = a.nq;
+    p.scores = nullptr; p.emit_mode = 1;
+    return bq_launch(s, p, a.emit, stream);
+}
+
+qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores,
+                             cudaStream_t stream) {
+    BqParams p{};
+    p.bits = bits;
+    p.begin = 0; p.end = n; p.ids = d_ids;
+    p.q_enc = reinterpret_cast<const uint8_t*>(d_q_enc); p.nq = 1;
+    p.scores = d_scores; p.emit_mode = 0;
+    QbEmit e{};
+    return bq_launch(s, p, e, stream);
+}

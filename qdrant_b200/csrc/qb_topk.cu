@@ -1,0 +1,167 @@
+// qb_topk.cu — per-query top-k selection over candidate key lists.
+//
+// Replaces the reference's FixedLengthPriorityQueue<ScoredPointOffset> (binary min-heap of size `top`,
+// lib/common/common/src/fixed_length_priority_queue.rs:20-65) + into_sorted_vec (descending).  A heap is a
+// serial structure; on the GPU the scan kernels emit 64-bit keys (score-major, id-minor, qb_common.cuh) and
+// this file selects the k largest per query:
+//     n <= 4096 : load into shared memory, bitonic sort, take the first k
+//     n  > 4096 : 8-pass MSB radix select for the exact k-th key, gather keys >= it, bitonic sort those
+// Keys are unique (ids are), so the result is deterministic: (score desc, id asc).
+#include "qb_internal.h"
+
+namespace {
+
+constexpr int SORT_CAP = 4096;
+
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* buf, int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = buf[i], b = buf[ixj];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) { buf[i] = b; buf[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(QB_SELECT_THREADS)
+qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned long long cap,
+                 unsigned long long fixed_n, uint32_t top, int mode, qb_scored_point* __restrict__ out,
+                 uint32_t* __restrict__ out_counts, float* __restrict__ thr, unsigned int* __restrict__ overflow) {
+    __shared__ unsigned long long buf[SORT_CAP];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_kk, s_fill, s_short;
+
+    const uint32_t q = blockIdx.x;
+    unsigned long long n;
+    if (fixed_n) {
+        n = fixed_n;
+    } else {
+        unsigned int c = cnt[q];
+        if (c > cap) {
+            if (threadIdx.x == 0 && overflow) atomicExch(overflow, 1u);
+            c = (unsigned int)cap;
+        }
+        n = c;
+    }
+    const unsigned long long* keys = cand + (unsigned long long)q * cap;
+    int m = 0;  // number of keys staged in buf
+
+    if (n <= SORT_CAP) {
+        for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = (i < (int)n) ? keys[i] : 0ull;
+        m = (int)n;
+        __syncthreads();
+    } else {
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_kk = top; s_short = 0u; }
+        unsigned long long mask = 0ull;
+        __syncthreads();
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            for (unsigned long long i0 = 0; i0 < n; i0 += blockDim.x) {
+                unsigned long long i = i0 + threadIdx.x;
+                bool valid = false;
+                unsigned int digit = 0xFFFFFFFFu;
+                if (i < n) {
+                    unsigned long long key = keys[i];
+                    if ((key & mask) == prefix) { valid = true; digit = (unsigned int)((key >> shift) & 255ull); }
+                }
+                // warp-aggregated histogram update: keys share high bytes, so plain atomics would serialise
+                unsigned int peers = __match_any_sync(0xFFFFFFFFu, digit);
+                if (valid && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int kk = s_kk, cum = 0;
+                int d = 255;
+                for (; d >= 0; --d) {
+                    unsigned int h = hist[d];
+                    if (cum + h >= kk) break;
+                    cum += h;
+                }
+                if (d < 0) { s_short = 1u; d = 0; cum = 0; }  // fewer than `top` keys in total
+                else s_kk = kk - cum;
+                s_prefix = prefix | ((unsigned long long)d << shift);
+            }
+            mask |= (255ull << shift);
+            __syncthreads();
+            if (s_short) break;
+        }
+        const unsigned long long kth = s_short ? 1ull : s_prefix;  // short: take every non-empty key
+        if (threadIdx.x == 0) s_fill = 0u;
+        for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = 0ull;
+        __syncthreads();
+        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+            unsigned long long key = keys[i];
+            if (key >= kth && key != 0ull) {
+                unsigned int p = atomicAdd(&s_fill, 1u);
+                if (p < SORT_CAP) buf[p] = key;
+            }
+        }
+        __syncthreads();
+        m = (int)min(s_fill, (unsigned int)SORT_CAP);
+    }
+
+    int p2 = 32;
+    while (p2 < m) p2 <<= 1;
+    bitonic_sort_desc(buf, p2);
+
+    if (mode == 1) {
+        if (threadIdx.x == 0) {
+            unsigned long long k = (top <= (uint32_t)SORT_CAP && top >= 1 && (int)top <= m) ? buf[top - 1] : 0ull;
+            thr[q] = (k == 0ull) ? __int_as_float(0xff800000) : qb_key_score(k);
+        }
+        return;
+    }
+    // mode 0: write results; count = number of non-empty keys among the first `top`
+    unsigned int valid = 0;
+    for (int i = threadIdx.x; i < (int)top; i += blockDim.x) {
+        unsigned long long k = (i < m) ? buf[i] : 0ull;
+        qb_scored_point sp;
+        if (k != 0ull) { sp.idx = qb_key_id(k); sp.score = qb_key_score(k); valid++; }
+        else { sp.idx = 0; sp.score = 0.0f; }
+        out[(unsigned long long)q * top + i] = sp;
+    }
+    // block-reduce `valid`
+    __shared__ unsigned int s_valid;
+    if (threadIdx.x == 0) s_valid = 0u;
+    __syncthreads();
+    if (valid) atomicAdd(&s_valid, valid);
+    __syncthreads();
+    if (threadIdx.x == 0) out_counts[q] = s_valid;
+}
+
+__global__ void qb_fill_u32_kernel(unsigned int* p, unsigned int v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+qb_status qb_launch_select(const unsigned long long* d_cand, const unsigned int* d_cnt, unsigned long long cap,
+                           unsigned long long fixed_n, uint32_t nq, uint32_t top, int mode, qb_scored_point* d_out,
+                           uint32_t* d_out_counts, float* d_thr, unsigned int* d_overflow, cudaStream_t stream) {
+    QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_UNSUPPORTED, "top=%u outside [1,%u]", top, QB_MAX_TOP);
+    if (nq == 0) return QB_OK;
+    qb_select_kernel<<<nq, QB_SELECT_THREADS, 0, stream>>>(d_cand, d_cnt, cap, fixed_n, top, mode, d_out, d_out_counts, d_thr,
+                                                          d_overflow);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+qb_status qb_launch_fill_u32(unsigned int* p, unsigned int v, size_t n, cudaStream_t stream) {
+    if (n == 0) return QB_OK;
+    qb_fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, v, n);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}

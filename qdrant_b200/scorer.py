@@ -1,0 +1,415 @@
+"""Host-side mirror of the reference's scorer interface, over the C ABI (include/qb200.h).
+
+Same names, argument meaning and error behaviour as lib/segment:
+    Distance                         lib/segment/src/types.rs:313-370
+    RawScorer                        lib/segment/src/vector_storage/raw_scorer.rs:39-54
+    RawScorerBuilder.build_raw_scorer                               raw_scorer.rs:122-128
+    QuantizedVectorsRead.raw_scorer / raw_internal_scorer           quantized/quantized_vectors/read_access.rs:26-34
+    FilteredScorer                   lib/segment/src/index/hnsw_index/point_scorer.rs:53-58,160-304
+    BatchFilteredSearcher            point_scorer.rs:312-472
+    get_oversampled_top / postprocess_search_result                 index/vector_index_search_common.rs:27-91
+All scoring happens in libqdrant_b200.so on the GPU; this file holds no arithmetic (numpy is used for buffers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import HwCounters, QbError, ScoredPoint, check, f32p, i32p, lib, u8p, u32p, u64p, vp
+
+SCORED_POINT_OFFSET = np.dtype([("idx", np.uint32), ("score", np.float32)])  # #[repr(C)] ScoredPointOffset
+VECTOR_READ_BATCH_SIZE = 64  # lib/segment/src/vector_storage/common.rs:20
+
+
+class Distance(enum.IntEnum):
+    Cosine = 0
+    Euclid = 1
+    Dot = 2
+    Manhattan = 3
+
+    def postprocess_score(self, score: float) -> float:
+        """Distance::postprocess_score (types.rs:349-358) — applied at shard level for Nearest queries."""
+        return float(lib().qb_metric_postprocess(int(self), C.c_float(score)))
+
+
+class VectorStorageDatatype(enum.IntEnum):
+    Float32 = 0
+    Float16 = 1
+    Uint8 = 2
+
+
+class DistanceType(enum.IntEnum):  # quantization::DistanceType
+    Cosine = 0
+    Dot = 1
+    L1 = 2
+    L2 = 3
+
+
+class BQEncoding(enum.IntEnum):
+    OneBit = 0
+    TwoBits = 1
+    OneAndHalfBits = 2
+
+
+class BQQueryEncoding(enum.IntEnum):
+    SameAsStorage = 0
+    Scalar4bits = 1
+    Scalar8bits = 2
+
+
+def construct_vector_parameters(distance: Distance) -> tuple[DistanceType, bool]:
+    """construct_vector_parameters (quantized_vectors.rs:205-234): Cosine -> Dot; invert = Euclid | Manhattan."""
+    dt = {Distance.Cosine: DistanceType.Dot, Distance.Dot: DistanceType.Dot, Distance.Euclid: DistanceType.L2,
+          Distance.Manhattan: DistanceType.L1}[distance]
+    return dt, distance in (Distance.Euclid, Distance.Manhattan)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ids(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _bitmap(point_deleted, count: int) -> Optional[np.ndarray]:
+    """bool mask / BitSlice -> u64 words, bit i set = point i deleted."""
+    if point_deleted is None:
+        return None
+    m = np.asarray(point_deleted)
+    if m.dtype == np.uint64:
+        return np.ascontiguousarray(m)
+    bits = np.zeros(((count + 63) // 64) * 64, dtype=bool)
+    bits[: m.size] = m.astype(bool)
+    return np.packbits(bits, bitorder="little").view(np.uint64).copy()
+
+
+def metric_preprocess(distance: Distance, vectors, device: int = 0) -> np.ndarray:
+    """Metric::preprocess for a batch (cosine normalisation at insert time, types.rs:334-347)."""
+    v = np.atleast_2d(_f32(vectors))
+    out = np.empty_like(v)
+    check(lib().qb_metric_preprocess(device, int(distance), v.shape[1], v.shape[0], v.ctypes.data_as(f32p), out.ctypes.data_as(f32p)))
+    return out.reshape(np.shape(vectors))
+
+
+class RawScorer:
+    """Box<dyn RawScorer>.  Scoring calls are infallible in the reference; here a CUDA failure raises QbError."""
+
+    def __init__(self, storage: "_Storage", handle: int):
+        self._storage = storage  # keeps the borrow alive ('a)
+        self._h = vp(handle)
+
+    def score_points(self, points: Sequence[int], scores: Optional[np.ndarray] = None) -> np.ndarray:
+        ids = _ids(points)
+        if scores is None:
+            scores = np.empty(ids.size, dtype=np.float32)
+        assert scores.size == ids.size  # raw_scorer.rs:562
+        check(lib().qb_score_points(self._h, ids.ctypes.data_as(u32p), ids.size, scores.ctypes.data_as(f32p)))
+        return scores
+
+    def score_point(self, point: int) -> float:
+        s = C.c_float()
+        check(lib().qb_score_point(self._h, int(point), C.byref(s)))
+        return np.float32(s.value)
+
+    def score_internal(self, point_a: int, point_b: int) -> float:
+        s = C.c_float()
+        st = lib().qb_score_internal(self._h, int(point_a), int(point_b), C.byref(s))
+        if st == _capi.QB_ERR_INVALID:
+            raise IndexError(lib().qb_last_error().decode())  # "Panics if any id is out of range"
+        check(st)
+        return np.float32(s.value)
+
+    def scorer_bytes(self):
+        return None  # a GPU scorer has no QueryScorerBytes view
+
+    def take_hardware_counters(self) -> tuple[int, int]:
+        hc = HwCounters()
+        check(lib().qb_scorer_take_counters(self._h, C.byref(hc)))
+        return int(hc.cpu), int(hc.vector_io_read)
+
+    def close(self):
+        if self._h:
+            lib().qb_scorer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Storage:
+    def __init__(self):
+        self._h = vp()
+        self.count = 0
+        self.dim = 0
+        self.device = 0
+
+    def _raw_scorer(self, query) -> RawScorer:
+        q = _f32(query)
+        if q.size != self.dim:
+            raise ValueError(f"query has dim {q.size}, storage has {self.dim}")  # OperationError at construction
+        h = vp()
+        check(lib().qb_scorer_create(self._h, q.ctypes.data_as(f32p), C.byref(h)))
+        return RawScorer(self, h.value)
+
+    def _raw_internal_scorer(self, point_id: int) -> RawScorer:
+        h = vp()
+        check(lib().qb_scorer_create_internal(self._h, int(point_id), C.byref(h)))
+        return RawScorer(self, h.value)
+
+    def set_deleted(self, point_deleted) -> None:
+        bm = _bitmap(point_deleted, self.count)
+        if bm is None:
+            check(lib().qb_storage_set_deleted(self._h, None, 0))
+        else:
+            check(lib().qb_storage_set_deleted(self._h, bm.ctypes.data_as(u64p), bm.size))
+
+    def hbm_bytes(self) -> int:
+        b = C.c_uint64()
+        check(lib().qb_storage_info(self._h, None, None, C.byref(b)))
+        return int(b.value)
+
+    def stream_ptr(self) -> int:
+        return int(lib().qb_storage_stream(self._h) or 0)
+
+    def profile(self, on: bool) -> None:
+        check(lib().qb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> tuple[int, float]:
+        n, ms = C.c_uint64(), C.c_double()
+        check(lib().qb_profile_read(self._h, C.byref(n), C.byref(ms), 1 if reset else 0))
+        return int(n.value), float(ms.value)
+
+    def search_batch(self, queries, top: int, point_deleted=None, id_list=None, is_stopped=None, counters: Optional[HwCounters] = None):
+        """Fused BatchFilteredSearcher scan -> list (one per query) of SCORED_POINT_OFFSET arrays, descending."""
+        q = np.atleast_2d(_f32(queries))
+        if q.shape[1] != self.dim:
+            raise ValueError(f"queries have dim {q.shape[1]}, storage has {self.dim}")
+        nq = q.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED_POINT_OFFSET)
+        counts = np.zeros(nq, dtype=np.uint32)
+        bm = _bitmap(point_deleted, self.count)
+        ids = None if id_list is None else _ids(id_list)
+        stop = None
+        if is_stopped is not None:
+            stop = is_stopped if isinstance(is_stopped, C.c_int32) else C.c_int32(int(bool(is_stopped)))
+        check(lib().qb_search_batch(
+            self._h, q.ctypes.data_as(f32p), nq, int(top),
+            None if bm is None else bm.ctypes.data_as(u64p),
+            None if ids is None else ids.ctypes.data_as(u32p), 0 if ids is None else ids.size,
+            None if stop is None else C.byref(stop),
+            out.ctypes.data_as(C.POINTER(ScoredPoint)), counts.ctypes.data_as(u32p),
+            None if counters is None else C.byref(counters)))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
+
+    def close(self):
+        if self._h:
+            lib().qb_storage_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DenseVectorStorage(_Storage):
+    """A segment's dense vectors resident in HBM (the GPU copy is a cache of VectorStorageEnum's rows)."""
+
+    def __init__(self, vectors, distance: Distance, datatype: VectorStorageDatatype = VectorStorageDatatype.Float32, device: int = 0,
+                 count: Optional[int] = None, dim: Optional[int] = None):
+        super().__init__()
+        self.distance, self.datatype, self.device = Distance(distance), VectorStorageDatatype(datatype), device
+        np_dt = {VectorStorageDatatype.Float32: np.float32, VectorStorageDatatype.Float16: np.float16, VectorStorageDatatype.Uint8: np.uint8}[self.datatype]
+        if vectors is None:
+            self.count, self.dim = int(count), int(dim)
+            ptr, stride = None, 0
+        else:
+            v = np.ascontiguousarray(vectors, dtype=np_dt)
+            assert v.ndim == 2
+            self.count, self.dim = v.shape
+            ptr, stride = v.ctypes.data_as(vp), v.strides[0]
+        check(lib().qb_storage_create_dense(device, int(self.datatype), int(self.distance), self.dim, self.count, ptr, stride, C.byref(self._h)))
+
+    # RawScorerBuilder
+    def build_raw_scorer(self, query) -> RawScorer:
+        return self._raw_scorer(query)
+
+    def raw_internal_scorer(self, point_id: int) -> RawScorer:
+        return self._raw_internal_scorer(point_id)
+
+    def write_rows_device(self, first_row: int, n_rows: int, dev_ptr: int, row_stride_bytes: int = 0) -> None:
+        check(lib().qb_storage_write_rows_device(self._h, first_row, n_rows, vp(dev_ptr), row_stride_bytes))
+
+    def write_rows(self, first_row: int, rows) -> None:
+        r = np.ascontiguousarray(rows)
+        check(lib().qb_storage_write_rows(self._h, first_row, r.shape[0], r.ctypes.data_as(vp), r.strides[0]))
+
+    def get_dense(self, ids) -> np.ndarray:
+        ids = _ids(ids)
+        np_dt = {VectorStorageDatatype.Float32: np.float32, VectorStorageDatatype.Float16: np.float16, VectorStorageDatatype.Uint8: np.uint8}[self.datatype]
+        out = np.empty((ids.size, self.dim), dtype=np_dt)
+        check(lib().qb_storage_read_rows(self._h, ids.ctypes.data_as(u32p), ids.size, out.ctypes.data_as(vp)))
+        return out
+
+
+class ScalarQuantizedVectors(_Storage):
+    """QuantizedVectors backed by EncodedVectorsU8: `rows` is quantized.data ([f32 v_off][actual_dim u8] per row)."""
+
+    def __init__(self, rows, dim: int, alpha: float, offset: float, multiplier: float, distance: Distance, device: int = 0):
+        super().__init__()
+        r = np.ascontiguousarray(rows, dtype=np.uint8)
+        self.count, self.dim, self.device, self.distance = r.shape[0], int(dim), device, Distance(distance)
+        dt, invert = construct_vector_parameters(self.distance)
+        check(lib().qb_storage_create_sq8(device, self.dim, self.count, r.ctypes.data_as(u8p), r.shape[1] if r.ndim == 2 else 0, C.c_float(alpha),
+                                          C.c_float(offset), C.c_float(multiplier), int(dt), int(invert), int(self.distance), C.byref(self._h)))
+
+    def raw_scorer(self, query) -> RawScorer:
+        return self._raw_scorer(query)
+
+    def raw_internal_scorer(self, point_id: int) -> RawScorer:
+        return self._raw_internal_scorer(point_id)
+
+
+class ProductQuantizedVectors(_Storage):
+    def __init__(self, codes, centroids, chunk: int, dim: int, distance: Distance, device: int = 0):
+        super().__init__()
+        c = np.ascontiguousarray(codes, dtype=np.uint8)
+        cent = _f32(centroids)
+        self.count, self.dim, self.device, self.distance = c.shape[0], int(dim), device, Distance(distance)
+        starts = np.arange(0, dim, chunk, dtype=np.uint32)  # get_vector_division, encoded_vectors_pq.rs:164-169
+        div = np.stack([starts, np.minimum(starts + chunk, dim).astype(np.uint32)], axis=1).astype(np.uint32).copy()
+        self.m = div.shape[0]
+        assert c.shape[1] == self.m
+        dt, invert = construct_vector_parameters(self.distance)
+        check(lib().qb_storage_create_pq(device, self.dim, self.m, div.ctypes.data_as(u32p), cent.ctypes.data_as(f32p), cent.shape[0],
+                                         c.ctypes.data_as(u8p), self.count, int(dt), int(invert), int(self.distance), C.byref(self._h)))
+
+    def raw_scorer(self, query) -> RawScorer:
+        return self._raw_scorer(query)
+
+    def raw_internal_scorer(self, point_id: int) -> RawScorer:
+        """InternalScorerUnsupported for PQ (quantized_query_scorer.rs:60-66): raises QbError(QB_ERR_UNSUPPORTED)."""
+        return self._raw_internal_scorer(point_id)
+
+
+class BinaryQuantizedVectors(_Storage):
+    def __init__(self, rows, dim: int, distance: Distance, encoding: BQEncoding = BQEncoding.OneBit,
+                 query_encoding: BQQueryEncoding = BQQueryEncoding.SameAsStorage, mean_std=None, device: int = 0):
+        super().__init__()
+        r = np.ascontiguousarray(rows, dtype=np.uint8)
+        self.count, self.dim, self.device, self.distance = r.shape[0], int(dim), device, Distance(distance)
+        dt, invert = construct_vector_parameters(self.distance)
+        ms = None if mean_std is None else _f32(mean_std)
+        check(lib().qb_storage_create_bq(device, self.dim, int(encoding), int(query_encoding), r.ctypes.data_as(u8p), r.shape[1], self.count, int(dt),
+                                         int(invert), None if ms is None else ms.ctypes.data_as(f32p), int(self.distance), C.byref(self._h)))
+
+    def raw_scorer(self, query) -> RawScorer:
+        return self._raw_scorer(query)
+
+    def raw_internal_scorer(self, point_id: int) -> RawScorer:
+        return self._raw_internal_scorer(point_id)
+
+
+class FilteredScorer:
+    """point_scorer.rs:53-58: a RawScorer plus the deleted-points filter; score_points clobbers and truncates `ids`."""
+
+    def __init__(self, raw_scorer: RawScorer, point_deleted=None, filter_fn=None):
+        self.raw_scorer = raw_scorer
+        self.point_deleted = None if point_deleted is None else np.asarray(point_deleted, dtype=bool)
+        self.filter_fn = filter_fn
+
+    @classmethod
+    def new(cls, query, vectors: _Storage, quantized_vectors: Optional[_Storage] = None, point_deleted=None, filter_fn=None):
+        # point_scorer.rs:172-175
+        rs = quantized_vectors.raw_scorer(query) if quantized_vectors is not None else vectors.build_raw_scorer(query)
+        return cls(rs, point_deleted, filter_fn)
+
+    @classmethod
+    def new_internal(cls, point_id: int, vectors: _Storage, quantized_vectors: Optional[_Storage] = None, point_deleted=None):
+        # point_scorer.rs:183-218: fall back to the original vectors when the quantizer cannot build an internal scorer (PQ)
+        rs = None
+        if quantized_vectors is not None:
+            try:
+                rs = quantized_vectors.raw_internal_scorer(point_id)
+            except QbError as e:
+                if e.status != _capi.QB_ERR_UNSUPPORTED:
+                    raise
+        if rs is None:
+            rs = vectors.raw_internal_scorer(point_id)
+        return cls(rs, point_deleted)
+
+    def check_vector(self, point_id: int) -> bool:
+        if self.point_deleted is not None and point_id < self.point_deleted.size and self.point_deleted[point_id]:
+            return False
+        return self.filter_fn is None or bool(self.filter_fn(point_id))
+
+    def score_points(self, point_ids: list, limit: int = 0) -> np.ndarray:
+        """point_scorer.rs:265-295 -> array of ScoredPointOffset for the ids that passed the filters."""
+        kept = [p for p in point_ids if self.check_vector(p)]
+        if limit:
+            kept = kept[:limit]
+        point_ids[:] = kept
+        out = np.zeros(len(kept), dtype=SCORED_POINT_OFFSET)
+        if kept:
+            out["idx"] = kept
+            out["score"] = self.raw_scorer.score_points(kept)
+        return out
+
+    def score_point(self, point_id: int) -> float:
+        return self.raw_scorer.score_point(point_id)
+
+    def score_internal(self, a: int, b: int) -> float:
+        return self.raw_scorer.score_internal(a, b)
+
+
+class BatchFilteredSearcher:
+    """point_scorer.rs:312-472.  The reference keeps one RawScorer + one heap per query and walks 64-id chunks;
+    here the whole scan + top-k is ONE fused call into the library (qb_search_batch)."""
+
+    def __init__(self, queries, storage: _Storage, top: int, point_deleted=None):
+        self.queries = np.atleast_2d(_f32(queries))
+        self.storage = storage
+        self.top = int(top)
+        self.point_deleted = point_deleted
+        if self.top == 0:
+            raise ValueError("length must be greater than zero")  # FixedLengthPriorityQueue::new expect()
+
+    @classmethod
+    def new(cls, queries, vectors: _Storage, quantized_vectors: Optional[_Storage], top: int, point_deleted=None):
+        return cls(queries, quantized_vectors if quantized_vectors is not None else vectors, top, point_deleted)
+
+    def peek_top_all(self, is_stopped=None):
+        return self.storage.search_batch(self.queries, self.top, point_deleted=self.point_deleted, is_stopped=is_stopped)
+
+    def peek_top_iter(self, points: Iterable[int], is_stopped=None):
+        ids = _ids(list(points))
+        return self.storage.search_batch(self.queries, self.top, point_deleted=self.point_deleted, id_list=ids, is_stopped=is_stopped)
+
+
+def get_oversampled_top(top: int, quantized: bool, oversampling: Optional[float]) -> int:
+    """vector_index_search_common.rs:27-45."""
+    if quantized and oversampling is not None and oversampling > 1.0:
+        return int(oversampling * top)
+    return top
+
+
+def postprocess_search_result(search_result: np.ndarray, original: DenseVectorStorage, query, top: int, rescore: bool) -> np.ndarray:
+    """vector_index_search_common.rs:48-91: optionally rescore the candidates with the original vectors, sort desc, truncate."""
+    if not rescore:
+        return search_result[:top].copy()
+    sc = original.build_raw_scorer(query)
+    ids = _ids(search_result["idx"])
+    out = np.zeros(max(top, 1), dtype=SCORED_POINT_OFFSET)
+    n = C.c_uint32()
+    check(lib().qb_rescore(sc._h, ids.ctypes.data_as(u32p), ids.size, int(top), out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(n)))
+    sc.close()
+    return out[: n.value].copy()

@@ -1,0 +1,107 @@
+"""Multi-GPU brute-force search: one process per GPU, rows sharded by contiguous ranges.
+
+The reference searches independent segments on separate blocking tasks and merges their top-k lists on the host
+(SegmentsSearcher, lib/collection/src/collection_manager/segments_searcher.rs:212-345 -> BatchResultAggregator,
+lib/shard/src/search_result_aggregator.rs:50-117).  Here every rank holds one shard in HBM, runs the fused scan
+locally, and the ONLY exchange is an all-gather of `n_queries x top x 8 B` per rank over NCCL/NVLink, followed by
+a device-side merge (qb_topk_merge_device).  torch is used for device buffers, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._capi import check, lib, vp
+from .scorer import SCORED_POINT_OFFSET, _Storage
+
+
+def shard_ranges(n_rows: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous row ranges per rank (whole-segment granularity in the reference); the first n_rows % world ranks
+    get one extra row.  Range r is [begin, end); its id_base is begin."""
+    base, extra = divmod(int(n_rows), int(world))
+    out, b = [], 0
+    for r in range(world):
+        e = b + base + (1 if r < extra else 0)
+        out.append((b, e))
+        b = e
+    return out
+
+
+def merge_topk_host(lists, top: int) -> np.ndarray:
+    """Host-side BatchResultAggregator for one query: k-way merge of per-shard descending lists, ordered like the
+    device merge (score desc, id asc).  Used when results are already on the host (qb_search_batch per shard)."""
+    allp = np.concatenate([np.asarray(l, dtype=SCORED_POINT_OFFSET) for l in lists]) if len(lists) else np.zeros(0, SCORED_POINT_OFFSET)
+    if allp.size == 0:
+        return allp
+    order = np.lexsort((allp["idx"], -allp["score"].astype(np.float64)))
+    return allp[order][:top].copy()
+
+
+class ShardedSegmentSearcher:
+    def __init__(self, storage: _Storage, id_base: int, top: int, max_queries: int, device: torch.device):
+        self.storage, self.top, self.max_queries, self.device = storage, int(top), int(max_queries), device
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        check(lib().qb_storage_set_id_base(storage._h, int(id_base)))
+        self.stream = torch.cuda.ExternalStream(storage.stream_ptr(), device=device)
+        nq, k, w = self.max_queries, self.top, self.world
+        # ScoredPointOffset = 8 bytes -> int64 tensors as opaque 8-byte records
+        self.d_queries = torch.empty((nq, storage.dim), dtype=torch.float32, device=device)
+        self.d_local = torch.empty((nq, k), dtype=torch.int64, device=device)
+        self.d_local_cnt = torch.empty((nq,), dtype=torch.int32, device=device)
+        self.d_all = torch.empty((w, nq, k), dtype=torch.int64, device=device)
+        self.d_all_cnt = torch.empty((w, nq), dtype=torch.int32, device=device)
+        self.d_out = torch.empty((nq, k), dtype=torch.int64, device=device)
+        self.d_out_cnt = torch.empty((nq,), dtype=torch.int32, device=device)
+        self.d_scratch = torch.empty((nq * w * k,), dtype=torch.int64, device=device)
+        self.h_queries = torch.empty((nq, storage.dim), dtype=torch.float32).pin_memory()
+        self.h_out = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        self.h_out_cnt = torch.empty((nq,), dtype=torch.int32).pin_memory()
+
+    # ---- device-resident step: queries already in self.d_queries[:nq]; results land in self.d_out / d_out_cnt
+    def search_device(self, nq: int) -> None:
+        with torch.cuda.stream(self.stream):
+            check(lib().qb_search_batch_device(self.storage._h, vp(self.d_queries.data_ptr()), nq, self.top,
+                                               vp(self.d_local.data_ptr()), vp(self.d_local_cnt.data_ptr())))
+            if self.world == 1:
+                self.d_out[:nq].copy_(self.d_local[:nq], non_blocking=True)
+                self.d_out_cnt[:nq].copy_(self.d_local_cnt[:nq], non_blocking=True)
+                return
+            # one collective per batch: gather every rank's local top-k (k x 8 B per query) over NVLink
+            dist.all_gather_into_tensor(self.d_all.view(-1), self.d_local.view(-1))
+            dist.all_gather_into_tensor(self.d_all_cnt.view(-1), self.d_local_cnt.view(-1))
+            check(lib().qb_topk_merge_device(self.device.index, vp(self.d_all.data_ptr()), vp(self.d_all_cnt.data_ptr()), self.world,
+                                             self.max_queries, self.top, vp(self.d_out.data_ptr()), vp(self.d_out_cnt.data_ptr()),
+                                             vp(self.d_scratch.data_ptr()), self.d_scratch.numel() * 8, vp(self.stream.cuda_stream)))
+
+    # ---- end-to-end call: host queries in, host results out (H2D + D2H inside)
+    def search(self, queries: np.ndarray):
+        q = np.atleast_2d(np.ascontiguousarray(queries, dtype=np.float32))
+        nq = q.shape[0]
+        assert nq <= self.max_queries
+        if self.world == 1:
+            return self.storage.search_batch(q, self.top)  # the plain C-ABI call (qb_search_batch)
+        self.h_queries[:nq].copy_(torch.from_numpy(q))
+        with torch.cuda.stream(self.stream):
+            self.d_queries[:nq].copy_(self.h_queries[:nq], non_blocking=True)
+        self.search_device(nq)
+        with torch.cuda.stream(self.stream):
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            self.h_out_cnt.copy_(self.d_out_cnt, non_blocking=True)
+        self.stream.synchronize()
+        rec = self.h_out.numpy().view(SCORED_POINT_OFFSET).reshape(self.max_queries, self.top)
+        cnt = self.h_out_cnt.numpy()
+        return [rec[i, : cnt[i]].copy() for i in range(nq)]
+
+    def results_host(self, nq: int):
+        """Copy the device results of the last search_device() to the host (synchronises)."""
+        with torch.cuda.stream(self.stream):
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            self.h_out_cnt.copy_(self.d_out_cnt, non_blocking=True)
+        self.stream.synchronize()
+        rec = self.h_out.numpy().view(SCORED_POINT_OFFSET).reshape(self.max_queries, self.top)
+        cnt = self.h_out_cnt.numpy()
+        return [rec[i, : cnt[i]].copy() for i in range(nq)]

@@ -1,0 +1,70 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol that
+include/qb200.h declares; without a GPU every entry point fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from qdrant_b200 import build
+
+    build.build()
+    from qdrant_b200 import _capi
+
+    return _capi
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "qb200.h")).read()
+    return sorted(set(re.findall(r"QB_API[^;(]*?\b(qb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_surface():
+    fns = header_functions()
+    for must in ("qb_storage_create_dense", "qb_storage_create_sq8", "qb_storage_create_pq", "qb_storage_create_bq", "qb_scorer_create",
+                 "qb_scorer_create_internal", "qb_score_points", "qb_score_point", "qb_score_internal", "qb_search_batch", "qb_rescore"):
+        assert must in fns
+
+
+def test_library_exports_every_declared_symbol(capi):
+    L = C.CDLL(capi.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(L, name), f"{name} declared in include/qb200.h but not exported"
+
+
+def test_python_binding_covers_header(capi):
+    assert sorted(capi.SIGNATURES.keys()) == header_functions()
+    assert capi.lib().qb_abi_version() == 1
+
+
+def test_no_silent_cpu_fallback(capi):
+    """Without a CUDA device creation must fail with QB_ERR_NO_DEVICE — never compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    n = C.c_int32(-1)
+    assert capi.lib().qb_device_count(C.byref(n)) == capi.QB_ERR_NO_DEVICE
+    assert n.value == 0
+    from qdrant_b200.scorer import DenseVectorStorage, Distance
+
+    with pytest.raises(capi.QbError) as ei:
+        DenseVectorStorage(np.zeros((4, 32), np.float32), Distance.Dot)
+    assert ei.value.status == capi.QB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in capi.lib().qb_last_error()
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never reach into oracle/ (tier rule: the oracle is test infrastructure)."""
+    pkg = os.path.join(ROOT, "qdrant_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.replace("test_product_does_not_import_oracle", ""), f"{f} mentions oracle"

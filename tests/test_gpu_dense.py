@@ -1,0 +1,193 @@
+"""GPU parity: f32 dense metrics through the C ABI vs the CPU oracle (bit-exact: assert_array_equal).
+
+Mirrors the reference's two-backends-must-agree pattern (lib/segment/src/vector_storage/tests/async_raw_scorer.rs:41-114)
+and its GPU-vs-CPU harness (index/hnsw_index/gpu/gpu_vector_storage/tests.rs:965-1060), with tolerance 0 instead of
+get_precision (:790-802): the kernels reproduce the AVX2+FMA accumulation order.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.util import assert_topk_equal
+
+pytestmark = pytest.mark.gpu
+
+DISTS = ["Cosine", "Euclid", "Dot", "Manhattan"]
+
+
+@pytest.fixture(scope="module")
+def qb():
+    from qdrant_b200 import scorer
+
+    return scorer
+
+
+def make_data(oracle, dist, n, dim, seed=42, nq=3):
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    if dist == oracle.COSINE:
+        base = oracle.preprocess_rows_f32(oracle.COSINE, base)  # Distance::preprocess_vector at insert time
+    return base, queries
+
+
+@pytest.mark.parametrize("dist", DISTS)
+@pytest.mark.parametrize("dim", [1, 8, 15, 16, 31, 32, 33, 70, 128, 200, 768, 1000])
+def test_score_points_bit_exact(qb, oracle, dist, dim):
+    d = getattr(qb.Distance, dist)
+    base, queries = make_data(oracle, int(d), 300, dim)
+    st = qb.DenseVectorStorage(base, d)
+    rng = np.random.default_rng(1)
+    for q in queries:
+        sc = st.build_raw_scorer(q)
+        ids = rng.integers(0, base.shape[0], 77).astype(np.uint32)
+        got = sc.score_points(ids)
+        qp = oracle.preprocess_f32(int(d), q)
+        want = oracle.score_points_f32(int(d), base, qp, ids)
+        np.testing.assert_array_equal(got, want)
+        assert sc.score_point(5) == want_one(oracle, int(d), base, qp, 5)
+        # score_internal(a, b): TMetric::similarity(stored a, stored b)  (metric_query_scorer.rs:95-100)
+        assert sc.score_internal(3, 9) == oracle.similarity_f32(int(d), base[3], base[9])
+        cpu, io = sc.take_hardware_counters()
+        assert cpu == (77 + 1 + 1) * dim * 4 and io == 0
+        sc.close()
+    st.close()
+
+
+def want_one(oracle, d, base, qp, i):
+    return oracle.similarity_f32(d, qp, base[i])
+
+
+def test_metric_preprocess_bit_exact(qb, oracle):
+    rng = np.random.default_rng(3)
+    for dim in (4, 20, 32, 70, 768, 1500):
+        v = rng.uniform(-1, 1, (50, dim)).astype(np.float32)
+        v[0] = 0.0                                        # zero vector stays zero (simple.rs:248-252)
+        v[1] = oracle.preprocess_f32(oracle.COSINE, v[1])  # already normalised -> unchanged (tools.rs:14-16)
+        got = qb.metric_preprocess(qb.Distance.Cosine, v)
+        np.testing.assert_array_equal(got, oracle.preprocess_rows_f32(oracle.COSINE, v))
+        np.testing.assert_array_equal(qb.metric_preprocess(qb.Distance.Dot, v), v)
+
+
+@pytest.mark.parametrize("dist", DISTS)
+@pytest.mark.parametrize("n,dim", [(1000, 32), (5000, 70), (20000, 128), (100_000, 128), (150_000, 48), (70_000, 768)])
+def test_search_batch_matches_peek_top_iter(qb, oracle, dist, n, dim):
+    d = getattr(qb.Distance, dist)
+    base, queries = make_data(oracle, int(d), n, dim, nq=4)
+    st = qb.DenseVectorStorage(base, d)
+    qp = np.stack([oracle.preprocess_f32(int(d), q) for q in queries])
+    for top in (1, 10, 100):
+        got = st.search_batch(queries, top)
+        want = oracle.scan_f32(int(d), base, qp, top)
+        for i in range(len(queries)):
+            assert_topk_equal(got[i], want[i], oracle.score_rows_f32(int(d), base, qp[i]), f"{dist} n={n} dim={dim} top={top} q={i}")
+    # batched search == per-query search (lib/segment/tests/integration/batch_search_test.rs:33-223)
+    single = [st.search_batch(q, 10)[0] for q in queries]
+    batched = st.search_batch(queries, 10)
+    for a, b in zip(single, batched):
+        np.testing.assert_array_equal(a, b)
+    st.close()
+
+
+def test_config_c1_100k_x128_dot(qb, oracle):
+    """BASELINE.json configs[0]: 100K x 128 f32 dot-product brute force (uniform(-1,1), seeds 42/43, top 10)."""
+    base = np.random.default_rng(42).uniform(-1, 1, (100_000, 128)).astype(np.float32)
+    queries = np.random.default_rng(43).uniform(-1, 1, (16, 128)).astype(np.float32)
+    st = qb.DenseVectorStorage(base, qb.Distance.Dot)
+    got = st.search_batch(queries, 10)
+    want = oracle.scan_f32(oracle.DOT, base, queries, 10)
+    for i in range(len(queries)):
+        assert_topk_equal(got[i], want[i], None, f"C1 q={i}")
+    st.close()
+
+
+def test_deleted_and_filtered(qb, oracle):
+    d = qb.Distance.Dot
+    base, queries = make_data(oracle, int(d), 90_000, 64, nq=2)
+    st = qb.DenseVectorStorage(base, d)
+    rng = np.random.default_rng(8)
+    deleted = rng.random(base.shape[0]) < 0.3
+    from tests.util import pack_bitmap
+
+    bm = pack_bitmap(deleted)
+    want = oracle.scan_f32(int(d), base, queries, 10, deleted=bm)
+    got = st.search_batch(queries, 10, point_deleted=deleted)          # per-call bitslice
+    for i in range(2):
+        assert_topk_equal(got[i], want[i])
+        assert not deleted[got[i]["idx"]].any()
+    st.set_deleted(deleted)                                            # resident flags
+    got2 = st.search_batch(queries, 10)
+    for i in range(2):
+        np.testing.assert_array_equal(got[i], got2[i])
+    st.set_deleted(None)
+    # explicit candidate ids (a payload filter's result), small and large
+    for n_ids in (500, 80_000):
+        ids = rng.choice(base.shape[0], n_ids, replace=False).astype(np.uint32)
+        got = qb.BatchFilteredSearcher.new(queries, st, None, 10).peek_top_iter(ids)
+        for i in range(2):
+            sc = oracle.score_points_f32(int(d), base, queries[i], ids)
+            want_i = oracle.topk(sc, 10, ids)
+            assert_topk_equal(got[i], want_i)
+    st.close()
+
+
+def test_edges(qb, oracle):
+    d = qb.Distance.Euclid
+    rng = np.random.default_rng(0)
+    # fewer points than top
+    base = rng.standard_normal((7, 40)).astype(np.float32)
+    st = qb.DenseVectorStorage(base, d)
+    q = rng.standard_normal(40).astype(np.float32)
+    got = st.search_batch(q, 10)[0]
+    assert got.size == 7
+    assert_topk_equal(got, oracle.scan_f32(int(d), base, q, 10)[0])
+    # everything deleted -> empty result
+    assert st.search_batch(q, 10, point_deleted=np.ones(7, bool))[0].size == 0
+    # cancellation flag already set -> QB_ERR_CANCELLED (check_process_stopped)
+    from qdrant_b200._capi import QbError, QB_ERR_CANCELLED, QB_ERR_INVALID
+
+    with pytest.raises(QbError) as ei:
+        st.search_batch(q, 10, is_stopped=True)
+    assert ei.value.status == QB_ERR_CANCELLED
+    # top == 0 panics in the reference (NonZeroUsize); here a construction error
+    with pytest.raises(ValueError):
+        qb.BatchFilteredSearcher(q, st, 0)
+    # out-of-range ids
+    sc = st.build_raw_scorer(q)
+    with pytest.raises(QbError) as ei:
+        sc.score_points([99])
+    assert ei.value.status == QB_ERR_INVALID
+    with pytest.raises(IndexError):
+        sc.score_internal(0, 99)
+    # wrong query dim -> error at construction only (OperationResult)
+    with pytest.raises(ValueError):
+        st.build_raw_scorer(np.zeros(3, np.float32))
+    st.close()
+    # empty storage
+    st = qb.DenseVectorStorage(np.zeros((0, 16), np.float32), qb.Distance.Dot)
+    assert st.search_batch(np.zeros(16, np.float32), 5)[0].size == 0
+    st.close()
+    # identical rows: mass ties must not break selection (overflow fallback path)
+    base = np.tile(rng.standard_normal((1, 64)).astype(np.float32), (120_000, 1))
+    st = qb.DenseVectorStorage(base, qb.Distance.Dot)
+    got = st.search_batch(base[0], 10)[0]
+    assert got.size == 10 and np.all(got["score"] == got["score"][0])
+    assert sorted(got["idx"].tolist()) == list(range(10))  # (score desc, id asc)
+    st.close()
+
+
+def test_filtered_scorer_like_hnsw_hop(qb, oracle):
+    """FilteredScorer::score_points (point_scorer.rs:265-295): filter deleted, truncate to limit, one batch call."""
+    d = qb.Distance.Cosine
+    base, queries = make_data(oracle, int(d), 2000, 96, nq=1)
+    st = qb.DenseVectorStorage(base, d)
+    deleted = np.zeros(2000, bool)
+    deleted[::3] = True
+    fs = qb.FilteredScorer.new(queries[0], st, None, point_deleted=deleted)
+    ids = list(range(100, 140))
+    res = fs.score_points(ids, limit=16)
+    assert len(ids) == 16 and all(not deleted[i] for i in ids)
+    qp = oracle.preprocess_f32(int(d), queries[0])
+    np.testing.assert_array_equal(res["score"], oracle.score_points_f32(int(d), base, qp, np.array(ids, np.uint32)))
+    st.close()

@@ -171,3 +171,17 @@ def test_bq_popcount_matches_reference_c(oracle):
             bits_q = (q > 0)
             bits_v = (data[i] > 0)
             assert x == int(np.sum(bits_q != bits_v))
+
+
+def test_f16_avx_vs_scalar_tolerance(oracle):
+    # metric_f16/avx/dot.rs:82-124: 256-element vectors in [1, 8], |simd - scalar| / |scalar| < 5e-4
+    rng = np.random.default_rng(16)
+    v1 = (rng.integers(10, 80, 256) / 10.0).astype(np.float32).astype(np.float16)
+    v2 = (rng.integers(10, 80, 256) / 10.0).astype(np.float32).astype(np.float16)
+    simd = oracle.raw_f16("dot_avx", v1, v2)
+    scalar = oracle.raw_f16("dot_scalar", v1, v2)
+    assert abs(simd - scalar) / abs(scalar) < 0.0005
+    exact = float(np.dot(v1.astype(np.float64), v2.astype(np.float64)))
+    assert abs(simd - exact) / exact < 1e-5
+    assert oracle.similarity_f16(oracle.DOT, v1, v2) == simd
+    assert oracle.similarity_f16(oracle.COSINE, v1, v2) == simd  # f16 cosine == dot (simple_cosine.rs:28-58)
