@@ -4,6 +4,7 @@
 // qb_topk.cu.  There is no CPU scoring path anywhere in this library.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -24,6 +25,9 @@ qb_status qb_pq_build_luts(const qb_storage* s, const float* d_q_pre, uint32_t q
 qb_status qb_pq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_pq_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
 qb_status qb_pq_score_internal(const qb_storage* s, uint32_t a, uint32_t b, float* d_out, cudaStream_t stream);
+uint32_t qb_sq8_mma_block(const qb_storage* s, uint32_t nq);
+qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_t nq_pad, const float* d_q_off, uint32_t nq, uint32_t n_blk,
+                          uint64_t row_begin, uint64_t row_end, const QbEmit& emit, unsigned int* d_flags, cudaStream_t stream);
 qb_status qb_bq_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, int force_binary, void* d_out, cudaStream_t stream);
 qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
@@ -498,8 +502,10 @@ static void profile_end(qb_storage* s, cudaStream_t stream, cudaEvent_t e0, cuda
 
 // Core of the fused scan: queries already encoded in c->d_queries_enc (+ c->d_q_off).  Results to d_out/d_counts
 // (device).  Sets *overflow_possible when the filter pass is used (caller checks c->d_cnt overflow flag at [nq]).
+enum { RS_FORCE_DIRECT = 1, RS_NO_MMA = 2 };
 static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t top, const uint32_t* d_ids, uint64_t n_ids, const uint32_t* d_deleted2,
-                            const volatile int32_t* is_stopped, bool force_direct, qb_scored_point* d_out, uint32_t* d_counts, unsigned int* d_overflow) {
+                            const volatile int32_t* is_stopped, uint32_t rs_flags, qb_scored_point* d_out, uint32_t* d_counts, unsigned int* d_overflow) {
+    const bool force_direct = (rs_flags & RS_FORCE_DIRECT) != 0;
     const uint64_t n_cand = d_ids ? n_ids : s->count;
     cudaStream_t stream = c->stream;
     if (n_cand == 0) { QB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, stream)); return QB_OK; }
@@ -542,7 +548,14 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             a.emit.dense = 0; a.emit.thr = c->d_thr + q0; a.emit.cnt = c->d_cnt + q0;
             if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
             profile_begin(s, c, stream, &e0, &e1);
-            QB_TRY(qb_launch_scan(s, a, stream));
+            const uint32_t mma_blk = (!d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr) ? qb_sq8_mma_block(s, qn) : 0;
+            if (mma_blk) {
+                // batched SQ8: tensor-core GEMM with the fused epilogue/filter (qb_sq8_mma.cu)
+                const uint32_t nq_pad = (uint32_t)round_up_u64(qn, mma_blk);
+                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, n_cand, a.emit, d_overflow, stream));
+            } else {
+                QB_TRY(qb_launch_scan(s, a, stream));
+            }
             profile_end(s, stream, e0, e1);
             QB_TRY(qb_launch_select(c->d_cand, c->d_cnt + q0, plan.cap, 0, qn, top, 0, d_out + (size_t)q0 * top, d_counts + q0, nullptr, d_overflow, stream));
         }
@@ -583,7 +596,8 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
     uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
     memcpy(hs, queries, raw_bytes);
     QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, raw_bytes + (size_t)n_queries * pre_stride_f(s) * 4));
-    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, (size_t)n_queries * qb_encoded_query_bytes(s)));
+    // +256 rows: the tensor-core SQ8 path reads whole query blocks (rows past n_queries are masked, never scored)
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)n_queries + 256) * qb_encoded_query_bytes(s)));
     QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
     QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)n_queries * top));
     QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)n_queries + 4));
@@ -606,7 +620,7 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
     }
     unsigned int* d_overflow = reinterpret_cast<unsigned int*>(c->d_out_counts + n_queries);
     QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
-    QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, false, c->d_out, c->d_out_counts, d_overflow));
+    QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, 0, c->d_out, c->d_out_counts, d_overflow));
     uint8_t* h_res = hs + raw_bytes;
     uint8_t* h_cnt = h_res + res_bytes;
     QB_CUDA(cudaMemcpyAsync(h_res, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
@@ -617,7 +631,10 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
     if (overflow) {
         // the threshold admitted more candidates than the buffer holds (adversarial data, e.g. mass ties or a
         // mostly-deleted sample): redo with full materialisation, which cannot overflow
-        QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, true, c->d_out, c->d_out_counts, d_overflow));
+        // bit 2: a tensor-core dot product left the f32-exact window (>= 2^24): redo on the lane-exact CUDA-core kernel
+        QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
+        QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, ((overflow & 1u) ? RS_FORCE_DIRECT : 0u) | RS_NO_MMA, c->d_out,
+                          c->d_out_counts, d_overflow));
         QB_CUDA(cudaMemcpyAsync(h_res, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
         QB_CUDA(cudaMemcpyAsync(h_cnt, c->d_out_counts, cnt_bytes, cudaMemcpyDeviceToHost, stream));
         QB_CUDA(cudaStreamSynchronize(stream));
@@ -645,12 +662,13 @@ extern "C" qb_status qb_search_batch_device(qb_storage* s, const float* dev_quer
     }
     if (!c) { QB_TRY(qb_ctx_acquire(s, &c)); qb_ctx_release(s, c); }
     QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, (size_t)n_queries * pre_stride_f(s) * 4 + 256));
-    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, (size_t)n_queries * qb_encoded_query_bytes(s)));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)n_queries + 256) * qb_encoded_query_bytes(s)));
     QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
     QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)n_queries + 4));
     QB_TRY(prepare_queries(s, dev_queries, n_queries, reinterpret_cast<float*>(c->d_queries_raw), c->d_queries_enc, c->d_q_off, c->stream));
     unsigned int* d_overflow = reinterpret_cast<unsigned int*>(c->d_out_counts + n_queries);
-    return run_search(s, c, n_queries, top, nullptr, 0, nullptr, nullptr, false, dev_out, dev_counts, d_overflow);
+    QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, c->stream));
+    return run_search(s, c, n_queries, top, nullptr, 0, nullptr, nullptr, 0, dev_out, dev_counts, d_overflow);
 }
 
 // ------------------------------------------------------------------------------------------------ RawScorer

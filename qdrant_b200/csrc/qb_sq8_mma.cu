@@ -1,0 +1,313 @@
+// qb_sq8_mma.cu — batched SQ8 scoring on the 5th-gen tensor cores (tcgen05.mma kind::i8, TMEM accumulators, TMA).
+//
+// The one dense contraction on the path (north_star): many queries x one segment.  In the reference every
+// (query, vector) pair is a separate impl_score_dot_avx call (lib/quantization/cpp/avx2.c:25-63) made from
+// QuantizedQueryScorer::score_stored_batch (quantized_query_scorer.rs:81-93) inside the peek_top_iter loop
+// (point_scorer.rs:453-462), i.e. the batch re-reads each 64-vector chunk once per query.  Here it is
+//      D[128 vectors x N queries] (s32, TMEM)  +=  A[128 x K] (u8 codes, smem via TMA)  x  B[N x K]^T (u8 query codes)
+// with the integer dot exact by construction, followed by the reference's epilogue
+//      score = multiplier * f32(dot) + q_off[q] + v_off[v]              (encoded_vectors_u8.rs:101-103)
+// and the fused threshold filter that feeds the top-k selection (the N x 10M score matrix is never materialised).
+//
+// Layout / pipeline (one persistent CTA per SM, 10 warps):
+//   warp 0   TMA producer: the CTA's query block B (N <= 256 queries x K bytes, 128-B-swizzled K-blocks) is loaded
+//            once and stays resident in shared memory; vector-code tiles A (128 rows x 64 B, 64-B swizzle) stream
+//            through a 4-stage ring.
+//   warp 1   allocates 512 TMEM columns (two N-column s32 accumulators) and issues tcgen05.mma (M=128, N, K=32)
+//            from one lane; tcgen05.commit releases smem stages and publishes finished accumulators.
+//   warps 2-9 epilogue: tcgen05.ld (lane = vector row, column = query), exact int->f32, three-rounding epilogue,
+//            compare with the per-query threshold, emit survivors.  Double-buffered against the next tile's MMAs.
+// CTAs are grouped by query block (c % n_qblocks) so that the n_qblocks CTAs reading the same A tiles run in
+// lock-step and hit L2 after the first HBM read.
+//
+// Exactness: codes are <= 127, so dot <= 127^2 * K.  While dot < 2^24 the CPU's lane-wise f32 tree equals f32(dot)
+// exactly (all partial sums are non-negative integers <= dot).  If any dot >= 2^24 (possible only for K > 1040) the
+// kernel raises a flag and the host reruns the batch on the lane-exact CUDA-core kernel.
+#include <cuda.h>
+
+#include "qb_internal.h"
+
+namespace {
+
+constexpr int MMA_M = 128;
+constexpr int A_KB = 64;                    // K bytes per A stage (one 64-B swizzle atom wide)
+constexpr int A_STAGES = 4;
+constexpr int A_STAGE_BYTES = MMA_M * A_KB;  // 8 KB
+constexpr int B_KB = 128;                   // K bytes per resident B block (128-B swizzle)
+constexpr int N_MAX = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);
+constexpr uint32_t TMEM_COLS = 512;
+
+struct MmaParams {
+    const float* voff;
+    uint64_t n_rows;
+    uint32_t ad;            // K bytes
+    uint32_t n_blk;         // queries per block (multiple of 16, <= 256)
+    uint32_t n_qblocks;
+    uint32_t nq;            // real number of queries
+    uint32_t n_workers;     // CTAs per query block
+    float multiplier;
+    const float* q_off;     // [nq]
+    unsigned int* flags;    // bit 1: a dot product reached 2^24 (inexact for the f32 tree)
+    int check_exact;
+};
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            qb_smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(qb_smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(qb_smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, swizzled, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);          // start address  [0,14)
+    d |= (uint64_t)0 << 16;                               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                               // version = 1
+    d |= (uint64_t)(layout_type & 7u) << 61;              // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const MmaParams p, const QbEmit emit) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // 1024-B alignment is required by the 128-B swizzle atoms (no static shared memory precedes this array)
+    if ((qb_smem_u32(smem) & 1023u) != 0u) __trap();
+    const uint32_t n_kb_b = (p.ad + B_KB - 1) / B_KB;
+    const uint32_t n_ka = (p.ad + A_KB - 1) / A_KB;
+    const uint32_t b_block_bytes = p.n_blk * B_KB;
+    uint8_t* b_s = smem;
+    uint8_t* a_s = b_s + (size_t)n_kb_b * b_block_bytes;
+    float* thr_s = reinterpret_cast<float*>(a_s + A_STAGES * A_STAGE_BYTES);
+    float* qoff_s = thr_s + N_MAX;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qoff_s + N_MAX);
+    uint64_t* full_a = bars;                 // [A_STAGES]
+    uint64_t* empty_a = bars + A_STAGES;     // [A_STAGES]
+    uint64_t* b_full = bars + 2 * A_STAGES;  // [1]
+    uint64_t* tm_full = b_full + 1;          // [2]
+    uint64_t* tm_empty = tm_full + 2;        // [2]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tm_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qblock = blockIdx.x % p.n_qblocks;
+    const uint32_t worker = blockIdx.x / p.n_qblocks;
+    const uint64_t n_tiles = (p.n_rows + MMA_M - 1) / MMA_M;
+    const uint64_t my_tiles = (worker < n_tiles) ? (n_tiles - worker + p.n_workers - 1) / p.n_workers : 0;
+    const uint32_t q_base = qblock * p.n_blk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { qb_mbar_init(&full_a[s], 1); qb_mbar_init(&empty_a[s], 1); }
+        qb_mbar_init(b_full, 1);
+        for (int a = 0; a < 2; ++a) { qb_mbar_init(&tm_full[a], 1); qb_mbar_init(&tm_empty[a], EPI_WARPS); }
+        qb_fence_barrier_init();
+    }
+    for (uint32_t i = threadIdx.x; i < N_MAX; i += blockDim.x) {
+        const uint32_t q = q_base + i;
+        const bool real = (i < p.n_blk) && (q < p.nq);
+        thr_s[i] = real ? emit.thr[q] : __int_as_float(0x7f800000);  // +inf: padded queries never emit
+        qoff_s[i] = real ? p.q_off[q] : 0.0f;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qb_smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const uint64_t pol_keep = qb_policy_evict_last();
+            const uint64_t pol_stream = qb_policy_evict_first();
+            qb_mbar_arrive_expect_tx(b_full, n_kb_b * b_block_bytes);
+            for (uint32_t kb = 0; kb < n_kb_b; ++kb) tma_load_2d(&map_b, b_full, b_s + (size_t)kb * b_block_bytes, (int32_t)(kb * B_KB), (int32_t)q_base, pol_keep);
+            uint64_t it = 0;
+            for (uint64_t ti = 0; ti < my_tiles; ++ti) {
+                const uint64_t tile = worker + ti * p.n_workers;
+                const int32_t row0 = (int32_t)(tile * MMA_M);
+                for (uint32_t ka = 0; ka < n_ka; ++ka, ++it) {
+                    const uint32_t s = (uint32_t)(it % A_STAGES), ph = (uint32_t)((it / A_STAGES) & 1);
+                    qb_mbar_wait(&empty_a[s], ph ^ 1u);
+                    qb_mbar_arrive_expect_tx(&full_a[s], A_STAGE_BYTES);
+                    // the n_qblocks CTAs of a worker group read the same tile: the first read comes from HBM, the rest from L2
+                    tma_load_2d(&map_a, &full_a[s], a_s + (size_t)s * A_STAGE_BYTES, (int32_t)(ka * A_KB), row0, p.n_qblocks > 1 ? pol_keep : pol_stream);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one lane)
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A/B = u8, both K-major, M = 128, N = n_blk
+            const uint32_t idesc = (2u << 4) | (0u << 7) | (0u << 10) | ((p.n_blk >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+            qb_mbar_wait(b_full, 0);
+            tc_fence_after();
+            const uint32_t a_addr0 = qb_smem_u32(a_s), b_addr0 = qb_smem_u32(b_s);
+            uint64_t it = 0;
+            for (uint64_t ti = 0; ti < my_tiles; ++ti) {
+                const uint32_t acc = (uint32_t)(ti & 1), acc_ph = (uint32_t)((ti >> 1) & 1);
+                qb_mbar_wait(&tm_empty[acc], acc_ph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * p.n_blk;
+                for (uint32_t ka = 0; ka < n_ka; ++ka, ++it) {
+                    const uint32_t s = (uint32_t)(it % A_STAGES), ph = (uint32_t)((it / A_STAGES) & 1);
+                    qb_mbar_wait(&full_a[s], ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t j = 0; j < A_KB / 32; ++j) {
+                        const uint32_t kbyte = ka * A_KB + j * 32;
+                        if (kbyte < p.ad) {
+                            const uint64_t a_desc = make_smem_desc(a_addr0 + s * A_STAGE_BYTES + j * 32, 8 * A_KB, 4);
+                            const uint64_t b_desc = make_smem_desc(b_addr0 + (kbyte / B_KB) * b_block_bytes + (kbyte % B_KB), 8 * B_KB, 2);
+                            mma_i8(d_tmem, a_desc, b_desc, idesc, (ka | j) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&empty_a[s]);  // frees the smem stage once the MMAs above have read it
+                }
+                tc_commit(&tm_full[acc]);    // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps
+        const int ew = warp - 2;
+        const uint32_t quarter = (uint32_t)(warp & 3);   // TMEM lanes this warp may read: [32*quarter, 32*quarter+32)
+        const uint32_t half = (uint32_t)(ew >> 2);       // which alternate 16-column chunks
+        const uint32_t n_chunks = p.n_blk >> 4;
+        const float mult = p.multiplier;
+        for (uint64_t ti = 0; ti < my_tiles; ++ti) {
+            const uint64_t tile = worker + ti * p.n_workers;
+            const uint32_t acc = (uint32_t)(ti & 1), acc_ph = (uint32_t)((ti >> 1) & 1);
+            const uint64_t row = tile * MMA_M + quarter * 32 + lane;
+            const bool valid_row = row < p.n_rows;
+            const float v_off = valid_row ? p.voff[row] : 0.0f;
+            const bool dead = !valid_row || qb_is_deleted(emit, (uint32_t)(valid_row ? row : 0));
+            qb_mbar_wait(&tm_full[acc], acc_ph);
+            tc_fence_after();
+            for (uint32_t c = half; c < n_chunks; c += 2) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((quarter * 32u) << 16) + acc * p.n_blk + c * 16, r);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t dot = r[j];
+                    float f = __uint_as_float(dot | 0x4B000000u) - 8388608.0f;  // exact for dot < 2^23, full-rate pipes
+                    if (dot >= 0x800000u) {
+                        f = (float)dot;
+                        if (p.check_exact && dot >= 0x1000000u) atomicOr(p.flags, 2u);
+                    }
+                    const uint32_t n = c * 16 + j;
+                    const float sc = __fadd_rn(__fadd_rn(__fmul_rn(mult, f), qoff_s[n]), v_off);
+                    if (sc >= thr_s[n] && !dead) {
+                        const uint32_t q = q_base + n;
+                        const unsigned int pos = atomicAdd(&emit.cnt[q], 1u);
+                        if (pos < emit.cap) emit.cand[(unsigned long long)q * emit.cap + pos] = qb_pack_key(sc, (uint32_t)row + emit.id_base);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) qb_mbar_arrive(&tm_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+qb_status make_map_u8(CUtensorMap* m, const void* base, uint64_t inner_bytes, uint64_t rows, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle sw) {
+    EncodeTiledFn fn = get_encode_fn();
+    QB_CHECK(fn, QB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {inner_bytes, rows};
+    cuuint64_t gstride[1] = {inner_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QB_CHECK(r == CUDA_SUCCESS, QB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return QB_OK;
+}
+
+}  // namespace
+
+// Can this (storage, batch) use the tensor-core path?  Returns the per-CTA query block size (0 = no).
+uint32_t qb_sq8_mma_block(const qb_storage* s, uint32_t nq) {
+    if (s->kind != QB_KIND_SQ8 || s->qdist == QB_QD_L1) return 0;
+    if (nq < 32 || s->count < 4 * 128) return 0;
+    const uint32_t n_kb_b = (s->actual_dim + B_KB - 1) / B_KB;
+    uint32_t n_blk = (uint32_t)((192 * 1024) / ((size_t)n_kb_b * B_KB));
+    n_blk = (n_blk > (uint32_t)N_MAX ? (uint32_t)N_MAX : n_blk) & ~15u;
+    if (n_blk < 16) return 0;
+    if (nq < n_blk) n_blk = (nq + 15u) & ~15u;  // a single, narrower block
+    return n_blk;
+}
+
+// d_q_codes: [nq_pad][ad] u8 with nq_pad = round_up(nq, n_blk) rows (zero padded); filter-mode emit only.
+qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_t nq_pad, const float* d_q_off, uint32_t nq, uint32_t n_blk,
+                          uint64_t row_begin, uint64_t row_end, const QbEmit& emit, unsigned int* d_flags, cudaStream_t stream) {
+    QB_CHECK(row_begin == 0, QB_ERR_INVALID, "sq8_mma_scan: scans start at row 0");
+    QB_CHECK(!emit.dense && emit.thr && emit.cnt, QB_ERR_INVALID, "sq8_mma_scan: filter-mode emission only");
+    const uint32_t ad = s->actual_dim;
+    const uint32_t n_qblocks = (nq + n_blk - 1) / n_blk;
+    QB_CHECK(nq_pad >= n_qblocks * n_blk, QB_ERR_INVALID, "sq8_mma_scan: query buffer not padded");
+    CUtensorMap map_a, map_b;
+    QB_TRY(make_map_u8(&map_a, s->d_codes, ad, row_end, A_KB, MMA_M, CU_TENSOR_MAP_SWIZZLE_64B));
+    QB_TRY(make_map_u8(&map_b, d_q_codes, ad, nq_pad, B_KB, n_blk, CU_TENSOR_MAP_SWIZZLE_128B));
+    MmaParams p{};
+    p.voff = s->d_voff; p.n_rows = row_end; p.ad = ad; p.n_blk = n_blk; p.n_qblocks = n_qblocks; p.nq = nq;
+    p.multiplier = s->multiplier; p.q_off = d_q_off; p.flags = d_flags;
+    p.check_exact = ((uint64_t)ad * 127ull * 127ull >= (1ull << 24)) ? 1 : 0;
+    uint32_t workers = (uint32_t)s->sm_count / n_qblocks;
+    if (workers < 1) workers = 1;
+    const uint64_t n_tiles = (row_end + MMA_M - 1) / MMA_M;
+    if (workers > n_tiles) workers = (uint32_t)n_tiles;
+    p.n_workers = workers;
+    const uint32_t n_kb_b = (ad + B_KB - 1) / B_KB;
+    const size_t smem = (size_t)n_kb_b * n_blk * B_KB + A_STAGES * A_STAGE_BYTES + 2 * N_MAX * 4 + 16 * 8 + 16;
+    QB_CHECK(smem <= 227 * 1024, QB_ERR_INVALID, "sq8_mma_scan: shared memory %zu exceeds 227 KB", smem);
+    QB_CUDA(cudaFuncSetAttribute(sq8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sq8_mma_kernel<<<workers * n_qblocks, THREADS, smem, stream>>>(map_a, map_b, p, emit);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}

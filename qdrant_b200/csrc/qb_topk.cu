@@ -45,7 +45,7 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
     } else {
         unsigned int c = cnt[q];
         if (c > cap) {
-            if (threadIdx.x == 0 && overflow) atomicExch(overflow, 1u);
+            if (threadIdx.x == 0 && overflow) atomicOr(overflow, 1u);
             c = (unsigned int)cap;
         }
         n = c;

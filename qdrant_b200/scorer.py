@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import sys
 from typing import Iterable, Optional, Sequence
 
 import numpy as np
@@ -138,6 +139,8 @@ class RawScorer:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():  # the CUDA runtime / library may already be torn down at interpreter exit
+            return
         try:
             self.close()
         except Exception:
@@ -215,6 +218,8 @@ class _Storage:
             self._h = vp()
 
     def __del__(self):
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
