@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--cpu-sample-rows", type=int, default=CPU_SAMPLE_ROWS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
+                    help="c2 = headline (single-query f32 cosine, default); c3 = 10Mx768 SQ8 cosine, 1024-query batch on the int8 tensor cores")
+    ap.add_argument("--batch", type=int, default=1024, help="queries per batch (c3)")
     return ap.parse_args()
 
 
@@ -328,6 +331,150 @@ def main_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ C3: batched SQ8 (1 GPU)
+def main_c3(args):
+    """BASELINE configs[2]: 10M x 768 SQ8 cosine, batch = 1024 queries, int8 tensor-core GEMM scorer, 1 GPU.
+    A step = one 1024-query batch over the whole segment.  Not the default bench line (that is c2)."""
+    import torch
+
+    from qdrant_b200 import scorer as qb
+    from qdrant_b200._capi import check, lib, vp
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n, dim, nq, top = args.rows, args.dim, args.batch, TOP
+    ad = dim + (16 - dim % 16) % 16
+    chunk = 500_000
+
+    def gen_chunk(i, cn):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1000 + i)
+        x = torch.randn((cn, dim), generator=g, device=dev, dtype=torch.float32)
+        check(lib().qb_metric_preprocess_device(0, int(qb.Distance.Cosine), dim, cn, vp(x.data_ptr()), dim * 4))
+        return x
+
+    mn, mx = float("inf"), float("-inf")
+    for i, r0 in enumerate(range(0, n, chunk)):
+        x = gen_chunk(i, min(chunk, n - r0))
+        a, b = torch.aminmax(x)
+        mn, mx = min(mn, float(a)), max(mx, float(b))
+        del x
+    alpha, offset = np.float32((np.float32(mx) - np.float32(mn)) / np.float32(127.0)), np.float32(mn)
+    multiplier = np.float32(alpha * alpha)
+    rows = torch.empty((n, 4 + ad), dtype=torch.uint8, device=dev)
+    for i, r0 in enumerate(range(0, n, chunk)):
+        cn = min(chunk, n - r0)
+        x = gen_chunk(i, cn)
+        codes = torch.clamp(torch.floor((x - float(offset)) / float(alpha) + 0.5), 0, 127)
+        voff = (codes.sum(1) * float(alpha) * float(offset) + float(np.float32(ad) * offset * offset)).to(torch.float32)
+        rows[r0 : r0 + cn, 4 : 4 + dim] = codes.to(torch.uint8)
+        if ad > dim:
+            rows[r0 : r0 + cn, 4 + dim :] = int(min(max(round((0.0 - float(offset)) / float(alpha)), 0), 127))
+        rows[r0 : r0 + cn, :4] = voff.view(torch.uint8).view(cn, 4)
+        del x, codes, voff
+    torch.cuda.synchronize()
+    st = qb.ScalarQuantizedVectors(None, dim, float(alpha), float(offset), float(multiplier), qb.Distance.Cosine, rows_ptr=rows.data_ptr(), count=n)
+    sample_rows = min(65536, n)
+    h_sample = rows[:sample_rows].cpu().numpy()
+    del rows
+    torch.cuda.empty_cache()
+
+    queries = np.random.default_rng(44).standard_normal((nq, dim)).astype(np.float32)
+    stream = torch.cuda.ExternalStream(st.stream_ptr(), device=dev)
+    d_q = torch.from_numpy(queries).to(dev)
+    d_out = torch.empty((nq, top), dtype=torch.int64, device=dev)
+    d_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+
+    def step_device():
+        check(lib().qb_search_batch_device(st._h, vp(d_q.data_ptr()), nq, top, vp(d_out.data_ptr()), vp(d_cnt.data_ptr())))
+
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        step_device()
+    torch.cuda.synchronize()
+    st.profile(True)
+    launches0 = int(lib().qb_kernel_launch_count())
+    clocks = ClockSampler(0)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = int(lib().qb_kernel_launch_count()) - launches0
+    n_prof, prof_ms = st.profile_read(reset=True)
+    st.profile(False)
+    clk = clocks.stop()
+    for _ in range(2):
+        st.search_batch(queries, top)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        res = st.search_batch(queries, top)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    # the tensor-core path must agree with the lane-exact CUDA-core path (bit-exact), on a slice of the batch
+    os.environ["QB_DISABLE_MMA"] = "1"
+    res_cc = st.search_batch(queries[:48], top)
+    os.environ.pop("QB_DISABLE_MMA", None)
+    for a, b in zip(res[:48], res_cc):
+        assert np.array_equal(a, b), "tensor-core and CUDA-core SQ8 paths disagree"
+
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as o
+
+        meta = o.SQ8Meta(dim, ad, float(alpha), float(offset), float(multiplier), o.QD_DOT, 0)
+        sq = o.SQ8(meta, h_sample)
+        enc = [sq.encode_query(o.preprocess_f32(o.COSINE, q)) for q in queries]
+        codes = np.stack([e[0] for e in enc]); offs = np.array([e[1] for e in enc], np.float32)
+        threads = os.cpu_count() or 1
+        from qdrant_b200.sharded import shard_ranges
+        import ctypes as C
+
+        def seg(r):
+            b, e = r
+            out = np.zeros((nq, top), dtype=o.SCORED); cnt = np.zeros(nq, dtype=np.uint32)
+            o.lib().qo_scan_sq8(C.byref(meta), h_sample.ctypes.data_as(C.POINTER(C.c_uint8)), b, e, codes.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                offs.ctypes.data_as(C.POINTER(C.c_float)), nq, top, None, out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.POINTER(C.c_uint32)))
+            return out
+        with cf.ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(seg, shard_ranges(sample_rows, threads)))
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                list(pool.map(seg, shard_ranges(sample_rows, threads)))
+            dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": nq / (dt * n / sample_rows), "unit": "queries/s", "cores": threads, "kind": "reference+port",
+               "sample": f"{sample_rows} of {n} rows x {nq} queries: impl_score_dot_avx arithmetic + postprocess + heap (oracle qo_scan_sq8), {threads} threads over row "
+                         f"segments, {dt*1e3:.0f} ms per sample batch, extrapolated linearly to {n} rows"}
+    peak_bf16 = 1645.8
+    try:
+        peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    ops = 2.0 * nq * n * ad
+    kern_ms = prof_ms / max(n_prof, 1)
+    achieved = ops / (kern_ms / 1e3) / 1e12 if n_prof else None
+    line = {"metric": f"queries/sec, {n}x{dim} SQ8 cosine brute-force top-{top}, batch={nq} (BASELINE configs[2])", "value": nq * K / (dev_ms / 1e3), "unit": "queries/s",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 (s32 accumulate)",
+            "data": "synthetic", "config": {"workload": f"{n}x{dim} SQ8 cosine, batch={nq}, int8 tensor-core GEMM scorer + fused top-{top}", "rows": n, "dim": dim, "batch": nq,
+                                            "l2": "code plane 7.68 GB >> 126 MB L2"},
+            "e2e": {"value": nq * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top * 8 + nq * 4, "ms_per_step": e2e_ms / K},
+            "gpu_launches": launches, "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "sq8_mma_kernel (tcgen05.mma kind::i8, main pass)", "achieved": achieved, "peak": 2 * peak_bf16, "unit": "TOP/s",
+                         "frac": (achieved / (2 * peak_bf16)) if achieved else None, "traffic": None,
+                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (dense int8 = 2 x bf16 on sm_100; no measured int8 figure)", "avg_launch_ms": kern_ms,
+                         "launches_timed": n_prof, "algorithmic_ops_per_launch": ops}}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    st.close()
+    return 0
+
+
 if __name__ == "__main__":
     a = parse()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
+    if a.impl == "reference":
+        sys.exit(main_reference(a))
+    sys.exit(main_c3(a) if a.config == "c3" else main_ours(a))

@@ -250,7 +250,7 @@ extern "C" qb_status qb_storage_create_sq8(int32_t device, uint32_t dim, uint64_
         }
         for (uint64_t r = 0; r < count; r += chunk_rows) {
             const uint64_t n = std::min<uint64_t>(chunk_rows, count - r);
-            cudaError_t e = cudaMemcpy(d_stage, rows + r * row_bytes, n * row_bytes, cudaMemcpyHostToDevice);
+            cudaError_t e = cudaMemcpy(d_stage, rows + r * row_bytes, n * row_bytes, cudaMemcpyDefault);  // host or device source
             qb_status st = (e == cudaSuccess) ? qb_sq8_repack(s, d_stage, row_bytes, r, n, 0) : QB_ERR_CUDA;
             if (st == QB_OK && cudaDeviceSynchronize() != cudaSuccess) st = QB_ERR_CUDA;
             if (st != QB_OK) { qb_set_error("create_sq8: upload failed: %s", cudaGetErrorString(cudaGetLastError())); cudaFree(d_stage); qb_storage_destroy(s); return st; }

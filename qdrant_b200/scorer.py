@@ -269,12 +269,19 @@ class DenseVectorStorage(_Storage):
 class ScalarQuantizedVectors(_Storage):
     """QuantizedVectors backed by EncodedVectorsU8: `rows` is quantized.data ([f32 v_off][actual_dim u8] per row)."""
 
-    def __init__(self, rows, dim: int, alpha: float, offset: float, multiplier: float, distance: Distance, device: int = 0):
+    def __init__(self, rows, dim: int, alpha: float, offset: float, multiplier: float, distance: Distance, device: int = 0,
+                 rows_ptr: Optional[int] = None, count: Optional[int] = None):
+        """`rows`: numpy [count, 4 + actual_dim] u8, or None with `rows_ptr` = address (host or device) of such rows."""
         super().__init__()
-        r = np.ascontiguousarray(rows, dtype=np.uint8)
-        self.count, self.dim, self.device, self.distance = r.shape[0], int(dim), device, Distance(distance)
+        self.dim, self.device, self.distance = int(dim), device, Distance(distance)
+        actual_dim = self.dim + (16 - self.dim % 16) % 16
+        if rows is not None:
+            r = np.ascontiguousarray(rows, dtype=np.uint8)
+            self.count, ptr, row_bytes = r.shape[0], r.ctypes.data_as(u8p), (r.shape[1] if r.ndim == 2 else 0)
+        else:
+            self.count, ptr, row_bytes = int(count), C.cast(vp(int(rows_ptr)), u8p), 4 + actual_dim
         dt, invert = construct_vector_parameters(self.distance)
-        check(lib().qb_storage_create_sq8(device, self.dim, self.count, r.ctypes.data_as(u8p), r.shape[1] if r.ndim == 2 else 0, C.c_float(alpha),
+        check(lib().qb_storage_create_sq8(device, self.dim, self.count, ptr, row_bytes, C.c_float(alpha),
                                           C.c_float(offset), C.c_float(multiplier), int(dt), int(invert), int(self.distance), C.byref(self._h)))
 
     def raw_scorer(self, query) -> RawScorer:

@@ -195,3 +195,31 @@ def test_bq_search_batch_and_rescore(qb, oracle):
         order = np.argsort(-exact, kind="stable")[:10]
         np.testing.assert_array_equal(res["score"], exact[order])
     st.close(); orig.close()
+
+
+# ------------------------------------------------------------------------------------------------ SQ8 tensor-core batch path
+@pytest.mark.parametrize("dist,n,dim,nq", [("Cosine", 100_000, 768, 300), ("Euclid", 70_000, 128, 64), ("Dot", 80_000, 65, 33),
+                                           ("Cosine", 70_000, 1536, 40), ("Cosine", 66_000, 768, 256)])
+def test_sq8_batched_tensor_core_path(qb, oracle, dist, n, dim, nq):
+    """Batched SQ8 search (tcgen05 kind::i8 GEMM + fused epilogue/filter) == oracle peek_top_iter, bit-exact, and
+    == the CUDA-core path (QB_DISABLE_MMA=1)."""
+    import os
+
+    d = getattr(qb.Distance, dist)
+    dt, inv = qparams(qb, d)
+    base, queries = gen(oracle, qb, d, n, dim, nq=nq)
+    sq = oracle.SQ8.encode(base, dt, inv)
+    st = qb.ScalarQuantizedVectors(sq.rows, dim, sq.meta.alpha, sq.meta.offset, sq.meta.multiplier, d)
+    enc = [sq.encode_query(oracle.preprocess_f32(int(d), q)) for q in queries]
+    codes = np.stack([e[0] for e in enc]); offs = np.array([e[1] for e in enc], np.float32)
+    deleted = np.random.default_rng(4).random(n) < 0.05
+    os.environ.pop("QB_DISABLE_MMA", None)
+    got = st.search_batch(queries, 10, point_deleted=deleted)
+    os.environ["QB_DISABLE_MMA"] = "1"
+    got_cc = st.search_batch(queries, 10, point_deleted=deleted)
+    os.environ.pop("QB_DISABLE_MMA", None)
+    want = sq.scan(codes, offs, 10, deleted=pack_bitmap(deleted))
+    for i in range(nq):
+        np.testing.assert_array_equal(got[i], got_cc[i])
+        assert_topk_equal(got[i], want[i], None, f"sq8-mma {dist} q={i}")
+    st.close()
