@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--cpu-sample-rows", type=int, default=CPU_SAMPLE_ROWS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"],
                     help="c2 = headline (single-query f32 cosine, default); c3 = 10Mx768 SQ8 cosine, 1024-query batch on the int8 tensor cores")
     ap.add_argument("--batch", type=int, default=1024, help="queries per batch (c3)")
     return ap.parse_args()
@@ -473,8 +473,103 @@ def main_c3(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ C4: PQ LUT scorer
+def main_c4(args):
+    """BASELINE configs[3]: 50M x 1536 PQ (m=96, 256 centroids), batch = 256, rows sharded over 8 GPUs.  Each rank holds
+    50M/8 = 6.25M rows; with --gpus 1 this measures ONE such shard (1/8 of the job) and says so.  Codes and centroids are
+    random (scoring cost does not depend on their values; parity is covered by tests/test_gpu_quant.py)."""
+    import torch
+    import torch.distributed as dist
+
+    from qdrant_b200 import scorer as qb
+    from qdrant_b200._capi import check, lib, vp
+    from qdrant_b200.sharded import ShardedSegmentSearcher
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total_rows, dim, chunk, nq, top = 50_000_000, 1536, 16, 256, TOP
+    if args.rows != N_ROWS:
+        total_rows = args.rows
+    n_local = total_rows // 8   # one of eight shards per rank, whatever N is
+    m = dim // chunk
+    rng = np.random.default_rng(100 + rank)
+    codes = rng.integers(0, 256, (n_local, m), dtype=np.uint8)
+    cents = np.random.default_rng(7).standard_normal((256, dim)).astype(np.float32) * 0.05
+    st = qb.ProductQuantizedVectors(codes, cents, chunk, dim, qb.Distance.Dot, device=local_rank)
+    del codes
+    queries = np.random.default_rng(45).standard_normal((nq, dim)).astype(np.float32)
+    searcher = ShardedSegmentSearcher(st, id_base=rank * n_local, top=top, max_queries=nq, device=dev)
+    searcher.d_queries.copy_(torch.from_numpy(queries).to(dev))
+    W, K = max(args.warmup, 3), args.steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        searcher.search_device(nq)
+    barrier()
+    st.profile(True)
+    launches0 = int(lib().qb_kernel_launch_count())
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(searcher.stream)
+    for _ in range(K):
+        searcher.search_device(nq)
+    ev1.record(searcher.stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = int(lib().qb_kernel_launch_count()) - launches0
+    n_prof, prof_ms = st.profile_read(reset=True)
+    st.profile(False)
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        searcher.search(queries)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        searcher.search(queries)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        lookups = float(nq) * n_local * m
+        kern_ms = prof_ms / max(n_prof, 1)
+        # shared-memory gather peak: 148 SMs x 32 banks x 4 B per clock at clocks.max.sm
+        smem_peak_glookups = 148 * 32 * 1.965
+        line = {"metric": f"queries/sec, {total_rows}x{dim} PQ(m={m},256) LUT scorer top-{top}, batch={nq}, {world} of 8 shards resident (BASELINE configs[3])",
+                "value": nq * K / (dev_ms / 1e3), "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes, f32 LUT sums", "data": "synthetic (random codes / centroids)",
+                "config": {"workload": f"PQ m={m} chunk={chunk}, {n_local} rows per GPU (= 50M/8), batch={nq}", "rows_per_gpu": n_local, "dim": dim, "m": m, "batch": nq,
+                           "l2": "code plane 600 MB per GPU > 126 MB L2"},
+                "e2e": {"value": nq * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top * 8 + nq * 4, "ms_per_step": e2e_ms / K},
+                "gpu_launches": launches, "clocks": clk,
+                "roofline": {"bound": "smem-gather", "kernel": "pq_scan_kernel (main pass)", "achieved": (lookups / (kern_ms / 1e3) / 1e9) if n_prof else None,
+                             "peak": smem_peak_glookups, "unit": "Glookup/s", "frac": (lookups / (kern_ms / 1e3) / 1e9 / smem_peak_glookups) if n_prof else None, "traffic": None,
+                             "peak_source": "148 SMs x 32 banks x clocks.max.sm (conflict-free 4-B shared-memory gathers); no such figure in MEASURED_PEAKS.json",
+                             "avg_launch_ms": kern_ms, "launches_timed": n_prof, "hbm_gb_per_s": (float(nq) * n_local * m / (kern_ms / 1e3) / 1e9) if n_prof else None}}
+        print(json.dumps(line))
+    del searcher
+    torch.cuda.synchronize()
+    st.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         sys.exit(main_reference(a))
-    sys.exit(main_c3(a) if a.config == "c3" else main_ours(a))
+    sys.exit({"c3": main_c3, "c4": main_c4}.get(a.config, main_ours)(a))

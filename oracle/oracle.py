@@ -29,9 +29,8 @@ SCORED = np.dtype([("idx", np.uint32), ("score", np.float32)])  # #[repr(C)] Sco
 
 
 def ensure_built() -> None:
-    need = not os.path.exists(os.path.join(_HERE, "liboracle.so")) or (
-        os.path.getmtime(os.path.join(_HERE, "liboracle.so")) < os.path.getmtime(os.path.join(_HERE, "oracle.c"))
-    )
+    so = os.path.join(_HERE, "liboracle.so")
+    need = not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "hnsw.c"))
     need_ref = not os.path.exists(os.path.join(_HERE, "_ref", "libsimd_utils.so")) and os.path.isdir(
         "/root/reference/lib/quantization/cpp"
     )
@@ -112,6 +111,12 @@ def lib() -> C.CDLL:
         L.qo_score_rows_f32.argtypes = [C.c_int, f32p, C.c_uint64, C.c_uint32, f32p, f32p]
         L.qo_preprocess_rows_f32.restype = None
         L.qo_preprocess_rows_f32.argtypes = [C.c_int, f32p, f32p, C.c_uint64, C.c_uint32]
+        L.qo_hnsw_build.restype = C.c_void_p
+        L.qo_hnsw_build.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.qo_hnsw_search.restype = C.c_uint32
+        L.qo_hnsw_search.argtypes = [C.c_void_p, f32p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.qo_hnsw_stats.restype, L.qo_hnsw_stats.argtypes = None, [C.c_void_p, u64p, u64p, C.c_int]
+        L.qo_hnsw_free.restype, L.qo_hnsw_free.argtypes = None, [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -451,3 +456,40 @@ class BQ:
         lib().qo_scan_bq(_p(rows, C.c_uint8), 0, rows.shape[0], self.dim, self.encoding, self.query_bits, self.distance_type, int(self.invert),
                          _p(q_encs, C.c_uint8), q_encs.shape[1], nq, top, dp, out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
         return [out[i, : counts[i]].copy() for i in range(nq)]
+
+
+# ------------------------------------------------------------------ HNSW traversal driver (config #5 harness)
+HNSW_SCORE_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_float))
+
+
+class HNSW:
+    """From-spec CPU HNSW (oracle/hnsw.c): graph built with CPU scoring; search() drives the traversal either with the
+    CPU oracle scorer (score_points=None) or with any callable ids -> scores (e.g. a GPU RawScorer.score_points)."""
+
+    def __init__(self, base, distance: int, m: int = 16, ef_construct: int = 100, seed: int = 42):
+        self.base = _f32(base)
+        self.distance = distance
+        self._h = lib().qo_hnsw_build(_p(self.base, C.c_float), self.base.shape[0], self.base.shape[1], distance, m, ef_construct, seed)
+
+    def search(self, query_pre, top: int, ef: int, score_points=None) -> np.ndarray:
+        q = _f32(query_pre)
+        out = np.zeros(max(top, 1), dtype=SCORED)
+        cb = None
+        if score_points is not None:
+            def _cb(user, ids, n, scores):
+                a = np.ctypeslib.as_array(ids, shape=(n,))
+                res = score_points(a)
+                np.ctypeslib.as_array(scores, shape=(n,))[:] = res
+            cb = HNSW_SCORE_CB(_cb)
+        n = lib().qo_hnsw_search(self._h, _p(q, C.c_float), C.cast(cb, C.c_void_p) if cb else None, None, top, ef, out.ctypes.data_as(C.c_void_p))
+        return out[:n].copy()
+
+    def stats(self, reset=True):
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().qo_hnsw_stats(self._h, C.byref(a), C.byref(b), int(reset))
+        return int(a.value), int(b.value)
+
+    def close(self):
+        if self._h:
+            lib().qo_hnsw_free(self._h)
+            self._h = None

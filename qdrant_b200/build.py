@@ -36,7 +36,9 @@ def stale() -> bool:
         return True
     t = os.path.getmtime(OUT)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + [
-        os.path.join(HERE, "..", "include", "qb200.h")]
+        os.path.join(HERE, "..", "include", "qb200.h")] + glob.glob(os.path.join(HERE, "host", "*"))
+    if not os.path.exists(os.path.join(OUT_DIR, "host_selftest")):
+        return True
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -71,6 +73,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
+    # C++ host-side mirror self-test (drives the .so through qdrant_b200/host/qdrant_b200.hpp)
+    host = os.path.join(HERE, "host")
+    cmd = ["g++", "-std=c++17", "-O2", "-I", host, os.path.join(host, "host_selftest.cpp"), "-L", OUT_DIR, "-lqdrant_b200",
+           "-Wl,-rpath,$ORIGIN", "-o", os.path.join(OUT_DIR, "host_selftest")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("host_selftest build failed")
     return OUT
 
 

@@ -540,7 +540,13 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             // pass 1: sample prefix, materialised densely -> per-query threshold = k-th best of the sample
             a.row_begin = 0; a.row_end = plan.sample;
             a.emit.dense = 1; a.emit.dense_base = 0;
-            QB_TRY(qb_launch_scan(s, a, stream));
+            const uint32_t mma_blk = (!d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr) ? qb_sq8_mma_block(s, qn) : 0;
+            if (mma_blk) {
+                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), (uint32_t)round_up_u64(qn, mma_blk), a.d_q_off, qn, mma_blk, 0, plan.sample,
+                                       a.emit, d_overflow, stream));
+            } else {
+                QB_TRY(qb_launch_scan(s, a, stream));
+            }
             QB_TRY(qb_launch_select(c->d_cand, nullptr, plan.cap, plan.sample, qn, top, 1, nullptr, nullptr, c->d_thr + q0, nullptr, stream));
             // pass 2: everything, keeping only score >= threshold
             QB_CUDA(cudaMemsetAsync(c->d_cnt + q0, 0, (size_t)qn * 4, stream));
@@ -548,7 +554,6 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             a.emit.dense = 0; a.emit.thr = c->d_thr + q0; a.emit.cnt = c->d_cnt + q0;
             if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
             profile_begin(s, c, stream, &e0, &e1);
-            const uint32_t mma_blk = (!d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr) ? qb_sq8_mma_block(s, qn) : 0;
             if (mma_blk) {
                 // batched SQ8: tensor-core GEMM with the fused epilogue/filter (qb_sq8_mma.cu)
                 const uint32_t nq_pad = (uint32_t)round_up_u64(qn, mma_blk);

@@ -153,6 +153,15 @@ __device__ __forceinline__ void qb_mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s at 2 GHz
     }
 }
+// same, for producers that run far ahead of their consumers: back off between polls so the spin does not compete for issue slots
+__device__ __forceinline__ void qb_mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    if (qb_mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!qb_mbar_try_wait(bar, parity)) {
+        __nanosleep(100);
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes, src, dst 16-B aligned)
 __device__ __forceinline__ void qb_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile(

@@ -10,9 +10,9 @@
 // and the fused threshold filter that feeds the top-k selection (the N x 10M score matrix is never materialised).
 //
 // Layout / pipeline (one persistent CTA per SM, 10 warps):
-//   warp 0   TMA producer: the CTA's query block B (N <= 256 queries x K bytes, 128-B-swizzled K-blocks) is loaded
-//            once and stays resident in shared memory; vector-code tiles A (128 rows x 64 B, 64-B swizzle) stream
-//            through a 4-stage ring.
+//   warp 0   TMA producer: the CTA's query block B (N <= 256 queries x K bytes, 128-B-swizzled K-blocks; 208 at K=768 so that a 64 KB A ring fits) is loaded
+//            once and stays resident in shared memory; vector-code tiles A (128 rows x 128 B, 128-B swizzle) stream
+//            through a 4-stage (64 KB) ring.
 //   warp 1   allocates 512 TMEM columns (two N-column s32 accumulators) and issues tcgen05.mma (M=128, N, K=32)
 //            from one lane; tcgen05.commit releases smem stages and publishes finished accumulators.
 //   warps 2-9 epilogue: tcgen05.ld (lane = vector row, column = query), exact int->f32, three-rounding epilogue,
@@ -30,9 +30,9 @@
 namespace {
 
 constexpr int MMA_M = 128;
-constexpr int A_KB = 64;                    // K bytes per A stage (one 64-B swizzle atom wide)
+constexpr int A_KB = 128;                   // K bytes per A stage (one 128-B swizzle atom wide)
 constexpr int A_STAGES = 4;
-constexpr int A_STAGE_BYTES = MMA_M * A_KB;  // 8 KB
+constexpr int A_STAGE_BYTES = MMA_M * A_KB;  // 16 KB
 constexpr int B_KB = 128;                   // K bytes per resident B block (128-B swizzle)
 constexpr int N_MAX = 256;
 constexpr int EPI_WARPS = 8;
@@ -51,6 +51,7 @@ struct MmaParams {
     const float* q_off;     // [nq]
     unsigned int* flags;    // bit 1: a dot product reached 2^24 (inexact for the f32 tree)
     int check_exact;
+    int prefilter;          // 1: multiplier > 0 -> integer-domain prefilter in the epilogue
 };
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1, uint64_t policy) {
@@ -59,6 +60,10 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
             qb_smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(qb_smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
+}
+// L2 prefetch of a tile box (no shared-memory destination): later TMA loads of the same box hit L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -92,6 +97,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Exact epilogue of one (vector, query) pair: int -> f32 (exact), three roundings (encoded_vectors_u8.rs:101-103), emit.
+__device__ __noinline__ void epilogue_exact(const MmaParams& p, const QbEmit& emit, uint32_t dot, uint32_t n, uint32_t q_base, uint64_t row,
+                                            bool valid_row, bool dead, float v_off, float mult, const float* qoff_s, const float* thr_s) {
+    if (n >= p.n_blk) return;
+    float f = __uint_as_float(dot | 0x4B000000u) - 8388608.0f;  // exact for dot < 2^23
+    if (dot >= 0x800000u) {
+        f = (float)dot;
+        if (p.check_exact && dot >= 0x1000000u) atomicOr(p.flags, 2u);
+    }
+    const float sc = __fadd_rn(__fadd_rn(__fmul_rn(mult, f), qoff_s[n]), v_off);
+    const uint32_t q = q_base + n;
+    if (emit.dense) {
+        if (valid_row && q < p.nq)
+            emit.cand[(unsigned long long)q * emit.cap + (row - emit.dense_base)] = dead ? 0ull : qb_pack_key(sc, (uint32_t)row + emit.id_base);
+    } else if (sc >= thr_s[n] && !dead) {
+        const unsigned int pos = atomicAdd(&emit.cnt[q], 1u);
+        if (pos < emit.cap) emit.cand[(unsigned long long)q * emit.cap + pos] = qb_pack_key(sc, (uint32_t)row + emit.id_base);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const MmaParams p, const QbEmit emit) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -104,7 +129,8 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* a_s = b_s + (size_t)n_kb_b * b_block_bytes;
     float* thr_s = reinterpret_cast<float*>(a_s + A_STAGES * A_STAGE_BYTES);
     float* qoff_s = thr_s + N_MAX;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qoff_s + N_MAX);
+    float* c_s = qoff_s + N_MAX;  // prefilter: 2^23 + (thr - q_off) / mult - slack
+    uint64_t* bars = reinterpret_cast<uint64_t*>(c_s + N_MAX);
     uint64_t* full_a = bars;                 // [A_STAGES]
     uint64_t* empty_a = bars + A_STAGES;     // [A_STAGES]
     uint64_t* b_full = bars + 2 * A_STAGES;  // [1]
@@ -128,8 +154,13 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (uint32_t i = threadIdx.x; i < N_MAX; i += blockDim.x) {
         const uint32_t q = q_base + i;
         const bool real = (i < p.n_blk) && (q < p.nq);
-        thr_s[i] = real ? emit.thr[q] : __int_as_float(0x7f800000);  // +inf: padded queries never emit
-        qoff_s[i] = real ? p.q_off[q] : 0.0f;
+        const float th = real ? (emit.dense ? __int_as_float(0xff800000) : emit.thr[q]) : __int_as_float(0x7f800000);  // +inf: padded queries never emit
+        const float qo = real ? p.q_off[q] : 0.0f;
+        thr_s[i] = th;
+        qoff_s[i] = qo;
+        // score >= thr  <=>  2^23 + dot >= 2^23 + (thr - q_off - v_off)/mult   (mult > 0); slack of 8 dot units covers every rounding here
+        const float tq = (th - qo) / p.multiplier;
+        c_s[i] = (p.prefilter && !emit.dense) ? (8388608.0f + tq - (8.0f + 1.0e-5f * fabsf(tq))) : __int_as_float(0xff800000);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(qb_smem_u32(tmem_ptr_s)), "r"(TMEM_COLS) : "memory");
@@ -148,9 +179,18 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             qb_mbar_arrive_expect_tx(b_full, n_kb_b * b_block_bytes);
             for (uint32_t kb = 0; kb < n_kb_b; ++kb) tma_load_2d(&map_b, b_full, b_s + (size_t)kb * b_block_bytes, (int32_t)(kb * B_KB), (int32_t)q_base, pol_keep);
             uint64_t it = 0;
+            constexpr uint64_t PF = 3;  // L2 prefetch distance in tiles: hides the HBM latency that a 64 KB smem ring cannot
             for (uint64_t ti = 0; ti < my_tiles; ++ti) {
                 const uint64_t tile = worker + ti * p.n_workers;
                 const int32_t row0 = (int32_t)(tile * MMA_M);
+                {   // the n_qblocks CTAs of a worker group walk the same tiles: each prefetches its share of the K-blocks
+                    const uint64_t pt = (ti == 0) ? 0 : PF;
+                    for (uint64_t d = pt; d <= PF; ++d) {
+                        const uint64_t tile_pf = worker + (ti + d) * p.n_workers;
+                        if (ti + d < my_tiles)
+                            for (uint32_t ka = qblock; ka < n_ka; ka += p.n_qblocks) tma_prefetch_2d(&map_a, (int32_t)(ka * A_KB), (int32_t)(tile_pf * MMA_M));
+                    }
+                }
                 for (uint32_t ka = 0; ka < n_ka; ++ka, ++it) {
                     const uint32_t s = (uint32_t)(it % A_STAGES), ph = (uint32_t)((it / A_STAGES) & 1);
                     qb_mbar_wait(&empty_a[s], ph ^ 1u);
@@ -182,7 +222,7 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (uint32_t j = 0; j < A_KB / 32; ++j) {
                         const uint32_t kbyte = ka * A_KB + j * 32;
                         if (kbyte < p.ad) {
-                            const uint64_t a_desc = make_smem_desc(a_addr0 + s * A_STAGE_BYTES + j * 32, 8 * A_KB, 4);
+                            const uint64_t a_desc = make_smem_desc(a_addr0 + s * A_STAGE_BYTES + j * 32, 8 * A_KB, 2);
                             const uint64_t b_desc = make_smem_desc(b_addr0 + (kbyte / B_KB) * b_block_bytes + (kbyte % B_KB), 8 * B_KB, 2);
                             mma_i8(d_tmem, a_desc, b_desc, idesc, (ka | j) != 0 ? 1u : 0u);
                         }
@@ -208,23 +248,31 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool dead = !valid_row || qb_is_deleted(emit, (uint32_t)(valid_row ? row : 0));
             qb_mbar_wait(&tm_full[acc], acc_ph);
             tc_fence_after();
+            // subtracting a slightly larger value only makes the prefilter more permissive (never a false negative)
+            const float v_over_m = p.prefilter ? (v_off / mult + 4.0e-6f * fabsf(v_off / mult)) : 0.0f;
             for (uint32_t c = half; c < n_chunks; c += 2) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + ((quarter * 32u) << 16) + acc * p.n_blk + c * 16, r);
+                // Branch-free prefilter (3 full-rate instructions per element, small code): the float rhs = 2^23 + dot_threshold
+                // lies in [2^23, 2^24) in the common case, where (bits(rhs) - 0x4B000000) IS the integer threshold; outside that
+                // window the derived threshold is only ever lower than the true one (more permissive, never a false negative).
+                const float4* c4 = reinterpret_cast<const float4*>(c_s + c * 16);
+                int hit = -1;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t dot = r[j];
-                    float f = __uint_as_float(dot | 0x4B000000u) - 8388608.0f;  // exact for dot < 2^23, full-rate pipes
-                    if (dot >= 0x800000u) {
-                        f = (float)dot;
-                        if (p.check_exact && dot >= 0x1000000u) atomicOr(p.flags, 2u);
-                    }
-                    const uint32_t n = c * 16 + j;
-                    const float sc = __fadd_rn(__fadd_rn(__fmul_rn(mult, f), qoff_s[n]), v_off);
-                    if (sc >= thr_s[n] && !dead) {
-                        const uint32_t q = q_base + n;
-                        const unsigned int pos = atomicAdd(&emit.cnt[q], 1u);
-                        if (pos < emit.cap) emit.cand[(unsigned long long)q * emit.cap + pos] = qb_pack_key(sc, (uint32_t)row + emit.id_base);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 cc = c4[j4];
+                    hit = max(hit, (int)r[j4 * 4 + 0] - (__float_as_int(cc.x - v_over_m) - 0x4B000000));
+                    hit = max(hit, (int)r[j4 * 4 + 1] - (__float_as_int(cc.y - v_over_m) - 0x4B000000));
+                    hit = max(hit, (int)r[j4 * 4 + 2] - (__float_as_int(cc.z - v_over_m) - 0x4B000000));
+                    hit = max(hit, (int)r[j4 * 4 + 3] - (__float_as_int(cc.w - v_over_m) - 0x4B000000));
+                }
+                if (hit >= 0) {  // rare (or dense mode): exact scoring of this 16-column chunk, out of line to keep the hot loop in the I-cache
+#pragma unroll 1
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t dot = 0;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) dot = (k == j) ? r[k] : dot;   // register select, no local memory
+                        epilogue_exact(p, emit, dot, c * 16 + j, q_base, row, valid_row, dead, v_off, mult, qoff_s, thr_s);
                     }
                 }
             }
@@ -275,10 +323,14 @@ uint32_t qb_sq8_mma_block(const qb_storage* s, uint32_t nq) {
     if (s->kind != QB_KIND_SQ8 || s->qdist == QB_QD_L1) return 0;
     if (nq < 32 || s->count < 4 * 128) return 0;
     const uint32_t n_kb_b = (s->actual_dim + B_KB - 1) / B_KB;
-    uint32_t n_blk = (uint32_t)((192 * 1024) / ((size_t)n_kb_b * B_KB));
+    // resident query block + A ring + thresholds/barriers must fit 227 KB
+    const size_t budget = 227 * 1024 - (size_t)A_STAGES * A_STAGE_BYTES - (3 * N_MAX * 4 + 16 * 8 + 16);
+    uint32_t n_blk = (uint32_t)(budget / ((size_t)n_kb_b * B_KB));
     n_blk = (n_blk > (uint32_t)N_MAX ? (uint32_t)N_MAX : n_blk) & ~15u;
     if (n_blk < 16) return 0;
-    if (nq < n_blk) n_blk = (nq + 15u) & ~15u;  // a single, narrower block
+    // balance: same number of blocks, equal width (1024 queries at K=768: 5 blocks of 208)
+    const uint32_t n_qblocks = (nq + n_blk - 1) / n_blk;
+    n_blk = (((nq + n_qblocks - 1) / n_qblocks) + 15u) & ~15u;
     return n_blk;
 }
 
@@ -286,24 +338,25 @@ uint32_t qb_sq8_mma_block(const qb_storage* s, uint32_t nq) {
 qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_t nq_pad, const float* d_q_off, uint32_t nq, uint32_t n_blk,
                           uint64_t row_begin, uint64_t row_end, const QbEmit& emit, unsigned int* d_flags, cudaStream_t stream) {
     QB_CHECK(row_begin == 0, QB_ERR_INVALID, "sq8_mma_scan: scans start at row 0");
-    QB_CHECK(!emit.dense && emit.thr && emit.cnt, QB_ERR_INVALID, "sq8_mma_scan: filter-mode emission only");
+    QB_CHECK(emit.dense || (emit.thr && emit.cnt), QB_ERR_INVALID, "sq8_mma_scan: filter mode needs thresholds and counters");
     const uint32_t ad = s->actual_dim;
     const uint32_t n_qblocks = (nq + n_blk - 1) / n_blk;
     QB_CHECK(nq_pad >= n_qblocks * n_blk, QB_ERR_INVALID, "sq8_mma_scan: query buffer not padded");
     CUtensorMap map_a, map_b;
-    QB_TRY(make_map_u8(&map_a, s->d_codes, ad, row_end, A_KB, MMA_M, CU_TENSOR_MAP_SWIZZLE_64B));
+    QB_TRY(make_map_u8(&map_a, s->d_codes, ad, row_end, A_KB, MMA_M, CU_TENSOR_MAP_SWIZZLE_128B));
     QB_TRY(make_map_u8(&map_b, d_q_codes, ad, nq_pad, B_KB, n_blk, CU_TENSOR_MAP_SWIZZLE_128B));
     MmaParams p{};
     p.voff = s->d_voff; p.n_rows = row_end; p.ad = ad; p.n_blk = n_blk; p.n_qblocks = n_qblocks; p.nq = nq;
     p.multiplier = s->multiplier; p.q_off = d_q_off; p.flags = d_flags;
     p.check_exact = ((uint64_t)ad * 127ull * 127ull >= (1ull << 24)) ? 1 : 0;
+    p.prefilter = (s->multiplier > 0.0f) ? 1 : 0;
     uint32_t workers = (uint32_t)s->sm_count / n_qblocks;
     if (workers < 1) workers = 1;
     const uint64_t n_tiles = (row_end + MMA_M - 1) / MMA_M;
     if (workers > n_tiles) workers = (uint32_t)n_tiles;
     p.n_workers = workers;
     const uint32_t n_kb_b = (ad + B_KB - 1) / B_KB;
-    const size_t smem = (size_t)n_kb_b * n_blk * B_KB + A_STAGES * A_STAGE_BYTES + 2 * N_MAX * 4 + 16 * 8 + 16;
+    const size_t smem = (size_t)n_kb_b * n_blk * B_KB + A_STAGES * A_STAGE_BYTES + 3 * N_MAX * 4 + 16 * 8 + 16;
     QB_CHECK(smem <= 227 * 1024, QB_ERR_INVALID, "sq8_mma_scan: shared memory %zu exceeds 227 KB", smem);
     QB_CUDA(cudaFuncSetAttribute(sq8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sq8_mma_kernel<<<workers * n_qblocks, THREADS, smem, stream>>>(map_a, map_b, p, emit);
