@@ -73,7 +73,11 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.mark_at = index, None, [], 0
+
+    def mark(self):
+        """Call at the start of the timed region: only samples taken after this point are reported."""
+        self.mark_at = len(self.lines)
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -99,7 +103,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for l in self.lines:
+        lines = self.lines[self.mark_at:] or self.lines[-3:]   # a region shorter than one sampling period: nearest samples
+        for l in lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -252,6 +257,11 @@ def main_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)   # nvidia-smi start-up
+    for i in range(3):
+        step_device(i)       # every rank (collective inside): keep the GPUs under load while the first samples arrive
+    if rank == 0:
+        clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
@@ -396,6 +406,11 @@ def main_c3(args):
     launches0 = int(lib().qb_kernel_launch_count())
     clocks = ClockSampler(0)
     clocks.start()
+    time.sleep(0.3)
+    for _ in range(2):
+        step_device()
+    torch.cuda.synchronize()
+    clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(K):
@@ -518,6 +533,8 @@ def main_c4(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)
+        clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(searcher.stream)

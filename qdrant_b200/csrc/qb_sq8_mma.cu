@@ -88,13 +88,21 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+// asynchronous TMEM -> register load of 16 columns for the warp's 32 lanes; results are valid only after tmem_ld_wait(r)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the "+r" operands tie the registers to the wait so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 }
 
 // Exact epilogue of one (vector, query) pair: int -> f32 (exact), three roundings (encoded_vectors_u8.rs:101-103), emit.
@@ -114,6 +122,35 @@ __device__ __noinline__ void epilogue_exact(const MmaParams& p, const QbEmit& em
     } else if (sc >= thr_s[n] && !dead) {
         const unsigned int pos = atomicAdd(&emit.cnt[q], 1u);
         if (pos < emit.cap) emit.cand[(unsigned long long)q * emit.cap + pos] = qb_pack_key(sc, (uint32_t)row + emit.id_base);
+    }
+}
+
+// Filter one 16-column chunk of the accumulator row held by this lane (see the kernel comment for the arithmetic).
+__device__ __forceinline__ void epilogue_chunk(const MmaParams& p, const QbEmit& emit, uint32_t (&r)[16], uint32_t c, const float* c_s, float v_over_m,
+                                               uint32_t q_base, uint64_t row, bool valid_row, bool dead, float v_off, float mult, const float* qoff_s,
+                                               const float* thr_s) {
+    // Branch-free prefilter (3 full-rate instructions per element, small code): the float rhs = 2^23 + dot_threshold
+    // lies in [2^23, 2^24) in the common case, where (bits(rhs) - 0x4B000000) IS the integer threshold; outside that
+    // window the derived threshold is only ever lower than the true one (more permissive, never a false negative).
+    const float4* c4 = reinterpret_cast<const float4*>(c_s + c * 16);
+    int d[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 cc = c4[j4];
+        d[j4 * 4 + 0] = (int)r[j4 * 4 + 0] - (__float_as_int(cc.x - v_over_m) - 0x4B000000);
+        d[j4 * 4 + 1] = (int)r[j4 * 4 + 1] - (__float_as_int(cc.y - v_over_m) - 0x4B000000);
+        d[j4 * 4 + 2] = (int)r[j4 * 4 + 2] - (__float_as_int(cc.z - v_over_m) - 0x4B000000);
+        d[j4 * 4 + 3] = (int)r[j4 * 4 + 3] - (__float_as_int(cc.w - v_over_m) - 0x4B000000);
+    }
+    int hit = d[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) hit = max(hit, d[j]);
+    // ~0.01-0.05 % of the elements survive, but the branch is per warp (32 rows x 16 queries): keep the taken path cheap too —
+    // one predicated out-of-line call per surviving column, nothing for the others
+    if (__any_sync(0xFFFFFFFFu, hit >= 0)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (d[j] >= 0) epilogue_exact(p, emit, r[j], c * 16 + j, q_base, row, valid_row, dead, v_off, mult, qoff_s, thr_s);
     }
 }
 
@@ -250,31 +287,23 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_after();
             // subtracting a slightly larger value only makes the prefilter more permissive (never a false negative)
             const float v_over_m = p.prefilter ? (v_off / mult + 4.0e-6f * fabsf(v_off / mult)) : 0.0f;
-            for (uint32_t c = half; c < n_chunks; c += 2) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((quarter * 32u) << 16) + acc * p.n_blk + c * 16, r);
-                // Branch-free prefilter (3 full-rate instructions per element, small code): the float rhs = 2^23 + dot_threshold
-                // lies in [2^23, 2^24) in the common case, where (bits(rhs) - 0x4B000000) IS the integer threshold; outside that
-                // window the derived threshold is only ever lower than the true one (more permissive, never a false negative).
-                const float4* c4 = reinterpret_cast<const float4*>(c_s + c * 16);
-                int hit = -1;
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 cc = c4[j4];
-                    hit = max(hit, (int)r[j4 * 4 + 0] - (__float_as_int(cc.x - v_over_m) - 0x4B000000));
-                    hit = max(hit, (int)r[j4 * 4 + 1] - (__float_as_int(cc.y - v_over_m) - 0x4B000000));
-                    hit = max(hit, (int)r[j4 * 4 + 2] - (__float_as_int(cc.z - v_over_m) - 0x4B000000));
-                    hit = max(hit, (int)r[j4 * 4 + 3] - (__float_as_int(cc.w - v_over_m) - 0x4B000000));
-                }
-                if (hit >= 0) {  // rare (or dense mode): exact scoring of this 16-column chunk, out of line to keep the hot loop in the I-cache
-#pragma unroll 1
-                    for (int j = 0; j < 16; ++j) {
-                        uint32_t dot = 0;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) dot = (k == j) ? r[k] : dot;   // register select, no local memory
-                        epilogue_exact(p, emit, dot, c * 16 + j, q_base, row, valid_row, dead, v_off, mult, qoff_s, thr_s);
-                    }
-                }
+            // software pipeline: the TMEM load of the next chunk is in flight while the current one is filtered
+            const uint32_t t_row = tmem_base + ((quarter * 32u) << 16) + acc * p.n_blk;
+            uint32_t ra[16], rb[16];
+            uint32_t c = half;
+            if (c < n_chunks) { tmem_ld16_issue(t_row + c * 16, ra); tmem_ld_wait(ra); }
+            while (c < n_chunks) {
+                const uint32_t c1 = c + 2;
+                if (c1 < n_chunks) tmem_ld16_issue(t_row + c1 * 16, rb);
+                epilogue_chunk(p, emit, ra, c, c_s, v_over_m, q_base, row, valid_row, dead, v_off, mult, qoff_s, thr_s);
+                if (c1 >= n_chunks) break;
+                tmem_ld_wait(rb);
+                const uint32_t c2 = c1 + 2;
+                if (c2 < n_chunks) tmem_ld16_issue(t_row + c2 * 16, ra);
+                epilogue_chunk(p, emit, rb, c1, c_s, v_over_m, q_base, row, valid_row, dead, v_off, mult, qoff_s, thr_s);
+                if (c2 >= n_chunks) break;
+                tmem_ld_wait(ra);
+                c = c2;
             }
             tc_fence_before();
             __syncwarp();

@@ -36,7 +36,7 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
     __shared__ unsigned long long buf[SORT_CAP];
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_kk, s_fill, s_short;
+    __shared__ unsigned int s_kk, s_fill, s_short, s_done;
 
     const uint32_t q = blockIdx.x;
     unsigned long long n;
@@ -58,10 +58,12 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
         m = (int)n;
         __syncthreads();
     } else {
-        if (threadIdx.x == 0) { s_prefix = 0ull; s_kk = top; s_short = 0u; }
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_kk = top; s_short = 0u; s_done = 0u; }
         unsigned long long mask = 0ull;
         __syncthreads();
-        for (int pass = 0; pass < 8; ++pass) {
+        // threshold mode only needs the k-th SCORE (high 32 bits of the key): 4 passes instead of 8
+        const int n_pass = (mode == 1) ? 4 : 8;
+        for (int pass = 0; pass < n_pass; ++pass) {
             const int shift = 56 - 8 * pass;
             for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
             __syncthreads();
@@ -79,21 +81,40 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
                 if (valid && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned int kk = s_kk, cum = 0;
-                int d = 255;
-                for (; d >= 0; --d) {
-                    unsigned int h = hist[d];
-                    if (cum + h >= kk) break;
-                    cum += h;
+            if (threadIdx.x < 32) {
+                // warp-parallel descending scan of the 256 bins: lane l owns bins 255-8l .. 248-8l
+                const int lane = threadIdx.x;
+                unsigned int h[8], local = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { h[k] = hist[255 - 8 * lane - k]; local += h[k]; }
+                unsigned int incl = local;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+                const unsigned int excl = incl - local;       // keys in strictly higher bins than this lane's group
+                const unsigned int kk = s_kk;
+                __syncwarp();
+                const unsigned int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const bool mine = (excl < kk) && (incl >= kk);  // the k-th key falls into one of my 8 bins
+                if (total < kk) { if (lane == 0) s_short = 1u; }
+                else if (mine) {
+                    unsigned int cum = excl;
+                    int k = 0;
+                    for (; k < 8; ++k) { if (cum + h[k] >= kk) break; cum += h[k]; }
+                    const int d = 255 - 8 * lane - k;
+                    s_kk = kk - cum;
+                    s_prefix = prefix | ((unsigned long long)d << shift);
+                    // every key of the chosen bin is needed: the remaining low bits cannot change the selected set
+                    if (h[k] == kk - cum && mode == 0) s_done = 1u;
                 }
-                if (d < 0) { s_short = 1u; d = 0; cum = 0; }  // fewer than `top` keys in total
-                else s_kk = kk - cum;
-                s_prefix = prefix | ((unsigned long long)d << shift);
             }
             mask |= (255ull << shift);
             __syncthreads();
-            if (s_short) break;
+            if (s_short || s_done) break;
+        }
+        if (mode == 1) {
+            // high word 0 == the empty key (fewer than `top` valid candidates): no threshold
+            if (threadIdx.x == 0) thr[q] = (s_short || (s_prefix >> 32) == 0ull) ? __int_as_float(0xff800000) : qb_unorderable((uint32_t)(s_prefix >> 32));
+            return;
         }
         const unsigned long long kth = s_short ? 1ull : s_prefix;  // short: take every non-empty key
         if (threadIdx.x == 0) s_fill = 0u;
