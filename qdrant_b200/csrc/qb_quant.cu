@@ -252,6 +252,59 @@ __global__ void __launch_bounds__(512) pq_scan_kernel(const PqParams p, const Qb
     }
 }
 
+
+// Two queries per pass: their LUTs are interleaved as float2 in shared memory (2 x m x 256 x 4 B = 192 KB at m = 96), so one
+// 64-bit shared load serves both queries and every code byte is decoded once per PAIR.  Same four-lane summation order.
+__global__ void __launch_bounds__(1024, 1) pq_scan2_kernel(const PqParams p, const QbEmit emit) {
+    extern __shared__ __align__(16) float lut_s[];
+    float2* lut2 = reinterpret_cast<float2*>(lut_s);
+    const uint64_t n = p.end - p.begin;
+    const size_t lut_elems = (size_t)p.m * p.n_centroids;
+    const uint32_t K = p.n_centroids;
+    const uint32_t m4 = p.m & ~3u;
+    for (uint32_t q = 0; q < p.nq; q += 2) {
+        const bool two = (q + 1 < p.nq);
+        const float* la = p.luts + (size_t)q * lut_elems;
+        const float* lb = p.luts + (size_t)(two ? q + 1 : q) * lut_elems;
+        __syncthreads();
+        for (size_t i = threadIdx.x; i < lut_elems; i += blockDim.x) lut2[i] = make_float2(la[i], lb[i]);
+        __syncthreads();
+        for (uint64_t ci = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t cand = p.begin + ci;
+            const uint32_t row = p.ids ? p.ids[cand] : (uint32_t)cand;
+            const uint8_t* code = p.codes + (size_t)row * p.stride;
+            float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            uint32_t j = 0;
+            for (; j + 16 <= m4; j += 16) {
+                const uint4 cw = *reinterpret_cast<const uint4*>(code + j);
+                const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2* l = lut2 + (size_t)(j + 4 * k) * K;
+                    const float2 a = l[w[k] & 255u], b = l[K + ((w[k] >> 8) & 255u)], c = l[2 * K + ((w[k] >> 16) & 255u)], d = l[3 * K + (w[k] >> 24)];
+                    s0.x = __fadd_rn(s0.x, a.x); s0.y = __fadd_rn(s0.y, a.y);
+                    s1.x = __fadd_rn(s1.x, b.x); s1.y = __fadd_rn(s1.y, b.y);
+                    s2.x = __fadd_rn(s2.x, c.x); s2.y = __fadd_rn(s2.y, c.y);
+                    s3.x = __fadd_rn(s3.x, d.x); s3.y = __fadd_rn(s3.y, d.y);
+                }
+            }
+            for (; j < m4; j += 4) {
+                const float2* l = lut2 + (size_t)j * K;
+                const float2 a = l[code[j]], b = l[K + code[j + 1]], c = l[2 * K + code[j + 2]], d = l[3 * K + code[j + 3]];
+                s0.x = __fadd_rn(s0.x, a.x); s0.y = __fadd_rn(s0.y, a.y);
+                s1.x = __fadd_rn(s1.x, b.x); s1.y = __fadd_rn(s1.y, b.y);
+                s2.x = __fadd_rn(s2.x, c.x); s2.y = __fadd_rn(s2.y, c.y);
+                s3.x = __fadd_rn(s3.x, d.x); s3.y = __fadd_rn(s3.y, d.y);
+            }
+            float sa = __fadd_rn(__fadd_rn(s0.x, s2.x), __fadd_rn(s1.x, s3.x));
+            float sb = __fadd_rn(__fadd_rn(s0.y, s2.y), __fadd_rn(s1.y, s3.y));
+            for (; j < p.m; ++j) { const float2 t = lut2[(size_t)j * K + code[j]]; sa = __fadd_rn(sa, t.x); sb = __fadd_rn(sb, t.y); }
+            qb_emit(emit, q, cand, row, sa);
+            if (two) qb_emit(emit, q + 1, cand, row, sb);
+        }
+    }
+}
+
 // score_internal (encoded_vectors_pq.rs:574-618): decode both codes through the centroids; single pair
 __global__ void pq_score_internal_kernel(const uint8_t* __restrict__ codes, uint32_t stride, uint32_t m, const uint32_t* __restrict__ div,
                                          const float* __restrict__ centroids, uint32_t dim, int qdist, int invert, uint32_t a, uint32_t b,
@@ -508,6 +561,16 @@ static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cu
     if (n == 0 || p.nq == 0) return QB_OK;
     p.codes = s->d_pq_codes; p.stride = s->pq_stride; p.m = s->pq_m; p.n_centroids = s->n_centroids;
     const size_t lut_bytes = (size_t)s->pq_m * s->n_centroids * sizeof(float);
+    if (p.emit_mode && p.nq >= 2 && 2 * lut_bytes <= 224 * 1024 && n >= 65536) {
+        // batched scans: two queries per pass (interleaved LUTs)
+        QB_CUDA(cudaFuncSetAttribute(pq_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        uint64_t blocks2 = ceil_div_u64(n, 1024);
+        if (blocks2 > (uint64_t)s->sm_count) blocks2 = (uint64_t)s->sm_count;
+        pq_scan2_kernel<<<(unsigned)blocks2, 1024, 2 * lut_bytes, stream>>>(p, e);
+        QB_LAUNCHED();
+        QB_CUDA(cudaGetLastError());
+        return QB_OK;
+    }
     p.lut_in_smem = (lut_bytes <= 200 * 1024 && n >= 4096) ? 1 : 0;
     const size_t smem = p.lut_in_smem ? lut_bytes : 0;
     if (smem > 48 * 1024) QB_CUDA(cudaFuncSetAttribute(pq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -9,13 +9,13 @@
 //      score = multiplier * f32(dot) + q_off[q] + v_off[v]              (encoded_vectors_u8.rs:101-103)
 // and the fused threshold filter that feeds the top-k selection (the N x 10M score matrix is never materialised).
 //
-// Layout / pipeline (one persistent CTA per SM, 10 warps):
+// Layout / pipeline (one persistent CTA per SM, 18 warps):
 //   warp 0   TMA producer: the CTA's query block B (N <= 256 queries x K bytes, 128-B-swizzled K-blocks; 208 at K=768 so that a 64 KB A ring fits) is loaded
 //            once and stays resident in shared memory; vector-code tiles A (128 rows x 128 B, 128-B swizzle) stream
 //            through a 4-stage (64 KB) ring.
 //   warp 1   allocates 512 TMEM columns (two N-column s32 accumulators) and issues tcgen05.mma (M=128, N, K=32)
 //            from one lane; tcgen05.commit releases smem stages and publishes finished accumulators.
-//   warps 2-9 epilogue: tcgen05.ld (lane = vector row, column = query), exact int->f32, three-rounding epilogue,
+//   warps 2-17 epilogue: tcgen05.ld (lane = vector row, column = query), exact int->f32, three-rounding epilogue,
 //            compare with the per-query threshold, emit survivors.  Double-buffered against the next tile's MMAs.
 // CTAs are grouped by query block (c % n_qblocks) so that the n_qblocks CTAs reading the same A tiles run in
 // lock-step and hit L2 after the first HBM read.
@@ -34,8 +34,10 @@ constexpr int A_KB = 128;                   // K bytes per A stage (one 128-B sw
 constexpr int A_STAGES = 4;
 constexpr int A_STAGE_BYTES = MMA_M * A_KB;  // 16 KB
 constexpr int B_KB = 128;                   // K bytes per resident B block (128-B swizzle)
+static_assert(A_KB == B_KB, "the MMA issue loop pairs A stage ka with B K-block ka");
 constexpr int N_MAX = 256;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                // 4 per TMEM lane quarter: enough warps in flight to hide tcgen05.ld and atomic latency
+constexpr int EPI_PARTS = EPI_WARPS / 4;     // column chunks are dealt round-robin to the warps of a quarter
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -64,6 +66,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 // L2 prefetch of a tile box (no shared-memory destination): later TMA loads of the same box hit L2
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
+// One elected lane of a converged warp (SASS ELECT).  Issuing TMA / tcgen05 work under `if (elect_one())` inside warp-uniform
+// control flow keeps descriptors in uniform registers; a plain `if (lane == 0)` makes the compiler wrap every UTC*/UTMA*
+// instruction in a vote-and-retry loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -209,18 +219,21 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+        {
             const uint64_t pol_keep = qb_policy_evict_last();
             const uint64_t pol_stream = qb_policy_evict_first();
-            qb_mbar_arrive_expect_tx(b_full, n_kb_b * b_block_bytes);
-            for (uint32_t kb = 0; kb < n_kb_b; ++kb) tma_load_2d(&map_b, b_full, b_s + (size_t)kb * b_block_bytes, (int32_t)(kb * B_KB), (int32_t)q_base, pol_keep);
+            if (elect_one()) {
+                qb_mbar_arrive_expect_tx(b_full, n_kb_b * b_block_bytes);
+                for (uint32_t kb = 0; kb < n_kb_b; ++kb) tma_load_2d(&map_b, b_full, b_s + (size_t)kb * b_block_bytes, (int32_t)(kb * B_KB), (int32_t)q_base, pol_keep);
+            }
+            __syncwarp();
             uint64_t it = 0;
             constexpr uint64_t PF = 3;  // L2 prefetch distance in tiles: hides the HBM latency that a 64 KB smem ring cannot
             for (uint64_t ti = 0; ti < my_tiles; ++ti) {
                 const uint64_t tile = worker + ti * p.n_workers;
                 const int32_t row0 = (int32_t)(tile * MMA_M);
-                {   // the n_qblocks CTAs of a worker group walk the same tiles: each prefetches its share of the K-blocks
+                if (elect_one()) {   // the n_qblocks CTAs of a worker group walk the same tiles: each prefetches its share of the K-blocks
                     const uint64_t pt = (ti == 0) ? 0 : PF;
                     for (uint64_t d = pt; d <= PF; ++d) {
                         const uint64_t tile_pf = worker + (ti + d) * p.n_workers;
@@ -228,23 +241,34 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (uint32_t ka = qblock; ka < n_ka; ka += p.n_qblocks) tma_prefetch_2d(&map_a, (int32_t)(ka * A_KB), (int32_t)(tile_pf * MMA_M));
                     }
                 }
+                __syncwarp();
                 for (uint32_t ka = 0; ka < n_ka; ++ka, ++it) {
                     const uint32_t s = (uint32_t)(it % A_STAGES), ph = (uint32_t)((it / A_STAGES) & 1);
                     qb_mbar_wait(&empty_a[s], ph ^ 1u);
-                    qb_mbar_arrive_expect_tx(&full_a[s], A_STAGE_BYTES);
-                    // the n_qblocks CTAs of a worker group read the same tile: the first read comes from HBM, the rest from L2
-                    tma_load_2d(&map_a, &full_a[s], a_s + (size_t)s * A_STAGE_BYTES, (int32_t)(ka * A_KB), row0, p.n_qblocks > 1 ? pol_keep : pol_stream);
+                    if (elect_one()) {
+                        qb_mbar_arrive_expect_tx(&full_a[s], A_STAGE_BYTES);
+                        // the n_qblocks CTAs of a worker group read the same tile: the first read comes from HBM, the rest from L2
+                        tma_load_2d(&map_a, &full_a[s], a_s + (size_t)s * A_STAGE_BYTES, (int32_t)(ka * A_KB), row0, p.n_qblocks > 1 ? pol_keep : pol_stream);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one lane)
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+        {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A/B = u8, both K-major, M = 128, N = n_blk
             const uint32_t idesc = (2u << 4) | (0u << 7) | (0u << 10) | ((p.n_blk >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
             qb_mbar_wait(b_full, 0);
             tc_fence_after();
-            const uint32_t a_addr0 = qb_smem_u32(a_s), b_addr0 = qb_smem_u32(b_s);
+            // One thread issues every MMA and an int8 MMA lasts only ~100 cycles, so the issue loop must be a handful of
+            // instructions: descriptors differ only in their 14-bit start-address field (low word), everything else is hoisted.
+            const uint64_t a_desc0 = make_smem_desc(qb_smem_u32(a_s), 8 * A_KB, 2);
+            const uint64_t b_desc0 = make_smem_desc(qb_smem_u32(b_s), 8 * B_KB, 2);
+            const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
+            const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
+            const uint32_t b_blk16 = b_block_bytes >> 4;   // K-block stride of the resident query block, in 16-B units
+            const uint32_t n_k32 = (p.ad + 31) / 32;       // MMAs (K = 32 B) per tile
             uint64_t it = 0;
             for (uint64_t ti = 0; ti < my_tiles; ++ti) {
                 const uint32_t acc = (uint32_t)(ti & 1), acc_ph = (uint32_t)((ti >> 1) & 1);
@@ -255,25 +279,30 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t s = (uint32_t)(it % A_STAGES), ph = (uint32_t)((it / A_STAGES) & 1);
                     qb_mbar_wait(&full_a[s], ph);
                     tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + s * (A_STAGE_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + ka * b_blk16;   // A_KB == B_KB: stage ka pairs with K-block ka
+                    const uint32_t k32 = ka * (A_KB / 32);
+                    if (elect_one()) {
 #pragma unroll
-                    for (uint32_t j = 0; j < A_KB / 32; ++j) {
-                        const uint32_t kbyte = ka * A_KB + j * 32;
-                        if (kbyte < p.ad) {
-                            const uint64_t a_desc = make_smem_desc(a_addr0 + s * A_STAGE_BYTES + j * 32, 8 * A_KB, 2);
-                            const uint64_t b_desc = make_smem_desc(b_addr0 + (kbyte / B_KB) * b_block_bytes + (kbyte % B_KB), 8 * B_KB, 2);
-                            mma_i8(d_tmem, a_desc, b_desc, idesc, (ka | j) != 0 ? 1u : 0u);
+                        for (uint32_t j = 0; j < A_KB / 32; ++j) {
+                            if (k32 + j < n_k32) {
+                                const uint64_t a_desc = ((uint64_t)a_hi << 32) | (a_lo + 2 * j);   // +32 B inside the swizzled row
+                                const uint64_t b_desc = ((uint64_t)b_hi << 32) | (b_lo + 2 * j);
+                                mma_i8(d_tmem, a_desc, b_desc, idesc, (k32 + j) != 0 ? 1u : 0u);
+                            }
                         }
+                        tc_commit(&empty_a[s]);  // frees the smem stage once the MMAs above have read it
+                        if (ka + 1 == n_ka) tc_commit(&tm_full[acc]);   // accumulator complete -> epilogue
                     }
-                    tc_commit(&empty_a[s]);  // frees the smem stage once the MMAs above have read it
+                    __syncwarp();
                 }
-                tc_commit(&tm_full[acc]);    // accumulator complete -> epilogue
             }
         }
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int ew = warp - 2;
         const uint32_t quarter = (uint32_t)(warp & 3);   // TMEM lanes this warp may read: [32*quarter, 32*quarter+32)
-        const uint32_t half = (uint32_t)(ew >> 2);       // which alternate 16-column chunks
+        const uint32_t half = (uint32_t)(ew >> 2);       // which of every EPI_PARTS 16-column chunks
         const uint32_t n_chunks = p.n_blk >> 4;
         const float mult = p.multiplier;
         for (uint64_t ti = 0; ti < my_tiles; ++ti) {
@@ -293,12 +322,12 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t c = half;
             if (c < n_chunks) { tmem_ld16_issue(t_row + c * 16, ra); tmem_ld_wait(ra); }
             while (c < n_chunks) {
-                const uint32_t c1 = c + 2;
+                const uint32_t c1 = c + EPI_PARTS;
                 if (c1 < n_chunks) tmem_ld16_issue(t_row + c1 * 16, rb);
                 epilogue_chunk(p, emit, ra, c, c_s, v_over_m, q_base, row, valid_row, dead, v_off, mult, qoff_s, thr_s);
                 if (c1 >= n_chunks) break;
                 tmem_ld_wait(rb);
-                const uint32_t c2 = c1 + 2;
+                const uint32_t c2 = c1 + EPI_PARTS;
                 if (c2 < n_chunks) tmem_ld16_issue(t_row + c2 * 16, ra);
                 epilogue_chunk(p, emit, rb, c1, c_s, v_over_m, q_base, row, valid_row, dead, v_off, mult, qoff_s, thr_s);
                 if (c2 >= n_chunks) break;
