@@ -27,7 +27,8 @@ qb_status qb_pq_score_points(const qb_storage* s, const void* d_q_enc, const uin
 qb_status qb_pq_score_internal(const qb_storage* s, uint32_t a, uint32_t b, float* d_out, cudaStream_t stream);
 uint32_t qb_sq8_mma_block(const qb_storage* s, uint32_t nq);
 qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_t nq_pad, const float* d_q_off, uint32_t nq, uint32_t n_blk,
-                          uint64_t row_begin, uint64_t row_end, const QbEmit& emit, unsigned int* d_flags, cudaStream_t stream);
+                          uint64_t row_begin, uint64_t row_end, const QbEmit& emit, unsigned int* d_flags, unsigned long long* seg_len,
+                          cudaStream_t stream);
 qb_status qb_bq_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, int force_binary, void* d_out, cudaStream_t stream);
 qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
@@ -504,7 +505,7 @@ static void profile_end(qb_storage* s, cudaStream_t stream, cudaEvent_t e0, cuda
 
 // Core of the fused scan: queries already encoded in c->d_queries_enc (+ c->d_q_off).  Results to d_out/d_counts
 // (device).  Sets *overflow_possible when the filter pass is used (caller checks c->d_cnt overflow flag at [nq]).
-enum { RS_FORCE_DIRECT = 1, RS_NO_MMA = 2 };
+enum { RS_FORCE_DIRECT = 1, RS_NO_MMA = 2, RS_NO_SEGMENTS = 4 };
 static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t top, const uint32_t* d_ids, uint64_t n_ids, const uint32_t* d_deleted2,
                             const volatile int32_t* is_stopped, uint32_t rs_flags, qb_scored_point* d_out, uint32_t* d_counts, unsigned int* d_overflow) {
     const bool force_direct = (rs_flags & RS_FORCE_DIRECT) != 0;
@@ -544,8 +545,8 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             a.emit.dense = 1; a.emit.dense_base = 0;
             const uint32_t mma_blk = (!d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr) ? qb_sq8_mma_block(s, qn) : 0;
             if (mma_blk) {
-                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), (uint32_t)round_up_u64(qn, mma_blk), a.d_q_off, qn, mma_blk, 0, plan.sample,
-                                       a.emit, d_overflow, stream));
+                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu), a.d_q_off, qn, mma_blk, 0, plan.sample,
+                                       a.emit, d_overflow, nullptr, stream));
             } else {
                 QB_TRY(qb_launch_scan(s, a, stream));
             }
@@ -556,15 +557,18 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             a.emit.dense = 0; a.emit.thr = c->d_thr + q0; a.emit.cnt = c->d_cnt + q0;
             if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
             profile_begin(s, c, stream, &e0, &e1);
+            unsigned long long seg_len = 0;
             if (mma_blk) {
                 // batched SQ8: tensor-core GEMM with the fused epilogue/filter (qb_sq8_mma.cu)
-                const uint32_t nq_pad = (uint32_t)round_up_u64(qn, mma_blk);
-                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, n_cand, a.emit, d_overflow, stream));
+                const uint32_t nq_pad = (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu);
+                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, n_cand, a.emit, d_overflow,
+                                       (rs_flags & RS_NO_SEGMENTS) ? nullptr : &seg_len, stream));
             } else {
                 QB_TRY(qb_launch_scan(s, a, stream));
             }
             profile_end(s, stream, e0, e1);
-            QB_TRY(qb_launch_select(c->d_cand, c->d_cnt + q0, plan.cap, 0, qn, top, 0, d_out + (size_t)q0 * top, d_counts + q0, nullptr, d_overflow, stream));
+            // seg_len != 0: per-(query, CTA) segments with empty (zero) slots -> fixed-length selection
+            QB_TRY(qb_launch_select(c->d_cand, c->d_cnt + q0, plan.cap, seg_len, qn, top, 0, d_out + (size_t)q0 * top, d_counts + q0, nullptr, d_overflow, stream));
         }
     }
     return QB_OK;
@@ -626,25 +630,28 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
         d_ids = c->d_ids;
     }
     unsigned int* d_overflow = reinterpret_cast<unsigned int*>(c->d_out_counts + n_queries);
-    QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
-    QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, 0, c->d_out, c->d_out_counts, d_overflow));
     uint8_t* h_res = hs + raw_bytes;
     uint8_t* h_cnt = h_res + res_bytes;
-    QB_CUDA(cudaMemcpyAsync(h_res, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
-    QB_CUDA(cudaMemcpyAsync(h_cnt, c->d_out_counts, cnt_bytes + 4, cudaMemcpyDeviceToHost, stream));
-    QB_CUDA(cudaStreamSynchronize(stream));
-    unsigned int overflow = 0;
-    memcpy(&overflow, h_cnt + cnt_bytes, 4);
-    if (overflow) {
-        // the threshold admitted more candidates than the buffer holds (adversarial data, e.g. mass ties or a
-        // mostly-deleted sample): redo with full materialisation, which cannot overflow
-        // bit 2: a tensor-core dot product left the f32-exact window (>= 2^24): redo on the lane-exact CUDA-core kernel
+    // Fast path first; the device reports (flags word) when one of its assumptions did not hold and the host reruns without it:
+    //   1 candidate buffer overflow (threshold admitted too much: mass ties, mostly-deleted sample) -> full materialisation
+    //   2 a tensor-core dot product left the f32-exact window (>= 2^24)                           -> lane-exact CUDA-core kernel
+    //   8 a per-(query, CTA) survivor segment filled up                                            -> global counters
+    uint32_t rs_flags = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
         QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
-        QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, ((overflow & 1u) ? RS_FORCE_DIRECT : 0u) | RS_NO_MMA, c->d_out,
-                          c->d_out_counts, d_overflow));
+        QB_TRY(run_search(s, c, n_queries, top, d_ids, n_ids, d_del2, is_stopped, rs_flags, c->d_out, c->d_out_counts, d_overflow));
         QB_CUDA(cudaMemcpyAsync(h_res, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
-        QB_CUDA(cudaMemcpyAsync(h_cnt, c->d_out_counts, cnt_bytes, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaMemcpyAsync(h_cnt, c->d_out_counts, cnt_bytes + 4, cudaMemcpyDeviceToHost, stream));
         QB_CUDA(cudaStreamSynchronize(stream));
+        unsigned int flags = 0;
+        memcpy(&flags, h_cnt + cnt_bytes, 4);
+        uint32_t next = rs_flags;
+        if (flags & 8u) next |= RS_NO_SEGMENTS;
+        if (flags & 2u) next |= RS_NO_MMA;
+        if (flags & 1u) next |= RS_FORCE_DIRECT | RS_NO_MMA;
+        if (next == rs_flags) break;
+        if (getenv("QB_VERBOSE")) fprintf(stderr, "[qb200] search rerun: device flags=0x%x, mode 0x%x -> 0x%x\n", flags, rs_flags, next);
+        rs_flags = next;
     }
     memcpy(out, h_res, res_bytes);
     memcpy(out_counts, h_cnt, cnt_bytes);

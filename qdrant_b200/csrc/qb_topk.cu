@@ -53,11 +53,29 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
     const unsigned long long* keys = cand + (unsigned long long)q * cap;
     int m = 0;  // number of keys staged in buf
 
+    bool staged = false;
     if (n <= SORT_CAP) {
         for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = (i < (int)n) ? keys[i] : 0ull;
         m = (int)n;
+        staged = true;
         __syncthreads();
-    } else {
+    } else if (fixed_n && mode == 0) {
+        // sparse fixed-length list (per-CTA segments with empty slots): compact the non-empty keys; if they fit, sort them directly
+        if (threadIdx.x == 0) s_fill = 0u;
+        for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = 0ull;
+        __syncthreads();
+        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = keys[i];
+            if (key != 0ull) {
+                const unsigned int p = atomicAdd(&s_fill, 1u);
+                if (p < SORT_CAP) buf[p] = key;
+            }
+        }
+        __syncthreads();
+        if (s_fill <= (unsigned int)SORT_CAP) { m = (int)s_fill; staged = true; }
+        __syncthreads();
+    }
+    if (!staged) {
         if (threadIdx.x == 0) { s_prefix = 0ull; s_kk = top; s_short = 0u; s_done = 0u; }
         unsigned long long mask = 0ull;
         __syncthreads();

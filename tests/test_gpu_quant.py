@@ -223,3 +223,21 @@ def test_sq8_batched_tensor_core_path(qb, oracle, dist, n, dim, nq):
         np.testing.assert_array_equal(got[i], got_cc[i])
         assert_topk_equal(got[i], want[i], None, f"sq8-mma {dist} q={i}")
     st.close()
+
+
+def test_sq8_batched_fallbacks_on_mass_ties(qb, oracle):
+    """Every row identical: the per-(query, CTA) segments overflow, then the global candidate buffer overflows, and the
+    search must still end on the exact full-materialisation path with the right answer."""
+    d = qb.Distance.Dot
+    rng = np.random.default_rng(12)
+    base = np.tile(rng.standard_normal((1, 64)).astype(np.float32), (70_000, 1))
+    queries = rng.standard_normal((40, 64)).astype(np.float32)
+    sq = oracle.SQ8.encode(base, oracle.QD_DOT, False)
+    st = qb.ScalarQuantizedVectors(sq.rows, 64, sq.meta.alpha, sq.meta.offset, sq.meta.multiplier, d)
+    got = st.search_batch(queries, 10)
+    for i, q in enumerate(queries):
+        code, off = sq.encode_query(q)
+        s0 = sq.score(code, off, 0)
+        assert got[i].size == 10 and np.all(got[i]["score"] == s0)
+        assert sorted(got[i]["idx"].tolist()) == list(range(10))
+    st.close()
