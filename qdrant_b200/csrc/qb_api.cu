@@ -26,9 +26,10 @@ qb_status qb_pq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stre
 qb_status qb_pq_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
 qb_status qb_pq_score_internal(const qb_storage* s, uint32_t a, uint32_t b, float* d_out, cudaStream_t stream);
 uint32_t qb_sq8_mma_block(const qb_storage* s, uint32_t nq);
+size_t qb_sq8_mma_scratch_bytes(const qb_storage* s, uint32_t nq_pad);
 qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_t nq_pad, const float* d_q_off, uint32_t nq, uint32_t n_blk,
                           uint64_t row_begin, uint64_t row_end, const QbEmit& emit, unsigned int* d_flags, unsigned long long* seg_len,
-                          cudaStream_t stream);
+                          void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
 qb_status qb_bq_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, int force_binary, void* d_out, cudaStream_t stream);
 qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
@@ -124,7 +125,7 @@ static void ctx_destroy(QbSearchCtx* c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_queries_raw); cudaFree(c->d_queries_enc); cudaFree(c->d_q_off); cudaFree(c->d_thr); cudaFree(c->d_cnt);
-    cudaFree(c->d_cand); cudaFree(c->d_out); cudaFree(c->d_out_counts); cudaFree(c->d_deleted2); cudaFree(c->d_ids);
+    cudaFree(c->d_cand); cudaFree(c->d_out); cudaFree(c->d_out_counts); cudaFree(c->d_deleted2); cudaFree(c->d_ids); cudaFree(c->d_mma);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -546,7 +547,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             const uint32_t mma_blk = (!d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr) ? qb_sq8_mma_block(s, qn) : 0;
             if (mma_blk) {
                 QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu), a.d_q_off, qn, mma_blk, 0, plan.sample,
-                                       a.emit, d_overflow, nullptr, stream));
+                                       a.emit, d_overflow, nullptr, nullptr, 0, stream));
             } else {
                 QB_TRY(qb_launch_scan(s, a, stream));
             }
@@ -561,8 +562,9 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             if (mma_blk) {
                 // batched SQ8: tensor-core GEMM with the fused epilogue/filter (qb_sq8_mma.cu)
                 const uint32_t nq_pad = (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu);
+                QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, qb_sq8_mma_scratch_bytes(s, nq_pad)));
                 QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, n_cand, a.emit, d_overflow,
-                                       (rs_flags & RS_NO_SEGMENTS) ? nullptr : &seg_len, stream));
+                                       (rs_flags & RS_NO_SEGMENTS) ? nullptr : &seg_len, c->d_mma, c->mma_bytes, stream));
             } else {
                 QB_TRY(qb_launch_scan(s, a, stream));
             }

@@ -23,6 +23,7 @@ struct QbSearchCtx {
     uint32_t* d_out_counts = nullptr; size_t out_counts_elems = 0;
     uint32_t* d_deleted2 = nullptr;  size_t deleted2_words = 0;
     uint32_t* d_ids = nullptr;       size_t ids_elems = 0;
+    void* d_mma = nullptr;           size_t mma_bytes = 0;           // batched SQ8: sorted query codes / permutation / chunk thresholds
     // pinned host staging
     void* h_stage = nullptr;         size_t h_stage_bytes = 0;
     // profiling

@@ -1,6 +1,6 @@
 // host_selftest.cpp — drives libqdrant_b200.so through the C++ mirror of the reference's interface
 // (RawScorerBuilder -> RawScorer, FilteredScorer, BatchFilteredSearcher).  Inputs/outputs are raw binary files so that
-// tests/test_gpu_cpp_host.py can compare the results with the CPU oracle bit for bit.
+// tests/test_gpu_cpp_host.py can compare the results with the CPU restatement bit for bit.
 //   host_selftest <base.f32> <queries.f32> <n> <dim> <nq> <top> <out.bin>
 // out.bin: for each query: u32 count, count x {u32 idx, f32 score}; then nq x 32 f32 = score_points of ids 0..31 after
 // FilteredScorer filtering (every 3rd point deleted), then 1 f32 = score_internal(1, 2).

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for mode in 0 32 8; do for cta in 1; do
+for mode in 0 4; do for cta in 1 2; do
   if [ $cta = 1 ]; then export QB_MMA_1CTA=1; else unset QB_MMA_1CTA; fi
   QB_MMA_DEBUG=$mode timeout 300 python - <<'PY'
 import os, sys, json, time
