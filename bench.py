@@ -464,9 +464,15 @@ def main_c3(args):
         cpu = {"value": nq / (dt * n / sample_rows), "unit": "queries/s", "cores": threads, "kind": "reference+port",
                "sample": f"{sample_rows} of {n} rows x {nq} queries: impl_score_dot_avx arithmetic + postprocess + heap (oracle qo_scan_sq8), {threads} threads over row "
                          f"segments, {dt*1e3:.0f} ms per sample batch, extrapolated linearly to {n} rows"}
-    peak_bf16 = 1645.8
+    # MEASURED_PEAKS.json has no int8 figure (its tensor number is cuBLAS bf16, 1645.8 TF/s); the denominator here is the stricter
+    # one: the tcgen05.mma kind::i8 issue rate measured on this pool by tools/mma_rate.cu (8190 MAC/clk/SM x 148 SMs x 1.965 GHz)
+    peak_i8 = 4539.0
     try:
-        peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        for ln in open(os.path.join(ROOT, "profiles", "mma_rate_r01.jsonl")):
+            r = json.loads(ln)
+            if r.get("kind") == "i8" and r.get("n") == 256:
+                peak_i8 = float(r["chip_tera_ops_per_s"])
+                break
     except Exception:
         pass
     ops = 2.0 * nq * n * ad
@@ -478,9 +484,10 @@ def main_c3(args):
                                             "l2": "code plane 7.68 GB >> 126 MB L2"},
             "e2e": {"value": nq * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top * 8 + nq * 4, "ms_per_step": e2e_ms / K},
             "gpu_launches": launches, "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "sq8_mma_kernel (tcgen05.mma kind::i8, main pass)", "achieved": achieved, "peak": 2 * peak_bf16, "unit": "TOP/s",
-                         "frac": (achieved / (2 * peak_bf16)) if achieved else None, "traffic": None,
-                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (dense int8 = 2 x bf16 on sm_100; no measured int8 figure)", "avg_launch_ms": kern_ms,
+            "roofline": {"bound": "tensor", "kernel": "sq8_mma_kernel (tcgen05.mma kind::i8, main pass)", "achieved": achieved, "peak": peak_i8, "unit": "TOP/s",
+                         "frac": (achieved / peak_i8) if achieved else None, "traffic": None,
+                         "peak_source": "measured tcgen05.mma kind::i8 issue rate (profiles/mma_rate_r01.jsonl, tools/mma_rate.cu); MEASURED_PEAKS.json holds no int8 figure "
+                                        "(2 x its cuBLAS bf16 number would be 3291.6)", "avg_launch_ms": kern_ms,
                          "launches_timed": n_prof, "algorithmic_ops_per_launch": ops}}
     if cpu:
         line["cpu_baseline"] = cpu

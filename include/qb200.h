@@ -156,8 +156,10 @@ QB_API qb_status qb_search_batch(qb_storage* s, const float* queries, uint32_t n
                           const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids,
                           const volatile int32_t* is_stopped, qb_scored_point* out, uint32_t* out_counts,
                           qb_hw_counters* counters /* optional */);
-/* Same scan with queries and outputs already resident in HBM; enqueued on qb_storage_stream(s), no host
- * synchronisation (bench.py's kernel-only `value`). */
+/* Same scan with queries and outputs already resident in HBM, enqueued on qb_storage_stream(s) (bench.py's
+ * kernel-only `value`).  The call waits for that stream once, to read the device's "fast-path assumption
+ * broken" flags word (reruns happen inside, as in qb_search_batch).  It uses the storage's first search context:
+ * do not run it concurrently with other searches on the same storage. */
 QB_API qb_status qb_search_batch_device(qb_storage* s, const float* dev_queries, uint32_t n_queries, uint32_t top,
                                  qb_scored_point* dev_out, uint32_t* dev_counts);
 

@@ -459,12 +459,13 @@ qb_status qb_launch_score_points(const qb_storage* s, const void* d_q_enc, const
 struct SearchPlan {
     uint64_t n_cand;       // candidates per query (rows or listed ids)
     bool direct;           // one dense pass + select
-    uint64_t sample;       // sample prefix length (two-pass)
+    uint64_t sample;       // sample prefix length (dense pass -> per-query threshold)
+    uint64_t sample2;      // 0, or a longer prefix scanned with that threshold to refine it before the full pass (three levels)
     uint64_t cap;          // per-query candidate capacity of the filter pass
     uint32_t q_chunk;      // queries per pass
 };
 
-static SearchPlan make_plan(uint64_t n_cand, uint32_t nq, uint32_t top, bool force_direct) {
+static SearchPlan make_plan(uint64_t n_cand, uint32_t nq, uint32_t top, bool force_direct, bool refine) {
     SearchPlan p{};
     p.n_cand = n_cand;
     const uint64_t kDirectRows = 65536;
@@ -472,6 +473,15 @@ static SearchPlan make_plan(uint64_t n_cand, uint32_t nq, uint32_t top, bool for
     if (force_direct || n_cand <= kDirectRows) {
         p.direct = true;
         p.cap = std::max<uint64_t>(n_cand, 1);
+    } else if (refine && n_cand >= (1ull << 20)) {
+        // Batched tensor-core scan: a dense sample costs 8 B per (row, query) to write and ~4x that to select from, and every survivor
+        // of the filter pass costs a trip through the epilogue's slow path.  Three levels keep both small:
+        //   S1 rows dense -> thr1;  S2 = 1.5 sqrt(N S1) rows filtered by thr1 -> thr2 (k-th best of S2);  all rows filtered by thr2.
+        p.direct = false;
+        p.sample = round_up_u64(std::max<uint64_t>(4096, 16ull * top), 256);
+        p.sample2 = std::min<uint64_t>(round_up_u64((uint64_t)(1.5 * sqrt((double)n_cand * (double)p.sample)), 1024), n_cand / 4);
+        const uint64_t expect = std::max<uint64_t>(p.sample2 * top / p.sample, n_cand * top / p.sample2);
+        p.cap = std::max<uint64_t>(p.sample, 8 * expect + 4096);
     } else {
         p.direct = false;
         // minimise sample + expected survivors (N*k/S): S ~ sqrt(N*k); x2 keeps the survivor list short
@@ -506,14 +516,15 @@ static void profile_end(qb_storage* s, cudaStream_t stream, cudaEvent_t e0, cuda
 
 // Core of the fused scan: queries already encoded in c->d_queries_enc (+ c->d_q_off).  Results to d_out/d_counts
 // (device).  Sets *overflow_possible when the filter pass is used (caller checks c->d_cnt overflow flag at [nq]).
-enum { RS_FORCE_DIRECT = 1, RS_NO_MMA = 2, RS_NO_SEGMENTS = 4 };
+enum { RS_FORCE_DIRECT = 1, RS_NO_MMA = 2, RS_NO_SEGMENTS = 4, RS_NO_REFINE = 8 };
 static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t top, const uint32_t* d_ids, uint64_t n_ids, const uint32_t* d_deleted2,
                             const volatile int32_t* is_stopped, uint32_t rs_flags, qb_scored_point* d_out, uint32_t* d_counts, unsigned int* d_overflow) {
     const bool force_direct = (rs_flags & RS_FORCE_DIRECT) != 0;
     const uint64_t n_cand = d_ids ? n_ids : s->count;
     cudaStream_t stream = c->stream;
     if (n_cand == 0) { QB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, stream)); return QB_OK; }
-    const SearchPlan plan = make_plan(n_cand, nq, top, force_direct);
+    const bool mma_ok = !d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr;
+    const SearchPlan plan = make_plan(n_cand, nq, top, force_direct, mma_ok && qb_sq8_mma_block(s, nq) != 0 && !(rs_flags & RS_NO_REFINE));
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)plan.q_chunk * plan.cap));
     QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)nq));
     QB_TRY(ensure_dev_elems(&c->d_cnt, &c->cnt_elems, (size_t)nq + 1));
@@ -544,14 +555,30 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             // pass 1: sample prefix, materialised densely -> per-query threshold = k-th best of the sample
             a.row_begin = 0; a.row_end = plan.sample;
             a.emit.dense = 1; a.emit.dense_base = 0;
-            const uint32_t mma_blk = (!d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr) ? qb_sq8_mma_block(s, qn) : 0;
+            const uint32_t mma_blk = mma_ok ? qb_sq8_mma_block(s, qn) : 0;
+            const uint32_t nq_pad = mma_blk ? (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu) : 0;
             if (mma_blk) {
-                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu), a.d_q_off, qn, mma_blk, 0, plan.sample,
-                                       a.emit, d_overflow, nullptr, nullptr, 0, stream));
+                QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, plan.sample, a.emit, d_overflow, nullptr,
+                                       nullptr, 0, stream));
             } else {
                 QB_TRY(qb_launch_scan(s, a, stream));
             }
             QB_TRY(qb_launch_select(c->d_cand, nullptr, plan.cap, plan.sample, qn, top, 1, nullptr, nullptr, c->d_thr + q0, nullptr, stream));
+            if (mma_blk) QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, qb_sq8_mma_scratch_bytes(s, nq_pad)));
+            if (plan.sample2) {
+                // level 2: a longer prefix filtered by the level-1 threshold; its k-th best survivor is the threshold of the full pass
+                QB_CUDA(cudaMemsetAsync(c->d_cnt + q0, 0, (size_t)qn * 4, stream));
+                a.row_end = plan.sample2;
+                a.emit.dense = 0; a.emit.thr = c->d_thr + q0; a.emit.cnt = c->d_cnt + q0;
+                unsigned long long seg2 = 0;
+                if (mma_blk) {
+                    QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, plan.sample2, a.emit, d_overflow,
+                                           (rs_flags & RS_NO_SEGMENTS) ? nullptr : &seg2, c->d_mma, c->mma_bytes, stream));
+                } else {
+                    QB_TRY(qb_launch_scan(s, a, stream));  // a chunk too small for the tensor-core kernel
+                }
+                QB_TRY(qb_launch_select(c->d_cand, c->d_cnt + q0, plan.cap, seg2, qn, top, 1, nullptr, nullptr, c->d_thr + q0, d_overflow, stream));
+            }
             // pass 2: everything, keeping only score >= threshold
             QB_CUDA(cudaMemsetAsync(c->d_cnt + q0, 0, (size_t)qn * 4, stream));
             a.row_begin = 0; a.row_end = n_cand;
@@ -561,8 +588,6 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             unsigned long long seg_len = 0;
             if (mma_blk) {
                 // batched SQ8: tensor-core GEMM with the fused epilogue/filter (qb_sq8_mma.cu)
-                const uint32_t nq_pad = (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu);
-                QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, qb_sq8_mma_scratch_bytes(s, nq_pad)));
                 QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, n_cand, a.emit, d_overflow,
                                        (rs_flags & RS_NO_SEGMENTS) ? nullptr : &seg_len, c->d_mma, c->mma_bytes, stream));
             } else {
@@ -683,8 +708,26 @@ extern "C" qb_status qb_search_batch_device(qb_storage* s, const float* dev_quer
     QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)n_queries + 4));
     QB_TRY(prepare_queries(s, dev_queries, n_queries, reinterpret_cast<float*>(c->d_queries_raw), c->d_queries_enc, c->d_q_off, c->stream));
     unsigned int* d_overflow = reinterpret_cast<unsigned int*>(c->d_out_counts + n_queries);
-    QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, c->stream));
-    return run_search(s, c, n_queries, top, nullptr, 0, nullptr, nullptr, 0, dev_out, dev_counts, d_overflow);
+    // same contract as qb_search_batch: the device reports a broken fast-path assumption in a flags word and the host reruns
+    // without it; reading that word is the one synchronisation of this call
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, 64));
+    uint32_t rs_flags = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, c->stream));
+        QB_TRY(run_search(s, c, n_queries, top, nullptr, 0, nullptr, nullptr, rs_flags, dev_out, dev_counts, d_overflow));
+        QB_CUDA(cudaMemcpyAsync(c->h_stage, d_overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+        QB_CUDA(cudaStreamSynchronize(c->stream));
+        unsigned int flags = 0;
+        memcpy(&flags, c->h_stage, 4);
+        uint32_t next = rs_flags;
+        if (flags & 8u) next |= RS_NO_SEGMENTS;
+        if (flags & 2u) next |= RS_NO_MMA;
+        if (flags & 1u) next |= RS_FORCE_DIRECT | RS_NO_MMA;
+        if (next == rs_flags) break;
+        if (getenv("QB_VERBOSE")) fprintf(stderr, "[qb200] search rerun: device flags=0x%x, mode 0x%x -> 0x%x\n", flags, rs_flags, next);
+        rs_flags = next;
+    }
+    return QB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ RawScorer

@@ -75,7 +75,7 @@ struct MmaParams {
     unsigned int* flags;     // 2: a dot product reached 2^24; 8: a survivor segment overflowed
     int check_exact;
     uint32_t seg_cap;        // survivors of (query, CTA of its block group) go to a private segment of this many slots (0 = global atomics)
-    int debug;               // QB_MMA_DEBUG perf experiments: 1 = epilogue skips its work, 2 = no bias MMA (every element re-scored), 4 = prefilter never passes
+    int debug;               // QB_MMA_DEBUG perf experiments: 1 = epilogue skips its work, 2 = no bias MMA (every element re-scored), 4 = prefilter never passes, 8 = no A loads, 16 = no L2 prefetch
 };
 
 // Everything the survivor path needs, in shared memory: the out-of-line slow path takes ONE pointer, and nothing it reads sits
@@ -344,7 +344,7 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr uint64_t PF = 3;  // L2 prefetch distance in tiles: hides the HBM latency that the smem ring cannot
         for (uint64_t ti = 0; ti < my_tiles; ++ti) {
             const int32_t row0 = (int32_t)((worker + ti * p.n_workers) * TILE_M + row_in_tile0);
-            if (elect_one()) {  // the n_qblocks groups of a worker walk the same tiles: each prefetches its share of the K-blocks
+            if (!(p.debug & 16) && elect_one()) {  // the n_qblocks groups of a worker walk the same tiles: each prefetches its share of the K-blocks
                 for (uint64_t d = (ti == 0) ? 0 : PF; d <= PF; ++d)
                     if (ti + d < my_tiles)
                         for (uint32_t ka = qblock; ka < n_kb; ka += p.n_qblocks)
@@ -354,7 +354,9 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (uint32_t ka = 0; ka < n_kb; ++ka, ++it) {
                 const uint32_t s = (uint32_t)(it % STAGES), ph = (uint32_t)((it / STAGES) & 1);
                 qb_mbar_wait(&empty_a[s], ph ^ 1u);
-                if (elect_one()) {
+                if (p.debug & 8) {  // timing experiment: stages are "filled" without moving data
+                    if (rank == 0 && elect_one()) qb_mbar_arrive(&full_a[s]);
+                } else if (elect_one()) {
                     if (rank == 0) qb_mbar_arrive_expect_tx(&full_a[s], (TWO ? 2 : 1) * A_STAGE_BYTES);  // TWO: both CTAs' boxes land on the leader's barrier
                     tma_load_2d<TWO>(&map_a, &full_a[s], a_s + (size_t)s * A_STAGE_BYTES, (int32_t)(ka * KB), row0, p.n_qblocks > 1 ? pol_keep : pol_stream);
                 }
@@ -434,7 +436,9 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             qb_mbar_wait(&tm_full[acc], acc_ph);
             tc_fence_after();
-            // software pipeline: the TMEM load of the next chunk is in flight while the current one is filtered
+            // software pipeline: the TMEM load of the next chunk is in flight while the current one is filtered.  (Pulling all four
+            // chunks into registers at once and releasing the accumulator before filtering was measured 30 % SLOWER: bursts of
+            // tcgen05.ld from 16 warps collide with the accumulator traffic of the running MMAs.)
             const uint32_t t_addr = tmem_base + ((quarter * 32u) << 16) + acc * p.n_blk;
             uint32_t ra[16], rb[16];
             const bool skip = (p.debug & 1) != 0;

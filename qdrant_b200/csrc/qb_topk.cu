@@ -30,7 +30,7 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* buf, int n
 }
 
 __global__ void __launch_bounds__(QB_SELECT_THREADS)
-qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned long long cap,
+qb_select_kernel(const unsigned long long* cand, const unsigned int* __restrict__ cnt, unsigned long long cap,
                  unsigned long long fixed_n, uint32_t top, int mode, qb_scored_point* __restrict__ out,
                  uint32_t* __restrict__ out_counts, float* __restrict__ thr, unsigned int* __restrict__ overflow) {
     __shared__ unsigned long long buf[SORT_CAP];
@@ -52,6 +52,7 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
     }
     const unsigned long long* keys = cand + (unsigned long long)q * cap;
     int m = 0;  // number of keys staged in buf
+    const bool select_only = (mode == 1);  // threshold mode never needs the sorted order: radix-select the staged keys instead of sorting them
 
     bool staged = false;
     if (n <= SORT_CAP) {
@@ -59,7 +60,7 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
         m = (int)n;
         staged = true;
         __syncthreads();
-    } else if (fixed_n && mode == 0) {
+    } else if (fixed_n) {
         // sparse fixed-length list (per-CTA segments with empty slots): compact the non-empty keys; if they fit, sort them directly
         if (threadIdx.x == 0) s_fill = 0u;
         for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = 0ull;
@@ -75,7 +76,8 @@ qb_select_kernel(const unsigned long long* __restrict__ cand, const unsigned int
         if (s_fill <= (unsigned int)SORT_CAP) { m = (int)s_fill; staged = true; }
         __syncthreads();
     }
-    if (!staged) {
+    if (staged && select_only) { keys = buf; n = (unsigned long long)m; }  // same select loop, reading shared memory
+    if (!staged || select_only) {
         if (threadIdx.x == 0) { s_prefix = 0ull; s_kk = top; s_short = 0u; s_done = 0u; }
         unsigned long long mask = 0ull;
         __syncthreads();
