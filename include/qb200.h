@@ -57,6 +57,8 @@ typedef enum { QB_QD_COSINE = 0, QB_QD_DOT = 1, QB_QD_L1 = 2, QB_QD_L2 = 3 } qb_
 /* BQ Encoding / QueryEncoding — lib/quantization/src/encoded_vectors_binary.rs:34-54 */
 typedef enum { QB_BQ_ONE_BIT = 0, QB_BQ_TWO_BITS = 1, QB_BQ_ONE_AND_HALF_BITS = 2 } qb_bq_encoding;
 typedef enum { QB_BQQ_SAME_AS_STORAGE = 0, QB_BQQ_SCALAR4 = 1, QB_BQQ_SCALAR8 = 2 } qb_bq_query_encoding;
+/* QueryVector variants beyond Nearest (lib/segment/src/data_types/vectors.rs QueryVector; vector_storage/query/*.rs) */
+typedef enum { QB_QUERY_RECO_BEST_SCORE = 1, QB_QUERY_RECO_SUM_SCORES = 2, QB_QUERY_DISCOVER = 3, QB_QUERY_CONTEXT = 4 } qb_query_kind;
 
 /* #[repr(C)] ScoredPointOffset — lib/common/common/src/types.rs:12-17 */
 typedef struct { uint32_t idx; float score; } qb_scored_point;
@@ -162,6 +164,43 @@ QB_API qb_status qb_search_batch(qb_storage* s, const float* queries, uint32_t n
  * do not run it concurrently with other searches on the same storage. */
 QB_API qb_status qb_search_batch_device(qb_storage* s, const float* dev_queries, uint32_t n_queries, uint32_t top,
                                  qb_scored_point* dev_out, uint32_t* dev_counts);
+
+/* ---------------------------------------------------------------- custom queries -- */
+/* RawScorer for a recommend / discover / context query: CustomQueryScorer (query_scorer/custom_query_scorer.rs:16-122)
+ * and QuantizedCustomQueryScorer.  Every example vector goes through Metric::preprocess (+ encode_query on quantized
+ * storages) exactly like a plain query; a candidate's score is Query::score_by over its similarities to the examples:
+ *   QB_QUERY_RECO_BEST_SCORE  vectors = n_a positives, then n_b negatives      (query/reco_query.rs:64-90)
+ *   QB_QUERY_RECO_SUM_SCORES  same layout                                       (query/reco_query.rs:116-133)
+ *   QB_QUERY_DISCOVER         vectors = target, then n_a (positive, negative) pairs; n_b = 0   (query/discover_query.rs:66-76)
+ *   QB_QUERY_CONTEXT          vectors = n_a (positive, negative) pairs; n_b = 0  (query/context_query.rs:111-119)
+ * The scorer works with qb_score_points / qb_score_point; qb_score_internal returns QB_ERR_UNSUPPORTED (the reference's
+ * score_internal is unimplemented!() for custom scorers). */
+QB_API qb_status qb_scorer_create_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, qb_scorer** out);
+/* Brute-force scan with a custom query: BatchFilteredSearcher::peek_top_iter driven by a custom RawScorer.  Same
+ * deleted_bitmap / id_list / is_stopped / out conventions as qb_search_batch, one query per call. */
+QB_API qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, uint32_t top,
+                                  const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
+                                  qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters /* optional */);
+
+/* ---------------------------------------------------------------- quantizer encode on the device -- */
+/* The ENCODE half of the quantizers, on f32 rows already resident in HBM; outputs are the reference's row formats bit
+ * for bit and can be passed straight to qb_storage_create_{sq8,pq,bq} (device pointers are accepted there) or copied
+ * into a segment's quantized.data.  Training (SQ quantiles, PQ k-means, BQ mean/std) stays with the caller.
+ * row_stride_bytes = 0 means dim * 4.  `stream` is a cudaStream_t (NULL = default stream). */
+/* alpha = (max - min) / 127, offset = min over all values: EncodedVectorsU8 with quantile = None (encoded_vectors_u8.rs:194-225,523-527) */
+QB_API qb_status qb_sq8_find_alpha_offset_device(int32_t device, uint32_t dim, uint64_t count, const float* dev_rows, uint64_t row_stride_bytes,
+                                                 float* alpha, float* offset);
+/* EncodedVectorsU8::encode (encoded_vectors_u8.rs:240-283): dev_out = count x [f32 v_off][actual_dim u8], actual_dim = dim rounded up to 16 */
+QB_API qb_status qb_sq8_encode_rows_device(int32_t device, uint32_t dim, uint64_t count, const float* dev_rows, uint64_t row_stride_bytes, float alpha,
+                                           float offset, qb_qdistance dt, int invert, uint8_t* dev_out, void* stream);
+/* get_quantized_vector_size_from_params for u128 words (encoded_vectors_binary.rs:829-839) */
+QB_API uint32_t qb_bq_row_bytes(uint32_t dim, qb_bq_encoding encoding);
+/* EncodedVectorsBin::encode_vector (encoded_vectors_binary.rs:531-671); mean_std = dim x (mean, stddev) on the HOST, NULL for one-bit */
+QB_API qb_status qb_bq_encode_rows_device(int32_t device, uint32_t dim, uint64_t count, const float* dev_rows, uint64_t row_stride_bytes,
+                                          qb_bq_encoding encoding, const float* mean_std, uint8_t* dev_out, void* stream);
+/* EncodedVectorsPQ::encode_vector (encoded_vectors_pq.rs:301-329); centroids = n_centroids x dim on the HOST; dev_codes = count x ceil(dim / chunk) */
+QB_API qb_status qb_pq_encode_rows_device(int32_t device, uint32_t dim, uint32_t chunk, uint32_t n_centroids, const float* centroids, uint64_t count,
+                                          const float* dev_rows, uint64_t row_stride_bytes, uint8_t* dev_codes, void* stream);
 
 /* Oversampling + rescoring contract (index/vector_index_search_common.rs:27-91): rescore `n` candidate ids of
  * one query with the ORIGINAL-vector scorer `orig`, sort descending, truncate to `top`. */

@@ -1017,3 +1017,52 @@ API float qo_f16_dot_scalar(const uint16_t* a, const uint16_t* b, size_t n) {
     for (size_t i = 0; i < n; i++) s += h2f(a[i]) * h2f(b[i]);
     return s;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Custom queries: Query::score_by over the similarities of one stored vector to the example vectors
+ *   lib/common/common/src/math.rs:7-18                      fast_sigmoid, scaled_fast_sigmoid
+ *   vector_storage/query/reco_query.rs:64-90                RecoBestScoreQuery
+ *   vector_storage/query/reco_query.rs:116-133              RecoSumScoresQuery
+ *   vector_storage/query/discover_query.rs:16-25,44-50,66-76 DiscoverQuery (rank_by + sigmoid of the target)
+ *   vector_storage/query/context_query.rs:52-62,111-119     ContextQuery (loss_by, MARGIN = f32::EPSILON)
+ * kinds: 1 reco best score, 2 reco sum scores, 3 discover, 4 context.  sims layout as in include/qb200.h.
+ * ------------------------------------------------------------------------------------------------ */
+static inline int f32_total_cmp(float a, float b) { /* f32::total_cmp */
+    int32_t x, y;
+    memcpy(&x, &a, 4);
+    memcpy(&y, &b, 4);
+    x ^= (int32_t)(((uint32_t)(x >> 31)) >> 1);
+    y ^= (int32_t)(((uint32_t)(y >> 31)) >> 1);
+    return (x > y) - (x < y);
+}
+API float qo_fast_sigmoid(float x) { return x / (1.0f + fabsf(x)); }
+API float qo_scaled_fast_sigmoid(float x) { return 0.5f * (qo_fast_sigmoid(x) + 1.0f); }
+
+API float qo_custom_score(int kind, uint32_t n_a, uint32_t n_b, const float* sims, uint64_t stride) {
+    if (kind == 1) {
+        float max_p = -INFINITY, max_n = -INFINITY;
+        for (uint32_t e = 0; e < n_a; e++) { float s = sims[e * stride]; if (f32_total_cmp(s, max_p) > 0) max_p = s; }
+        for (uint32_t e = 0; e < n_b; e++) { float s = sims[(n_a + e) * stride]; if (f32_total_cmp(s, max_n) > 0) max_n = s; }
+        return (max_p > max_n) ? qo_scaled_fast_sigmoid(max_p) : -qo_scaled_fast_sigmoid(max_n);
+    } else if (kind == 2) {
+        float p = 0.0f, n = 0.0f;
+        for (uint32_t e = 0; e < n_a; e++) p += sims[e * stride];
+        for (uint32_t e = 0; e < n_b; e++) n += sims[(n_a + e) * stride];
+        return p - n;
+    } else if (kind == 3) {
+        int32_t rank = 0;
+        for (uint32_t e = 0; e < n_a; e++) rank += f32_total_cmp(sims[(1 + 2 * e) * stride], sims[(2 + 2 * e) * stride]);
+        return (float)rank + qo_scaled_fast_sigmoid(sims[0]);
+    } else {
+        float sum = 0.0f;
+        for (uint32_t e = 0; e < n_a; e++) {
+            float difference = sims[(2 * e) * stride] - sims[(2 * e + 1) * stride] - FLT_EPSILON;
+            sum += qo_fast_sigmoid(fminf(difference, 0.0f));
+        }
+        return sum;
+    }
+}
+/* sims: [examples][stride], one column per candidate */
+API void qo_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* sims, uint64_t stride, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; i++) out[i] = qo_custom_score(kind, n_a, n_b, sims + i, stride);
+}

@@ -68,6 +68,10 @@ def lib() -> C.CDLL:
             fn = getattr(L, f"qo_cosine_preprocess_{tier}")
             fn.restype, fn.argtypes = None, [f32p, f32p, C.c_size_t]
         L.qo_similarity_f32.restype, L.qo_similarity_f32.argtypes = C.c_float, [C.c_int, f32p, f32p, C.c_size_t]
+        L.qo_fast_sigmoid.restype, L.qo_fast_sigmoid.argtypes = C.c_float, [C.c_float]
+        L.qo_scaled_fast_sigmoid.restype, L.qo_scaled_fast_sigmoid.argtypes = C.c_float, [C.c_float]
+        L.qo_custom_score.restype, L.qo_custom_score.argtypes = C.c_float, [C.c_int, C.c_uint32, C.c_uint32, f32p, C.c_uint64]
+        L.qo_custom_combine.restype, L.qo_custom_combine.argtypes = None, [C.c_int, C.c_uint32, C.c_uint32, f32p, C.c_uint64, C.c_uint64, f32p]
         L.qo_preprocess_f32.restype, L.qo_preprocess_f32.argtypes = None, [C.c_int, f32p, f32p, C.c_size_t]
         L.qo_postprocess_f32.restype, L.qo_postprocess_f32.argtypes = C.c_float, [C.c_int, C.c_float]
         for name in ("dot", "cosine", "euclid", "manhattan"):
@@ -269,11 +273,17 @@ class SQ8:
         return 4 + self.meta.actual_dim
 
     @staticmethod
-    def encode(data, distance_type: int, invert: bool) -> "SQ8":
-        """EncodedVectorsU8::encode with quantile=None (encoded_vectors_u8.rs:143-316)."""
+    def encode(data, distance_type: int, invert: bool, alpha=None, offset=None) -> "SQ8":
+        """EncodedVectorsU8::encode with quantile=None (encoded_vectors_u8.rs:143-316).  alpha/offset override the min/max
+        metadata (what a quantile-clipped range does, :194-208): values outside the range exercise the clamp."""
         data = _f32(data)
         m = SQ8Meta()
         lib().qo_sq8_make_meta(_p(data, C.c_float), data.shape[0], data.shape[1], distance_type, int(invert), C.byref(m))
+        if alpha is not None:
+            a = np.float32(alpha)
+            m.alpha, m.offset = a, np.float32(offset)
+            mult = a * a if distance_type in (QD_DOT, QD_COSINE) else (a if distance_type == QD_L1 else np.float32(-2.0) * a * a)   # :210-225
+            m.multiplier = np.float32(-mult if invert else mult)
         rows = np.zeros((data.shape[0], 4 + m.actual_dim), dtype=np.uint8)
         lib().qo_sq8_encode(C.byref(m), _p(data, C.c_float), data.shape[0], _p(rows, C.c_uint8))
         return SQ8(m, rows)
@@ -493,3 +503,35 @@ class HNSW:
         if self._h:
             lib().qo_hnsw_free(self._h)
             self._h = None
+
+
+# ------------------------------------------------------------------------------------------------ custom queries
+RECO_BEST_SCORE, RECO_SUM_SCORES, DISCOVER, CONTEXT = 1, 2, 3, 4   # include/qb200.h qb_query_kind
+
+
+def fast_sigmoid(x) -> np.float32:
+    return np.float32(lib().qo_fast_sigmoid(np.float32(x)))
+
+
+def scaled_fast_sigmoid(x) -> np.float32:
+    return np.float32(lib().qo_scaled_fast_sigmoid(np.float32(x)))
+
+
+def custom_examples(kind: int, n_a: int, n_b: int) -> int:
+    return {RECO_BEST_SCORE: n_a + n_b, RECO_SUM_SCORES: n_a + n_b, DISCOVER: 1 + 2 * n_a, CONTEXT: 2 * n_a}[kind]
+
+
+def custom_score(kind: int, n_a: int, n_b: int, sims) -> np.float32:
+    """Query::score_by for ONE candidate; sims = its similarities to the examples, in the layout of qb_scorer_create_custom."""
+    sims = _f32(sims).reshape(-1)
+    assert sims.size == custom_examples(kind, n_a, n_b)
+    return np.float32(lib().qo_custom_score(kind, n_a, n_b, _p(sims, C.c_float), 1))
+
+
+def custom_combine(kind: int, n_a: int, n_b: int, sims) -> np.ndarray:
+    """sims: [examples, candidates] -> [candidates] scores."""
+    sims = np.ascontiguousarray(_f32(sims))
+    assert sims.ndim == 2 and sims.shape[0] == custom_examples(kind, n_a, n_b)
+    out = np.empty(sims.shape[1], dtype=np.float32)
+    lib().qo_custom_combine(kind, n_a, n_b, _p(sims, C.c_float), sims.shape[1], sims.shape[1], _p(out, C.c_float))
+    return out

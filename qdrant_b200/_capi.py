@@ -56,6 +56,13 @@ SIGNATURES = {
     "qb_scorer_take_counters": (C.c_int32, [vp, C.POINTER(HwCounters)]),
     "qb_search_batch": (C.c_int32, [vp, f32p, C.c_uint32, C.c_uint32, u64p, u32p, C.c_uint64, i32p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
     "qb_search_batch_device": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp]),
+    "qb_scorer_create_custom": (C.c_int32, [vp, C.c_int, f32p, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "qb_search_custom": (C.c_int32, [vp, C.c_int, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, C.c_uint64, i32p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
+    "qb_sq8_find_alpha_offset_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, f32p, f32p]),
+    "qb_sq8_encode_rows_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]),
+    "qb_bq_row_bytes": (C.c_uint32, [C.c_uint32, C.c_int]),
+    "qb_bq_encode_rows_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_int, f32p, vp, vp]),
+    "qb_pq_encode_rows_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint64, vp, C.c_uint64, vp, vp]),
     "qb_rescore": (C.c_int32, [vp, u32p, C.c_size_t, C.c_uint32, C.POINTER(ScoredPoint), u32p]),
     "qb_storage_set_id_base": (C.c_int32, [vp, C.c_uint32]),
     "qb_topk_merge_device": (C.c_int32, [C.c_int32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]),

@@ -34,6 +34,11 @@ qb_status qb_bq_encode_queries(const qb_storage* s, const float* d_q_pre, uint32
 qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
 
+uint32_t qb_custom_examples(int kind, uint32_t n_a, uint32_t n_b);
+qb_status qb_launch_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* d_sims, uint64_t stride, uint64_t n, float* d_scores, const uint32_t* d_ids,
+                                   const QbEmit* emit, cudaStream_t stream);
+qb_status qb_launch_iota(uint32_t* d, uint64_t n, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
 std::atomic<uint64_t> g_qb_launches{0};
@@ -793,11 +798,113 @@ extern "C" qb_status qb_scorer_create_internal(qb_storage* s, uint32_t point_id,
     return QB_OK;
 }
 
+static qb_status launch_example(const qb_storage* s, const void* d_enc, const float* d_q_off, uint32_t e, bool internal, const uint32_t* d_ids, uint64_t n,
+                                float* d_scores, cudaStream_t stream);
+
+static qb_status check_custom(qb_query_kind kind, uint32_t n_a, uint32_t n_b, uint32_t* n_examples) {
+    QB_CHECK(kind >= QB_QUERY_RECO_BEST_SCORE && kind <= QB_QUERY_CONTEXT, QB_ERR_INVALID, "custom query: unknown kind %d", (int)kind);
+    QB_CHECK((kind != QB_QUERY_DISCOVER && kind != QB_QUERY_CONTEXT) || n_b == 0, QB_ERR_INVALID, "custom query: n_b must be 0 for discover / context (n_a = pairs)");
+    const uint32_t e = qb_custom_examples((int)kind, n_a, n_b);
+    QB_CHECK(e >= 1 && e <= 4096, QB_ERR_INVALID, "custom query: %u example vectors (need 1..4096)", e);
+    *n_examples = e;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_scorer_create_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, qb_scorer** out) {
+    QB_CHECK(s && vectors && out, QB_ERR_INVALID, "scorer_create_custom: null argument");
+    *out = nullptr;
+    uint32_t ne = 0;
+    QB_TRY(check_custom(kind, n_a, n_b, &ne));
+    QB_TRY(use_device(s->device));
+    qb_scorer* sc = new qb_scorer();
+    sc->st = s;
+    sc->custom_kind = (int)kind; sc->n_a = n_a; sc->n_b = n_b; sc->n_examples = ne;
+    sc->query_bytes = (size_t)ne * qb_encoded_query_bytes(s);
+    float* d_raw = nullptr;
+    const size_t raw = round_up_u64((size_t)ne * s->dim * 4, 16), pre = (size_t)ne * pre_stride_f(s) * 4;
+    qb_status st = QB_OK;
+    if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&sc->d_query, sc->query_bytes + 256) != cudaSuccess ||
+        cudaMalloc(&sc->d_q_off, (size_t)ne * 4 + 256) != cudaSuccess || cudaMalloc(&d_raw, raw + pre + 256) != cudaSuccess) {
+        st = QB_ERR_OOM;
+    } else if (cudaMemcpyAsync(d_raw, vectors, (size_t)ne * s->dim * 4, cudaMemcpyHostToDevice, sc->stream) != cudaSuccess) {
+        st = QB_ERR_CUDA;
+    } else {
+        st = prepare_queries(s, d_raw, ne, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_raw) + raw), sc->d_query, sc->d_q_off, sc->stream);
+        if (st == QB_OK && cudaStreamSynchronize(sc->stream) != cudaSuccess) st = QB_ERR_CUDA;
+    }
+    cudaFree(d_raw);
+    if (st != QB_OK) { qb_set_error("scorer_create_custom: %s", cudaGetErrorString(cudaGetLastError())); qb_scorer_destroy(sc); return st; }
+    *out = sc;
+    return QB_OK;
+}
+
+extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, uint32_t top,
+                                      const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
+                                      qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters) {
+    QB_CHECK(s && vectors && out && out_count, QB_ERR_INVALID, "search_custom: null argument");
+    QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "search_custom: top %u outside [1,%u]", top, QB_MAX_TOP);
+    uint32_t ne = 0;
+    QB_TRY(check_custom(kind, n_a, n_b, &ne));
+    if (id_list) for (uint64_t i = 0; i < n_ids; ++i) QB_CHECK(id_list[i] < s->count, QB_ERR_INVALID, "search_custom: id %u out of range", id_list[i]);
+    const uint64_t n = id_list ? n_ids : s->count;
+    *out_count = 0;
+    if (n == 0) return QB_OK;
+    // every candidate needs its similarity to every example before the fold: E x n floats + n keys of scratch
+    QB_CHECK(n * (12ull + 4ull * ne) <= (16ull << 30), QB_ERR_UNSUPPORTED, "search_custom: %llu candidates x %u examples exceed the 16 GB scratch budget",
+             (unsigned long long)n, ne);
+    if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+    QB_TRY(use_device(s->device));
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_acquire(s, &c));
+    struct Rel { qb_storage* s; QbSearchCtx* c; ~Rel() { qb_ctx_release(s, c); } } rel{s, c};
+    cudaStream_t stream = c->stream;
+    const size_t raw_bytes = (size_t)ne * s->dim * 4, res_bytes = (size_t)top * sizeof(qb_scored_point);
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + 16));
+    uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
+    memcpy(hs, vectors, raw_bytes);
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, round_up_u64(raw_bytes, 16) + (size_t)ne * pre_stride_f(s) * 4));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)ne + 256) * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)ne));
+    QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)top));
+    QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)8));
+    QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)n));
+    QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)n));
+    QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, (size_t)ne * n * 4));
+    QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
+    QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), ne,
+                           reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + round_up_u64(raw_bytes, 16)), c->d_queries_enc, c->d_q_off, stream));
+    const uint32_t* d_del2 = nullptr;
+    if (deleted_bitmap) {
+        const size_t words64 = (size_t)ceil_div_u64(s->count, 64);
+        QB_TRY(ensure_dev_elems(&c->d_deleted2, &c->deleted2_words, words64 * 2));
+        QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_bitmap, words64 * 8, cudaMemcpyHostToDevice, stream));
+        d_del2 = c->d_deleted2;
+    }
+    if (id_list) QB_CUDA(cudaMemcpyAsync(c->d_ids, id_list, n * 4, cudaMemcpyHostToDevice, stream));
+    else QB_TRY(qb_launch_iota(c->d_ids, n, stream));
+    float* d_sims = reinterpret_cast<float*>(c->d_mma);
+    for (uint32_t e = 0; e < ne; ++e) {
+        if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+        QB_TRY(launch_example(s, c->d_queries_enc, c->d_q_off, e, false, c->d_ids, n, d_sims + (size_t)e * n, stream));
+    }
+    QbEmit emit{};
+    emit.cand = c->d_cand; emit.cap = n; emit.dense = 1; emit.dense_base = 0; emit.deleted = s->d_deleted; emit.deleted2 = d_del2; emit.id_base = s->id_base;
+    QB_TRY(qb_launch_custom_combine((int)kind, n_a, n_b, d_sims, n, n, nullptr, c->d_ids, &emit, stream));
+    QB_TRY(qb_launch_select(c->d_cand, nullptr, n, n, 1, top, 0, c->d_out, c->d_out_counts, nullptr, nullptr, stream));
+    QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaMemcpyAsync(hs + raw_bytes + res_bytes, c->d_out_counts, 4, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaStreamSynchronize(stream));
+    memcpy(out, hs + raw_bytes, res_bytes);
+    memcpy(out_count, hs + raw_bytes + res_bytes, 4);
+    if (counters) counters->cpu += n * (uint64_t)ne * cpu_units_per_point(s);
+    return QB_OK;
+}
+
 extern "C" void qb_scorer_destroy(qb_scorer* sc) {
     if (!sc) return;
     cudaSetDevice(sc->st->device);
     if (sc->stream) cudaStreamSynchronize(sc->stream);
-    cudaFree(sc->d_query); cudaFree(sc->d_q_off); cudaFree(sc->d_ids); cudaFree(sc->d_scores);
+    cudaFree(sc->d_query); cudaFree(sc->d_q_off); cudaFree(sc->d_ids); cudaFree(sc->d_scores); cudaFree(sc->d_sims);
     if (sc->h_ids) cudaFreeHost(sc->h_ids);
     if (sc->h_scores) cudaFreeHost(sc->h_scores);
     if (sc->stream) cudaStreamDestroy(sc->stream);
@@ -815,19 +922,40 @@ static qb_status scorer_reserve(qb_scorer* sc, size_t n) {
     sc->d_ids = nullptr; sc->d_scores = nullptr; sc->h_ids = nullptr; sc->h_scores = nullptr; sc->cap = 0;
     QB_CUDA(cudaMalloc(&sc->d_ids, cap * 4));
     QB_CUDA(cudaMalloc(&sc->d_scores, cap * 4));
-    QB_CUDA(cudaMallocHost(&sc->h_ids, cap * 4));
-    QB_CUDA(cudaMallocHost(&sc->h_scores, cap * 4));
+    // pinned AND mapped: small batches (an HNSW hop is <= 32 ids) are read / written by the kernel straight through PCIe, which
+    // leaves one launch and one synchronisation per call instead of two copies around them
+    QB_CUDA(cudaHostAlloc(&sc->h_ids, cap * 4, cudaHostAllocMapped));
+    QB_CUDA(cudaHostAlloc(&sc->h_scores, cap * 4, cudaHostAllocMapped));
+    QB_CUDA(cudaHostGetDevicePointer(&sc->m_ids, sc->h_ids, 0));
+    QB_CUDA(cudaHostGetDevicePointer(&sc->m_scores, sc->h_scores, 0));
     sc->cap = cap;
     return QB_OK;
 }
 
+// similarities of `n` ids to encoded query `e` of a buffer of encoded queries
+static qb_status launch_example(const qb_storage* s, const void* d_enc, const float* d_q_off, uint32_t e, bool internal, const uint32_t* d_ids, uint64_t n,
+                                float* d_scores, cudaStream_t stream) {
+    const void* q = reinterpret_cast<const uint8_t*>(d_enc) + (size_t)e * qb_encoded_query_bytes(s);
+    if (s->kind == QB_KIND_BQ) {
+        const int bits = internal ? 1 : (s->bq_qenc == QB_BQQ_SCALAR4 ? 4 : (s->bq_qenc == QB_BQQ_SCALAR8 ? 8 : 1));
+        return qb_bq_score_points(s, q, bits, d_ids, n, d_scores, stream);
+    }
+    return qb_launch_score_points(s, q, d_q_off ? d_q_off + e : nullptr, d_ids, n, d_scores, stream);
+}
+
 static qb_status scorer_launch(qb_scorer* sc, const uint32_t* d_ids, uint64_t n, float* d_scores) {
     qb_storage* s = sc->st;
-    if (s->kind == QB_KIND_BQ) {
-        const int bits = sc->internal ? 1 : (s->bq_qenc == QB_BQQ_SCALAR4 ? 4 : (s->bq_qenc == QB_BQQ_SCALAR8 ? 8 : 1));
-        return qb_bq_score_points(s, sc->d_query, bits, d_ids, n, d_scores, sc->stream);
+    if (!sc->custom_kind) return launch_example(s, sc->d_query, sc->d_q_off, 0, sc->internal, d_ids, n, d_scores, sc->stream);
+    // custom query: one launch per example vector, then Query::score_by per candidate
+    if (n > sc->sims_cap) {
+        cudaFree(sc->d_sims); sc->d_sims = nullptr; sc->sims_cap = 0;
+        const size_t cap = round_up_u64(std::max<uint64_t>(n, 256), 256);
+        QB_CUDA(cudaMalloc(&sc->d_sims, (size_t)sc->n_examples * cap * 4));
+        sc->sims_cap = cap;
     }
-    return qb_launch_score_points(s, sc->d_query, sc->d_q_off, d_ids, n, d_scores, sc->stream);
+    for (uint32_t e = 0; e < sc->n_examples; ++e)
+        QB_TRY(launch_example(s, sc->d_query, sc->d_q_off, e, false, d_ids, n, sc->d_sims + (size_t)e * sc->sims_cap, sc->stream));
+    return qb_launch_custom_combine(sc->custom_kind, sc->n_a, sc->n_b, sc->d_sims, sc->sims_cap, n, d_scores, nullptr, nullptr, sc->stream);
 }
 
 extern "C" qb_status qb_score_points(qb_scorer* sc, const uint32_t* ids, size_t n, float* scores) {
@@ -838,9 +966,13 @@ extern "C" qb_status qb_score_points(qb_scorer* sc, const uint32_t* ids, size_t 
     QB_TRY(use_device(s->device));
     QB_TRY(scorer_reserve(sc, n));
     memcpy(sc->h_ids, ids, n * 4);
-    QB_CUDA(cudaMemcpyAsync(sc->d_ids, sc->h_ids, n * 4, cudaMemcpyHostToDevice, sc->stream));
-    QB_TRY(scorer_launch(sc, sc->d_ids, n, sc->d_scores));
-    QB_CUDA(cudaMemcpyAsync(sc->h_scores, sc->d_scores, n * 4, cudaMemcpyDeviceToHost, sc->stream));
+    if (n <= 2048) {
+        QB_TRY(scorer_launch(sc, reinterpret_cast<const uint32_t*>(sc->m_ids), n, reinterpret_cast<float*>(sc->m_scores)));
+    } else {
+        QB_CUDA(cudaMemcpyAsync(sc->d_ids, sc->h_ids, n * 4, cudaMemcpyHostToDevice, sc->stream));
+        QB_TRY(scorer_launch(sc, sc->d_ids, n, sc->d_scores));
+        QB_CUDA(cudaMemcpyAsync(sc->h_scores, sc->d_scores, n * 4, cudaMemcpyDeviceToHost, sc->stream));
+    }
     QB_CUDA(cudaStreamSynchronize(sc->stream));
     memcpy(scores, sc->h_scores, n * 4);
     sc->hw.cpu += (uint64_t)n * cpu_units_per_point(s);
@@ -851,6 +983,7 @@ extern "C" qb_status qb_score_point(qb_scorer* sc, uint32_t id, float* score) { 
 
 extern "C" qb_status qb_score_internal(qb_scorer* sc, uint32_t a, uint32_t b, float* score) {
     QB_CHECK(sc && score, QB_ERR_INVALID, "score_internal: null argument");
+    QB_CHECK(!sc->custom_kind, QB_ERR_UNSUPPORTED, "score_internal: custom scorers compare against several vectors (custom_query_scorer.rs:111-113: unimplemented!)");
     qb_storage* s = sc->st;
     QB_CHECK(a < s->count && b < s->count, QB_ERR_INVALID, "score_internal: id out of range (the reference panics)");
     QB_TRY(use_device(s->device));

@@ -1,0 +1,101 @@
+// qb_custom.cu — the custom-query combinators (recommend / discover / context) on top of the per-example similarities.
+//
+// In the reference a custom query is a set of example vectors plus `Query::score_by(similarity)`: the scorer evaluates the
+// ordinary similarity of the stored vector against EVERY example and folds the results
+// (vector_storage/query_scorer/custom_query_scorer.rs:78-122, quantized/quantized_custom_query_scorer.rs).  Here the E
+// similarities of a candidate come from the same kernels as plain queries (one launch per example, each bit-exact), and
+// this file is the fold: one thread per candidate, f32 operations in the reference's order.
+//   RecoBestScore  query/reco_query.rs:64-90     max over positives / negatives (total_cmp), scaled_fast_sigmoid of the winner
+//   RecoSumScores  query/reco_query.rs:116-133   sequential f32 sums, positives minus negatives
+//   Discover       query/discover_query.rs:16-76 rank = sum of total_cmp(positive, negative) per pair, + sigmoid(target)
+//   Context        query/context_query.rs:52-62,111-119   sum over pairs of fast_sigmoid(min(p - n - EPSILON, 0))
+// fast_sigmoid = x / (1 + |x|), scaled_fast_sigmoid = 0.5 * (fast_sigmoid(x) + 1)   (lib/common/common/src/math.rs:7-18)
+#include "qb_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int total_cmp(float a, float b) {  // f32::total_cmp as -1 / 0 / 1
+    int x = __float_as_int(a), y = __float_as_int(b);
+    x ^= (int)((unsigned int)(x >> 31) >> 1);
+    y ^= (int)((unsigned int)(y >> 31) >> 1);
+    return (x > y) - (x < y);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, fabsf(x))); }
+__device__ __forceinline__ float scaled_fast_sigmoid(float x) { return __fmul_rn(0.5f, __fadd_rn(fast_sigmoid(x), 1.0f)); }
+
+// sims: [n_examples][stride] similarities, example-major
+__device__ __forceinline__ float combine(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ sims, uint64_t stride, uint64_t i) {
+    switch (kind) {
+        case QB_QUERY_RECO_BEST_SCORE: {
+            float max_p = __int_as_float(0xff800000), max_n = __int_as_float(0xff800000);
+            for (uint32_t e = 0; e < n_a; ++e) { const float s = sims[e * stride + i]; if (total_cmp(s, max_p) > 0) max_p = s; }
+            for (uint32_t e = 0; e < n_b; ++e) { const float s = sims[(n_a + e) * stride + i]; if (total_cmp(s, max_n) > 0) max_n = s; }
+            return (max_p > max_n) ? scaled_fast_sigmoid(max_p) : -scaled_fast_sigmoid(max_n);
+        }
+        case QB_QUERY_RECO_SUM_SCORES: {
+            float p = 0.0f, n = 0.0f;
+            for (uint32_t e = 0; e < n_a; ++e) p = __fadd_rn(p, sims[e * stride + i]);
+            for (uint32_t e = 0; e < n_b; ++e) n = __fadd_rn(n, sims[(n_a + e) * stride + i]);
+            return __fsub_rn(p, n);
+        }
+        case QB_QUERY_DISCOVER: {
+            int rank = 0;
+            for (uint32_t e = 0; e < n_a; ++e) rank += total_cmp(sims[(1 + 2 * e) * stride + i], sims[(2 + 2 * e) * stride + i]);
+            return __fadd_rn((float)rank, scaled_fast_sigmoid(sims[i]));
+        }
+        default: {  // QB_QUERY_CONTEXT
+            float sum = 0.0f;
+            for (uint32_t e = 0; e < n_a; ++e) {
+                const float d = __fsub_rn(__fsub_rn(sims[(2 * e) * stride + i], sims[(2 * e + 1) * stride + i]), 1.1920929e-7f);
+                sum = __fadd_rn(sum, fast_sigmoid(fminf(d, 0.0f)));
+            }
+            return sum;
+        }
+    }
+}
+
+__global__ void custom_combine_kernel(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ sims, uint64_t stride, uint64_t n, float* __restrict__ scores,
+                                      const uint32_t* __restrict__ ids, QbEmit emit, int to_keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float sc = combine(kind, n_a, n_b, sims, stride, i);
+        if (to_keys) qb_emit(emit, 0, i, ids ? ids[i] : (uint32_t)i, sc);
+        else scores[i] = sc;
+    }
+}
+
+__global__ void iota_kernel(uint32_t* p, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+
+}  // namespace
+
+uint32_t qb_custom_examples(int kind, uint32_t n_a, uint32_t n_b) {
+    switch (kind) {
+        case QB_QUERY_RECO_BEST_SCORE:
+        case QB_QUERY_RECO_SUM_SCORES: return n_a + n_b;
+        case QB_QUERY_DISCOVER: return 1 + 2 * n_a;
+        case QB_QUERY_CONTEXT: return 2 * n_a;
+        default: return 0;
+    }
+}
+
+// scores (to_keys = 0) or dense-mode candidate keys for query slot 0 of `emit` (to_keys = 1; ids = null means row i)
+qb_status qb_launch_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* d_sims, uint64_t stride, uint64_t n, float* d_scores, const uint32_t* d_ids,
+                                   const QbEmit* emit, cudaStream_t stream) {
+    if (n == 0) return QB_OK;
+    QbEmit e{};
+    if (emit) e = *emit;
+    const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div_u64(n, 256), 148ull * 16);
+    custom_combine_kernel<<<grid, 256, 0, stream>>>(kind, n_a, n_b, d_sims, stride, n, d_scores, d_ids, e, emit ? 1 : 0);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+qb_status qb_launch_iota(uint32_t* d, uint64_t n, cudaStream_t stream) {
+    if (n == 0) return QB_OK;
+    iota_kernel<<<(unsigned)std::min<uint64_t>(ceil_div_u64(n, 256), 148ull * 16), 256, 0, stream>>>(d, n);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}

@@ -96,6 +96,10 @@ struct qb_scorer {
     // staging (grown on demand)
     uint32_t* d_ids = nullptr;  float* d_scores = nullptr;  size_t cap = 0;
     uint32_t* h_ids = nullptr;  float* h_scores = nullptr;  size_t h_cap = 0;
+    void* m_ids = nullptr;      void* m_scores = nullptr;   // device-side addresses of the mapped host buffers
+    // custom queries (recommend / discover / context): d_query holds n_examples encoded queries, d_q_off their SQ8 offsets
+    int custom_kind = 0;  uint32_t n_a = 0, n_b = 0, n_examples = 1;
+    float* d_sims = nullptr;  size_t sims_cap = 0;          // [n_examples][cap] per-example similarities
     qb_hw_counters hw = {0, 0};
 };
 

@@ -97,6 +97,66 @@ def metric_preprocess(distance: Distance, vectors, device: int = 0) -> np.ndarra
     return out.reshape(np.shape(vectors))
 
 
+class QueryKind(enum.IntEnum):  # QueryVector variants beyond Nearest (data_types/vectors.rs)
+    RecommendBestScore = 1
+    RecommendSumScores = 2
+    Discover = 3
+    Context = 4
+
+
+class RecoQuery:
+    """vector_storage/query/reco_query.rs:12-29 — positives and negatives; wrap in RecoBestScoreQuery / RecoSumScoresQuery."""
+
+    def __init__(self, positives, negatives):
+        self.positives = [np.asarray(v, dtype=np.float32) for v in positives]
+        self.negatives = [np.asarray(v, dtype=np.float32) for v in negatives]
+
+
+class RecoBestScoreQuery:
+    kind = QueryKind.RecommendBestScore
+
+    def __init__(self, query: RecoQuery):
+        self.query = query
+
+    def flat(self):
+        return self.query.positives + self.query.negatives, len(self.query.positives), len(self.query.negatives)
+
+
+class RecoSumScoresQuery(RecoBestScoreQuery):
+    kind = QueryKind.RecommendSumScores
+
+
+class ContextPair:
+    """vector_storage/query/context_query.rs:13-17"""
+
+    def __init__(self, positive, negative):
+        self.positive = np.asarray(positive, dtype=np.float32)
+        self.negative = np.asarray(negative, dtype=np.float32)
+
+
+class DiscoverQuery:
+    """vector_storage/query/discover_query.rs:27-36 — a target and context pairs."""
+    kind = QueryKind.Discover
+
+    def __init__(self, target, pairs: Sequence[ContextPair]):
+        self.target = np.asarray(target, dtype=np.float32)
+        self.pairs = list(pairs)
+
+    def flat(self):
+        return [self.target] + [v for p in self.pairs for v in (p.positive, p.negative)], len(self.pairs), 0
+
+
+class ContextQuery:
+    """vector_storage/query/context_query.rs:87-99"""
+    kind = QueryKind.Context
+
+    def __init__(self, pairs: Sequence[ContextPair]):
+        self.pairs = list(pairs)
+
+    def flat(self):
+        return [v for p in self.pairs for v in (p.positive, p.negative)], len(self.pairs), 0
+
+
 class RawScorer:
     """Box<dyn RawScorer>.  Scoring calls are infallible in the reference; here a CUDA failure raises QbError."""
 
@@ -161,6 +221,36 @@ class _Storage:
         h = vp()
         check(lib().qb_scorer_create(self._h, q.ctypes.data_as(f32p), C.byref(h)))
         return RawScorer(self, h.value)
+
+    def _flat_custom(self, query):
+        vecs, n_a, n_b = query.flat()
+        if not vecs:
+            raise ValueError("custom query without example vectors")
+        m = np.ascontiguousarray(np.stack([_f32(v).reshape(-1) for v in vecs]))
+        if m.shape[1] != self.dim:
+            raise ValueError(f"query vectors have dim {m.shape[1]}, storage has {self.dim}")
+        return m, n_a, n_b
+
+    def raw_scorer_custom(self, query) -> RawScorer:
+        """new_raw_scorer for QueryVector::{RecommendBestScore, RecommendSumScores, Discover, Context} (raw_scorer.rs:228-333)."""
+        m, n_a, n_b = self._flat_custom(query)
+        h = vp()
+        check(lib().qb_scorer_create_custom(self._h, int(query.kind), m.ctypes.data_as(f32p), n_a, n_b, C.byref(h)))
+        return RawScorer(self, h.value)
+
+    def search_custom(self, query, top: int, point_deleted=None, id_list=None, counters: Optional[HwCounters] = None):
+        """peek_top_iter driven by a custom-query scorer -> SCORED_POINT_OFFSET array, descending."""
+        m, n_a, n_b = self._flat_custom(query)
+        out = np.zeros(max(top, 1), dtype=SCORED_POINT_OFFSET)
+        count = C.c_uint32()
+        bm = _bitmap(point_deleted, self.count)
+        ids = None if id_list is None else _ids(id_list)
+        check(lib().qb_search_custom(
+            self._h, int(query.kind), m.ctypes.data_as(f32p), n_a, n_b, int(top),
+            None if bm is None else bm.ctypes.data_as(u64p),
+            None if ids is None else ids.ctypes.data_as(u32p), 0 if ids is None else ids.size, None,
+            out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(count), None if counters is None else C.byref(counters)))
+        return out[: count.value].copy()
 
     def _raw_internal_scorer(self, point_id: int) -> RawScorer:
         h = vp()
@@ -425,3 +515,44 @@ def postprocess_search_result(search_result: np.ndarray, original: DenseVectorSt
     check(lib().qb_rescore(sc._h, ids.ctypes.data_as(u32p), ids.size, int(top), out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(n)))
     sc.close()
     return out[: n.value].copy()
+
+
+# ------------------------------------------------------------------------------------------------ quantizer encode on the device
+# Thin wrappers over the C ABI (include/qb200.h, "quantizer encode on the device"): every pointer is a raw device address.
+def sq8_multiplier(alpha: float, distance: Distance) -> np.float32:
+    """EncodedVectorsU8::encode, encoded_vectors_u8.rs:210-225: Dot a^2, L1 a, L2 -2a^2; negated when `invert`."""
+    dt, inv = construct_vector_parameters(distance)
+    a = np.float32(alpha)
+    m = {DistanceType.Dot: a * a, DistanceType.L1: a, DistanceType.L2: np.float32(-2.0) * a * a}[dt]
+    return np.float32(-m if inv else m)
+
+
+def sq8_find_alpha_offset(rows_ptr: int, count: int, dim: int, row_stride_bytes: int = 0, device: int = 0) -> tuple[np.float32, np.float32]:
+    a, o = C.c_float(), C.c_float()
+    check(lib().qb_sq8_find_alpha_offset_device(device, dim, count, vp(rows_ptr), row_stride_bytes, C.byref(a), C.byref(o)))
+    return np.float32(a.value), np.float32(o.value)
+
+
+def sq8_encode_rows(rows_ptr: int, count: int, dim: int, alpha: float, offset: float, distance: Distance, out_ptr: int, row_stride_bytes: int = 0,
+                    device: int = 0, stream: int = 0) -> None:
+    """out_ptr: count x (4 + actual_dim) bytes, the row format qb_storage_create_sq8 / ScalarQuantizedVectors(rows_ptr=...) takes."""
+    dt, inv = construct_vector_parameters(distance)
+    check(lib().qb_sq8_encode_rows_device(device, dim, count, vp(rows_ptr), row_stride_bytes, np.float32(alpha), np.float32(offset), int(dt), int(inv), vp(out_ptr),
+                                          vp(stream)))
+
+
+def bq_row_bytes(dim: int, encoding: BQEncoding) -> int:
+    return int(lib().qb_bq_row_bytes(dim, int(encoding)))
+
+
+def bq_encode_rows(rows_ptr: int, count: int, dim: int, encoding: BQEncoding, out_ptr: int, mean_std=None, row_stride_bytes: int = 0, device: int = 0,
+                   stream: int = 0) -> None:
+    ms = None if mean_std is None else _f32(mean_std)
+    check(lib().qb_bq_encode_rows_device(device, dim, count, vp(rows_ptr), row_stride_bytes, int(encoding), None if ms is None else ms.ctypes.data_as(f32p),
+                                         vp(out_ptr), vp(stream)))
+
+
+def pq_encode_rows(rows_ptr: int, count: int, dim: int, chunk: int, centroids, out_ptr: int, row_stride_bytes: int = 0, device: int = 0, stream: int = 0) -> None:
+    c = _f32(centroids)
+    assert c.ndim == 2 and c.shape[1] == dim
+    check(lib().qb_pq_encode_rows_device(device, dim, chunk, c.shape[0], c.ctypes.data_as(f32p), count, vp(rows_ptr), row_stride_bytes, vp(out_ptr), vp(stream)))

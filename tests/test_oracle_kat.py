@@ -185,3 +185,66 @@ def test_f16_avx_vs_scalar_tolerance(oracle):
     assert abs(simd - exact) / exact < 1e-5
     assert oracle.similarity_f16(oracle.DOT, v1, v2) == simd
     assert oracle.similarity_f16(oracle.COSINE, v1, v2) == simd  # f16 cosine == dot (simple_cosine.rs:28-58)
+
+
+# ------------------------------------------------------------------------------------------------ custom queries
+def test_reco_best_score_reference_table(oracle):
+    """reco_query.rs:150-185 `score_query` rstest table (dummy similarity = the example itself)."""
+    cases = [([42], [4], "P", 42.0), ([4], [42], "N", 42.0), ([-1], [0], "N", 0.0), ([0], [-1], "P", 0.0), ([-42], [-84], "P", -42.0),
+             ([-84], [-42], "N", -42.0), ([1, 2, 3], [4, 5, 6], "N", 6.0), ([10, 2, 3], [4, 5, 6], "P", 10.0)]
+    for pos, neg, chosen, expected in cases:
+        got = oracle.custom_score(oracle.RECO_BEST_SCORE, len(pos), len(neg), np.array(pos + neg, np.float32))
+        want = oracle.scaled_fast_sigmoid(expected) if chosen == "P" else -oracle.scaled_fast_sigmoid(expected)
+        assert got == want, (pos, neg)
+    # math.rs:7-18
+    assert oracle.fast_sigmoid(3.0) == np.float32(3.0) / np.float32(4.0)
+    assert oracle.scaled_fast_sigmoid(-1.0) == np.float32(0.25)
+
+
+def test_reco_best_score_order_properties(oracle):
+    """reco_query.rs:204-262 proptests: negatives invert the order, positives keep it, positive-chosen >= negative-chosen."""
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        a, b = (np.float32(x) for x in rng.uniform(-100, 100, 2))
+        pa, pb = (oracle.custom_score(oracle.RECO_BEST_SCORE, 1, 0, np.array([x], np.float32)) for x in (a, b))
+        na, nb = (oracle.custom_score(oracle.RECO_BEST_SCORE, 0, 1, np.array([x], np.float32)) for x in (a, b))
+        if a < b:
+            assert pa <= pb and na >= nb
+        assert pa >= nb and pb >= na
+
+
+def test_discover_rank_reference_table(oracle):
+    """discover_query.rs:100-125 `context_ranking` rstest table; score = rank + scaled_fast_sigmoid(target) (:66-76)."""
+    cases = [([], 0), ([(10, 4)], 1), ([(4, 10)], -1), ([(11, 11)], 0), ([(10, 4), (4, 10)], 0), ([(10, 4), (4, 2)], 2), ([(4, 10), (2, 4)], -2),
+             ([(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (0, 4)], 4)]
+    for pairs, rank in cases:
+        sims = np.array([42.0] + [x for p in pairs for x in p], np.float32)
+        got = oracle.custom_score(oracle.DISCOVER, len(pairs), 0, sims)
+        assert got == np.float32(rank) + oracle.scaled_fast_sigmoid(42.0), pairs
+
+
+def test_context_loss_bounds_and_sum(oracle):
+    """context_query.rs:146-160: per-pair loss in (-1, 0]; :111-119: the score is the sequential f32 sum of the losses."""
+    rng = np.random.default_rng(1)
+    for _ in range(1000):
+        p, n = (np.float32(x) for x in rng.uniform(-100, 100, 2))
+        s = oracle.custom_score(oracle.CONTEXT, 1, 0, np.array([p, n], np.float32))
+        assert -1.0 < s <= 0.0
+        if p > n + np.float32(1e-3):
+            assert s == 0.0
+    sims = np.array([1.0, 3.0, 5.0, 2.0, -2.0, 0.5], np.float32)  # pairs (1,3) (5,2) (-2,0.5)
+    eps = np.float32(np.finfo(np.float32).eps)
+    want = np.float32(0.0)
+    for p, n in [(1.0, 3.0), (5.0, 2.0), (-2.0, 0.5)]:
+        d = min(np.float32(np.float32(p) - np.float32(n)) - eps, np.float32(0.0))
+        want = np.float32(want + np.float32(d / np.float32(np.float32(1.0) + abs(d))))
+    assert oracle.custom_score(oracle.CONTEXT, 3, 0, sims) == want
+
+
+def test_reco_sum_scores(oracle):
+    sims = np.array([0.1, 0.2, 0.7, 0.05], np.float32)
+    want = np.float32(np.float32(np.float32(0.0) + sims[0]) + sims[1]) - np.float32(np.float32(np.float32(0.0) + sims[2]) + sims[3])
+    assert oracle.custom_score(oracle.RECO_SUM_SCORES, 2, 2, sims) == np.float32(want)
+    m = np.stack([sims, sims[::-1]], axis=1)  # two candidates
+    out = oracle.custom_combine(oracle.RECO_SUM_SCORES, 2, 2, m)
+    assert out[0] == np.float32(want) and out.shape == (2,)
