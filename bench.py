@@ -397,13 +397,16 @@ def main_c3(args):
     for i, r0 in enumerate(range(0, n, chunk)):
         cn = min(chunk, n - r0)
         x = gen_chunk(i, cn)
-        codes = torch.clamp(torch.floor((x - float(offset)) / float(alpha) + 0.5), 0, 127)
-        voff = (codes.sum(1) * float(alpha) * float(offset) + float(np.float32(ad) * offset * offset)).to(torch.float32)
-        rows[r0 : r0 + cn, 4 : 4 + dim] = codes.to(torch.uint8)
-        if ad > dim:
-            rows[r0 : r0 + cn, 4 + dim :] = int(min(max(round((0.0 - float(offset)) / float(alpha)), 0), 127))
-        rows[r0 : r0 + cn, :4] = voff.view(torch.uint8).view(cn, 4)
-        del x, codes, voff
+        # EncodedVectorsU8::encode on the device (qb_sq8_encode_rows_device), straight into the storage's row format
+        qb.sq8_encode_rows(x.data_ptr(), cn, dim, alpha, offset, qb.Distance.Cosine, rows[r0:].data_ptr())
+        if i == 0 and not args.no_cpu:
+            from oracle import oracle as o
+
+            torch.cuda.synchronize()
+            want = o.SQ8.encode(x[:2000].cpu().numpy(), o.QD_DOT, False, alpha=alpha, offset=offset)
+            assert np.array_equal(rows[:2000].cpu().numpy(), want.rows), "bench parity spot-check failed: device SQ8 encode != oracle encode"
+        torch.cuda.synchronize()
+        del x
     torch.cuda.synchronize()
     st = qb.ScalarQuantizedVectors(None, dim, float(alpha), float(offset), float(multiplier), qb.Distance.Cosine, rows_ptr=rows.data_ptr(), count=n)
     sample_rows = min(65536, n)

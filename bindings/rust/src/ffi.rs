@@ -48,5 +48,21 @@ extern "C" {
     pub fn qb_search_batch(s: *mut qb_storage, queries: *const f32, n_queries: u32, top: u32, deleted_bitmap: *const u64,
                            id_list: *const u32, n_ids: u64, is_stopped: *const i32, out: *mut qb_scored_point,
                            out_counts: *mut u32, counters: *mut qb_hw_counters) -> qb_status;
+    /// QueryVector::{RecommendBestScore = 1, RecommendSumScores = 2, Discover = 3, Context = 4}: `vectors` holds the flattened
+    /// example vectors (positives then negatives / target then pairs / pairs), see include/qb200.h.
+    pub fn qb_scorer_create_custom(s: *mut qb_storage, kind: i32, vectors: *const f32, n_a: u32, n_b: u32, out: *mut *mut qb_scorer) -> qb_status;
+    pub fn qb_search_custom(s: *mut qb_storage, kind: i32, vectors: *const f32, n_a: u32, n_b: u32, top: u32, deleted_bitmap: *const u64,
+                            id_list: *const u32, n_ids: u64, is_stopped: *const i32, out: *mut qb_scored_point, out_count: *mut u32,
+                            counters: *mut qb_hw_counters) -> qb_status;
+    /// Quantizer encode on rows already resident in HBM (device pointers); outputs are the reference's row formats.
+    pub fn qb_sq8_find_alpha_offset_device(device: i32, dim: u32, count: u64, dev_rows: *const f32, row_stride_bytes: u64, alpha: *mut f32,
+                                           offset: *mut f32) -> qb_status;
+    pub fn qb_sq8_encode_rows_device(device: i32, dim: u32, count: u64, dev_rows: *const f32, row_stride_bytes: u64, alpha: f32, offset: f32, dt: i32,
+                                     invert: i32, dev_out: *mut u8, stream: *mut c_void) -> qb_status;
+    pub fn qb_bq_row_bytes(dim: u32, encoding: i32) -> u32;
+    pub fn qb_bq_encode_rows_device(device: i32, dim: u32, count: u64, dev_rows: *const f32, row_stride_bytes: u64, encoding: i32, mean_std: *const f32,
+                                    dev_out: *mut u8, stream: *mut c_void) -> qb_status;
+    pub fn qb_pq_encode_rows_device(device: i32, dim: u32, chunk: u32, n_centroids: u32, centroids: *const f32, count: u64, dev_rows: *const f32,
+                                    row_stride_bytes: u64, dev_codes: *mut u8, stream: *mut c_void) -> qb_status;
     pub fn qb_rescore(orig: *mut qb_scorer, ids: *const u32, n: usize, top: u32, out: *mut qb_scored_point, out_count: *mut u32) -> qb_status;
 }

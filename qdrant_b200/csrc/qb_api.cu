@@ -13,6 +13,7 @@
 // kernels' host entry points (qb_dense.cu / qb_quant.cu / qb_dtype.cu)
 qb_status qb_dense_f32_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_dense_f32_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
+qb_status qb_dense_f32_scan_localk(const qb_storage* s, const QbScanArgs& a, uint32_t top, uint64_t* n_slots, cudaStream_t stream);
 qb_status qb_dense_x_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_dense_x_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
 qb_status qb_dense_x_convert_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, void* d_out, cudaStream_t stream);
@@ -494,6 +495,7 @@ static SearchPlan make_plan(uint64_t n_cand, uint32_t nq, uint32_t top, bool for
         // costs < 1 % more scan work and cuts survivors 4x
         uint64_t sgoal = (uint64_t)((nq >= 32 ? 8.0 : 2.0) * sqrt((double)n_cand * (double)top));
         sgoal = round_up_u64(std::max<uint64_t>(sgoal, 8192), 1024);
+        if (const char* e = getenv("QB_SAMPLE_ROWS")) sgoal = std::max<uint64_t>(256, strtoull(e, nullptr, 10));  // tuning experiments
         p.sample = std::min<uint64_t>(sgoal, n_cand / 2);
         const uint64_t expect = (uint64_t)((double)n_cand * (double)top / (double)p.sample);
         p.cap = std::max<uint64_t>(p.sample, 8 * expect + 4096);
@@ -528,6 +530,23 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
     const uint64_t n_cand = d_ids ? n_ids : s->count;
     cudaStream_t stream = c->stream;
     if (n_cand == 0) { QB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, stream)); return QB_OK; }
+    // single query, small top, dense f32: one streaming scan with per-CTA top-k lists + one small select (qb_dense.cu, LOCALK)
+    if (nq == 1 && top <= 16 && !d_ids && !force_direct && s->kind == QB_KIND_DENSE && s->dtype == QB_DT_F32 && n_cand > 65536 && getenv("QB_DISABLE_LOCALK") == nullptr) {
+        QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)4096));
+        QbScanArgs a{};
+        a.d_q_enc = c->d_queries_enc; a.nq = 1; a.row_begin = 0; a.row_end = n_cand;
+        a.emit.deleted = s->d_deleted; a.emit.deleted2 = d_deleted2; a.emit.id_base = s->id_base; a.emit.cand = c->d_cand; a.emit.cap = 4096;
+        uint64_t n_slots = 0;
+        cudaEvent_t e0, e1;
+        profile_begin(s, c, stream, &e0, &e1);
+        QB_TRY(qb_dense_f32_scan_localk(s, a, top, &n_slots, stream));
+        if (n_slots != 0 && n_slots <= 4096) {
+            profile_end(s, stream, e0, e1);
+            return qb_launch_select(c->d_cand, nullptr, 4096, n_slots, 1, top, 0, d_out, d_counts, nullptr, nullptr, stream);
+        }
+        if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+        QB_CHECK(n_slots == 0, QB_ERR_CUDA, "local top-k scan wrote %llu slots", (unsigned long long)n_slots);
+    }
     const bool mma_ok = !d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr;
     const SearchPlan plan = make_plan(n_cand, nq, top, force_direct, mma_ok && qb_sq8_mma_block(s, nq) != 0 && !(rs_flags & RS_NO_REFINE));
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)plan.q_chunk * plan.cap));

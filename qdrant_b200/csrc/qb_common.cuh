@@ -93,6 +93,7 @@ struct QbEmit {
     unsigned long long dense_base;  // dense mode: position = slot - dense_base
     int dense;                      // 1 = dense mode
     uint32_t id_base;               // added to reported ids (row offset of this shard inside the sharded segment set)
+    uint32_t local_k;               // per-CTA top-k mode of the dense streaming kernel: entries kept per warp / written per CTA
 };
 
 #ifdef __CUDACC__

@@ -76,8 +76,11 @@ qb_select_kernel(const unsigned long long* cand, const unsigned int* __restrict_
         if (s_fill <= (unsigned int)SORT_CAP) { m = (int)s_fill; staged = true; }
         __syncthreads();
     }
-    if (staged && select_only) { keys = buf; n = (unsigned long long)m; }  // same select loop, reading shared memory
-    if (!staged || select_only) {
+    // staged keys: radix-select in shared memory instead of sorting all of them when only the threshold is wanted, or when the
+    // wanted prefix is short (sorting 4096 keys to keep 10 costs 78 bitonic steps; selecting costs <= 8 histogram passes)
+    const bool in_smem = staged && (select_only || (m >= 256 && (int)top * 4 <= m));
+    if (in_smem) { keys = buf; n = (unsigned long long)m; }
+    if (!staged || in_smem) {
         if (threadIdx.x == 0) { s_prefix = 0ull; s_kk = top; s_short = 0u; s_done = 0u; }
         unsigned long long mask = 0ull;
         __syncthreads();
@@ -138,13 +141,27 @@ qb_select_kernel(const unsigned long long* cand, const unsigned int* __restrict_
         }
         const unsigned long long kth = s_short ? 1ull : s_prefix;  // short: take every non-empty key
         if (threadIdx.x == 0) s_fill = 0u;
-        for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = 0ull;
-        __syncthreads();
-        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
-            unsigned long long key = keys[i];
-            if (key >= kth && key != 0ull) {
-                unsigned int p = atomicAdd(&s_fill, 1u);
-                if (p < SORT_CAP) buf[p] = key;
+        if (in_smem) {
+            // the source IS buf: pull this thread's keys into registers before the buffer is cleared and refilled
+            constexpr int PER = SORT_CAP / QB_SELECT_THREADS;
+            unsigned long long mine[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) { const int i = threadIdx.x + k * QB_SELECT_THREADS; mine[k] = (i < m) ? buf[i] : 0ull; }
+            __syncthreads();
+            for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = 0ull;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < PER; ++k)
+                if (mine[k] >= kth && mine[k] != 0ull) buf[atomicAdd(&s_fill, 1u)] = mine[k];  // at most m <= SORT_CAP keys
+        } else {
+            for (int i = threadIdx.x; i < SORT_CAP; i += blockDim.x) buf[i] = 0ull;
+            __syncthreads();
+            for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+                unsigned long long key = keys[i];
+                if (key >= kth && key != 0ull) {
+                    unsigned int p = atomicAdd(&s_fill, 1u);
+                    if (p < SORT_CAP) buf[p] = key;
+                }
             }
         }
         __syncthreads();

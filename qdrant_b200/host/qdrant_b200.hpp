@@ -97,6 +97,13 @@ public:
         check(qb_scorer_create(h_, query, &sc));
         return std::make_unique<B200RawScorer>(sc);
     }
+    // new_raw_scorer for QueryVector::{RecommendBestScore, RecommendSumScores, Discover, Context} (raw_scorer.rs:228-333):
+    // `vectors` = the flattened example vectors in the layout include/qb200.h documents
+    std::unique_ptr<RawScorer> build_custom_scorer(qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b) const {
+        qb_scorer* sc = nullptr;
+        check(qb_scorer_create_custom(h_, kind, vectors, n_a, n_b, &sc));
+        return std::make_unique<B200RawScorer>(sc);
+    }
     // QuantizedVectorsRead::raw_internal_scorer (throws OperationError{QB_ERR_UNSUPPORTED} for PQ)
     std::unique_ptr<RawScorer> raw_internal_scorer(PointOffsetType point) const {
         qb_scorer* sc = nullptr;
