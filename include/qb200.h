@@ -159,8 +159,9 @@ QB_API qb_status qb_search_batch(qb_storage* s, const float* queries, uint32_t n
                           const volatile int32_t* is_stopped, qb_scored_point* out, uint32_t* out_counts,
                           qb_hw_counters* counters /* optional */);
 /* Same scan with queries and outputs already resident in HBM, enqueued on qb_storage_stream(s) (bench.py's
- * kernel-only `value`).  The call waits for that stream once, to read the device's "fast-path assumption
- * broken" flags word (reruns happen inside, as in qb_search_batch).  It uses the storage's first search context:
+ * kernel-only `value`).  Paths with a fallback (threshold filter, tensor-core batch) wait for that stream once to
+ * read the device's "fast-path assumption broken" flags word (reruns happen inside, as in qb_search_batch); the
+ * single-pass paths (single-query dense f32 with top <= 16, small scans) return without synchronising.  It uses the storage's first search context:
  * do not run it concurrently with other searches on the same storage. */
 QB_API qb_status qb_search_batch_device(qb_storage* s, const float* dev_queries, uint32_t n_queries, uint32_t top,
                                  qb_scored_point* dev_out, uint32_t* dev_counts);

@@ -525,8 +525,10 @@ static void profile_end(qb_storage* s, cudaStream_t stream, cudaEvent_t e0, cuda
 // (device).  Sets *overflow_possible when the filter pass is used (caller checks c->d_cnt overflow flag at [nq]).
 enum { RS_FORCE_DIRECT = 1, RS_NO_MMA = 2, RS_NO_SEGMENTS = 4, RS_NO_REFINE = 8 };
 static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t top, const uint32_t* d_ids, uint64_t n_ids, const uint32_t* d_deleted2,
-                            const volatile int32_t* is_stopped, uint32_t rs_flags, qb_scored_point* d_out, uint32_t* d_counts, unsigned int* d_overflow) {
+                            const volatile int32_t* is_stopped, uint32_t rs_flags, qb_scored_point* d_out, uint32_t* d_counts, unsigned int* d_overflow,
+                            bool* can_flag = nullptr) {
     const bool force_direct = (rs_flags & RS_FORCE_DIRECT) != 0;
+    if (can_flag) *can_flag = true;  // cleared on the paths that have no heuristic to fall back from
     const uint64_t n_cand = d_ids ? n_ids : s->count;
     cudaStream_t stream = c->stream;
     if (n_cand == 0) { QB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, stream)); return QB_OK; }
@@ -542,6 +544,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         QB_TRY(qb_dense_f32_scan_localk(s, a, top, &n_slots, stream));
         if (n_slots != 0 && n_slots <= 4096) {
             profile_end(s, stream, e0, e1);
+            if (can_flag) *can_flag = false;
             return qb_launch_select(c->d_cand, nullptr, 4096, n_slots, 1, top, 0, d_out, d_counts, nullptr, nullptr, stream);
         }
         if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
@@ -549,6 +552,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
     }
     const bool mma_ok = !d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr;
     const SearchPlan plan = make_plan(n_cand, nq, top, force_direct, mma_ok && qb_sq8_mma_block(s, nq) != 0 && !(rs_flags & RS_NO_REFINE));
+    if (can_flag && plan.direct) *can_flag = false;  // full materialisation: no threshold, no counters, nothing to overflow
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)plan.q_chunk * plan.cap));
     QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)nq));
     QB_TRY(ensure_dev_elems(&c->d_cnt, &c->cnt_elems, (size_t)nq + 1));
@@ -738,7 +742,9 @@ extern "C" qb_status qb_search_batch_device(qb_storage* s, const float* dev_quer
     uint32_t rs_flags = 0;
     for (int attempt = 0; attempt < 4; ++attempt) {
         QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, c->stream));
-        QB_TRY(run_search(s, c, n_queries, top, nullptr, 0, nullptr, nullptr, rs_flags, dev_out, dev_counts, d_overflow));
+        bool can_flag = true;
+        QB_TRY(run_search(s, c, n_queries, top, nullptr, 0, nullptr, nullptr, rs_flags, dev_out, dev_counts, d_overflow, &can_flag));
+        if (!can_flag) break;  // exact single-pass path: nothing to check, the call stays asynchronous
         QB_CUDA(cudaMemcpyAsync(c->h_stage, d_overflow, 4, cudaMemcpyDeviceToHost, c->stream));
         QB_CUDA(cudaStreamSynchronize(c->stream));
         unsigned int flags = 0;
