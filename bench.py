@@ -333,7 +333,7 @@ def main_ours(args):
         achieved = algo_bytes / (kern_ms / 1e3) / 1e9 if n_prof else None
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's main pass from the committed `ncu --set full` capture; it
         # was taken on the 10M x 768 single-GPU workload, so it is only quoted for that shape
-        traffic, traffic_src = ncu_traffic("ncu_stream_kernel_r01.txt") if (n_local == 10_000_000 and args.dim == 768) else (None, None)
+        traffic, traffic_src = ncu_traffic("ncu_stream_kernel_r01_localk.txt") if (n_local == 10_000_000 and args.dim == 768) else (None, None)
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
