@@ -54,6 +54,11 @@ extern "C" {
     pub fn qb_search_custom(s: *mut qb_storage, kind: i32, vectors: *const f32, n_a: u32, n_b: u32, top: u32, deleted_bitmap: *const u64,
                             id_list: *const u32, n_ids: u64, is_stopped: *const i32, out: *mut qb_scored_point, out_count: *mut u32,
                             counters: *mut qb_hw_counters) -> qb_status;
+    /// Multivector MaxSim (score_max_similarity): point p = rows [point_offsets[p], point_offsets[p+1]) of a token-level storage.
+    pub fn qb_search_maxsim(s: *mut qb_storage, point_offsets: *const u32, n_points: u32, query_vectors: *const f32, n_query_vectors: u32, top: u32,
+                            deleted_points: *const u64, out: *mut qb_scored_point, out_count: *mut u32, counters: *mut qb_hw_counters) -> qb_status;
+    pub fn qb_score_maxsim(s: *mut qb_storage, point_offsets: *const u32, n_points: u32, query_vectors: *const f32, n_query_vectors: u32,
+                           point_ids: *const u32, n: usize, scores: *mut f32) -> qb_status;
     /// Quantizer encode on rows already resident in HBM (device pointers); outputs are the reference's row formats.
     pub fn qb_sq8_find_alpha_offset_device(device: i32, dim: u32, count: u64, dev_rows: *const f32, row_stride_bytes: u64, alpha: *mut f32,
                                            offset: *mut f32) -> qb_status;

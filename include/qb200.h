@@ -183,6 +183,19 @@ QB_API qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const float
                                   const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
                                   qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters /* optional */);
 
+/* ---------------------------------------------------------------- multivector MaxSim -- */
+/* ColBERT MaxSim, score_max_similarity (vector_storage/query_scorer/mod.rs:77-98) as used by MultiMetricQueryScorer
+ * (multi_metric_query_scorer.rs) and the quantized multivector storage: a point is a run of consecutive vectors of `s`
+ * (point p = rows [point_offsets[p], point_offsets[p+1]), the layout of the reference's flattened multivector storage,
+ * vector_storage/multi_dense/*.rs); score = sum over the query's vectors (sequential f32 from 0.0) of the best similarity
+ * (`sim > max`, from -inf) to any vector of the point.  Similarities are the storage's ordinary bit-exact ones, so `s`
+ * may be dense or quantized.  deleted_points: optional bitmap over POINTS (1 = skip). */
+QB_API qb_status qb_search_maxsim(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, const float* query_vectors,
+                                  uint32_t n_query_vectors, uint32_t top, const uint64_t* deleted_points, qb_scored_point* out, uint32_t* out_count,
+                                  qb_hw_counters* counters /* optional */);
+QB_API qb_status qb_score_maxsim(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, const float* query_vectors,
+                                 uint32_t n_query_vectors, const uint32_t* point_ids, size_t n, float* scores);
+
 /* ---------------------------------------------------------------- quantizer encode on the device -- */
 /* The ENCODE half of the quantizers, on f32 rows already resident in HBM; outputs are the reference's row formats bit
  * for bit and can be passed straight to qb_storage_create_{sq8,pq,bq} (device pointers are accepted there) or copied

@@ -1066,3 +1066,32 @@ API float qo_custom_score(int kind, uint32_t n_a, uint32_t n_b, const float* sim
 API void qo_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* sims, uint64_t stride, uint64_t n, float* out) {
     for (uint64_t i = 0; i < n; i++) out[i] = qo_custom_score(kind, n_a, n_b, sims + i, stride);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Multivector MaxSim: score_max_similarity, vector_storage/query_scorer/mod.rs:77-98.
+ * a = the query's vectors (na x dim), b = the stored point's vectors (nb x dim), both already preprocessed.
+ * ------------------------------------------------------------------------------------------------ */
+API float qo_maxsim_f32(int distance, const float* a, uint32_t na, const float* b, uint32_t nb, uint32_t dim) {
+    float sum = 0.0f;
+    for (uint32_t i = 0; i < na; i++) {
+        float max_sim = -INFINITY;
+        for (uint32_t j = 0; j < nb; j++) {
+            float sim = qo_similarity_f32(distance, a + (size_t)i * dim, b + (size_t)j * dim, dim);
+            if (sim > max_sim) max_sim = sim;
+        }
+        sum += max_sim;
+    }
+    return sum;
+}
+/* the same fold over precomputed similarities (quantized storages): sims[q * stride + row], point p = rows [off[p], off[p+1]) */
+API void qo_maxsim_fold(const float* sims, uint64_t stride, uint32_t n_query, const uint32_t* off, uint64_t n_points, float* out) {
+    for (uint64_t p = 0; p < n_points; p++) {
+        float sum = 0.0f;
+        for (uint32_t q = 0; q < n_query; q++) {
+            float max_sim = -INFINITY;
+            for (uint32_t r = off[p]; r < off[p + 1]; r++) { float sim = sims[(uint64_t)q * stride + r]; if (sim > max_sim) max_sim = sim; }
+            sum += max_sim;
+        }
+        out[p] = sum;
+    }
+}

@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
             fn = getattr(L, f"qo_cosine_preprocess_{tier}")
             fn.restype, fn.argtypes = None, [f32p, f32p, C.c_size_t]
         L.qo_similarity_f32.restype, L.qo_similarity_f32.argtypes = C.c_float, [C.c_int, f32p, f32p, C.c_size_t]
+        L.qo_maxsim_f32.restype, L.qo_maxsim_f32.argtypes = C.c_float, [C.c_int, f32p, C.c_uint32, f32p, C.c_uint32, C.c_uint32]
+        L.qo_maxsim_fold.restype, L.qo_maxsim_fold.argtypes = None, [f32p, C.c_uint64, C.c_uint32, u32p, C.c_uint64, f32p]
         L.qo_fast_sigmoid.restype, L.qo_fast_sigmoid.argtypes = C.c_float, [C.c_float]
         L.qo_scaled_fast_sigmoid.restype, L.qo_scaled_fast_sigmoid.argtypes = C.c_float, [C.c_float]
         L.qo_custom_score.restype, L.qo_custom_score.argtypes = C.c_float, [C.c_int, C.c_uint32, C.c_uint32, f32p, C.c_uint64]
@@ -534,4 +536,21 @@ def custom_combine(kind: int, n_a: int, n_b: int, sims) -> np.ndarray:
     assert sims.ndim == 2 and sims.shape[0] == custom_examples(kind, n_a, n_b)
     out = np.empty(sims.shape[1], dtype=np.float32)
     lib().qo_custom_combine(kind, n_a, n_b, _p(sims, C.c_float), sims.shape[1], sims.shape[1], _p(out, C.c_float))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ multivector MaxSim
+def maxsim_f32(distance: int, a_pre, b_pre) -> np.float32:
+    """score_max_similarity(query vectors a, stored vectors b), both [n, dim] and already preprocessed."""
+    a, b = np.atleast_2d(_f32(a_pre)), np.atleast_2d(_f32(b_pre))
+    assert a.shape[1] == b.shape[1]
+    return np.float32(lib().qo_maxsim_f32(distance, _p(a, C.c_float), a.shape[0], _p(b, C.c_float), b.shape[0], a.shape[1]))
+
+
+def maxsim_fold(sims, offsets) -> np.ndarray:
+    """sims: [query vectors, rows]; offsets: n_points + 1 row offsets -> per-point MaxSim scores."""
+    sims = np.ascontiguousarray(_f32(sims))
+    off = np.ascontiguousarray(offsets, dtype=np.uint32)
+    out = np.empty(off.size - 1, dtype=np.float32)
+    lib().qo_maxsim_fold(_p(sims, C.c_float), sims.shape[1], sims.shape[0], _p(off, C.c_uint32), off.size - 1, _p(out, C.c_float))
     return out

@@ -63,6 +63,8 @@ SIGNATURES = {
     "qb_bq_row_bytes": (C.c_uint32, [C.c_uint32, C.c_int]),
     "qb_bq_encode_rows_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_int, f32p, vp, vp]),
     "qb_pq_encode_rows_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint64, vp, C.c_uint64, vp, vp]),
+    "qb_search_maxsim": (C.c_int32, [vp, u32p, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
+    "qb_score_maxsim": (C.c_int32, [vp, u32p, C.c_uint32, f32p, C.c_uint32, u32p, C.c_size_t, f32p]),
     "qb_rescore": (C.c_int32, [vp, u32p, C.c_size_t, C.c_uint32, C.POINTER(ScoredPoint), u32p]),
     "qb_storage_set_id_base": (C.c_int32, [vp, C.c_uint32]),
     "qb_topk_merge_device": (C.c_int32, [C.c_int32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]),

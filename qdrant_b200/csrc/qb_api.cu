@@ -39,6 +39,8 @@ uint32_t qb_custom_examples(int kind, uint32_t n_a, uint32_t n_b);
 qb_status qb_launch_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* d_sims, uint64_t stride, uint64_t n, float* d_scores, const uint32_t* d_ids,
                                    const QbEmit* emit, cudaStream_t stream);
 qb_status qb_launch_iota(uint32_t* d, uint64_t n, cudaStream_t stream);
+qb_status qb_launch_maxsim_fold(const float* d_sims, uint64_t stride, uint32_t n_query_tokens, const uint32_t* d_row_offsets, const uint32_t* d_point_ids,
+                                uint64_t n_points, float* d_scores, const QbEmit* emit, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -923,6 +925,115 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
     memcpy(out_count, hs + raw_bytes + res_bytes, 4);
     if (counters) counters->cpu += n * (uint64_t)ne * cpu_units_per_point(s);
     return QB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multivector MaxSim
+// Shared body of qb_search_maxsim / qb_score_maxsim.  point_ids = null: every point (search); else the listed points (scores).
+static qb_status maxsim_run(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, const float* query_tokens, uint32_t nqt, const uint32_t* point_ids,
+                            uint64_t n_sel, const uint64_t* deleted_points, uint32_t top, qb_scored_point* out, uint32_t* out_count, float* scores,
+                            qb_hw_counters* counters) {
+    QB_CHECK(s && point_offsets && query_tokens, QB_ERR_INVALID, "maxsim: null argument");
+    QB_CHECK(nqt >= 1 && nqt <= 4096, QB_ERR_INVALID, "maxsim: %u query vectors (need 1..4096)", nqt);
+    for (uint32_t p = 0; p < n_points; ++p) QB_CHECK(point_offsets[p] <= point_offsets[p + 1], QB_ERR_INVALID, "maxsim: point_offsets not ascending at %u", p);
+    QB_CHECK(n_points == 0 || point_offsets[n_points] <= s->count, QB_ERR_INVALID, "maxsim: point_offsets end %u beyond the %llu stored vectors",
+             n_points ? point_offsets[n_points] : 0u, (unsigned long long)s->count);
+    const uint64_t n_pts = point_ids ? n_sel : n_points;
+    if (n_pts == 0) return QB_OK;
+    // rows to score and, per selected point, its column range in the similarity matrix
+    std::vector<uint32_t> h_off(n_pts + 1), h_rows;
+    uint64_t n_rows;
+    if (point_ids) {
+        uint64_t acc = 0;
+        for (uint64_t i = 0; i < n_pts; ++i) {
+            QB_CHECK(point_ids[i] < n_points, QB_ERR_INVALID, "maxsim: point id %u out of range", point_ids[i]);
+            h_off[i] = (uint32_t)acc;
+            for (uint32_t r = point_offsets[point_ids[i]]; r < point_offsets[point_ids[i] + 1]; ++r) h_rows.push_back(r);
+            acc = h_rows.size();
+        }
+        h_off[n_pts] = (uint32_t)acc;
+        n_rows = acc;
+    } else {
+        for (uint64_t i = 0; i <= n_pts; ++i) h_off[i] = point_offsets[i];
+        n_rows = point_offsets[n_points];
+    }
+    QB_CHECK(n_rows * (4ull * nqt + 4) + n_pts * 20 <= (16ull << 30), QB_ERR_UNSUPPORTED, "maxsim: %llu vectors x %u query vectors exceed the 16 GB scratch budget",
+             (unsigned long long)n_rows, nqt);
+    QB_TRY(use_device(s->device));
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_acquire(s, &c));
+    struct Rel { qb_storage* s; QbSearchCtx* c; ~Rel() { qb_ctx_release(s, c); } } rel{s, c};
+    cudaStream_t stream = c->stream;
+    const size_t raw_bytes = (size_t)nqt * s->dim * 4;
+    const size_t res_bytes = scores ? (size_t)n_pts * 4 : (size_t)top * sizeof(qb_scored_point);
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + 16));
+    uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
+    memcpy(hs, query_tokens, raw_bytes);
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, round_up_u64(raw_bytes, 16) + (size_t)nqt * pre_stride_f(s) * 4));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)nqt + 256) * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)nqt));
+    QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)std::max<uint64_t>(n_rows, 1)));
+    // scratch: [similarities nqt x n_rows][column offsets n_pts + 1][point ids n_pts][scores n_pts]
+    const size_t sims_bytes = round_up_u64((size_t)nqt * n_rows * 4, 256), off_bytes = round_up_u64((n_pts + 1) * 4, 256), pid_bytes = round_up_u64(n_pts * 4, 256);
+    QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, sims_bytes + off_bytes + pid_bytes + n_pts * 4 + 256));
+    uint8_t* sc = reinterpret_cast<uint8_t*>(c->d_mma);
+    float* d_sims = reinterpret_cast<float*>(sc);
+    uint32_t* d_off = reinterpret_cast<uint32_t*>(sc + sims_bytes);
+    uint32_t* d_pid = reinterpret_cast<uint32_t*>(sc + sims_bytes + off_bytes);
+    float* d_scores = reinterpret_cast<float*>(sc + sims_bytes + off_bytes + pid_bytes);
+    QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
+    QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), nqt,
+                           reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + round_up_u64(raw_bytes, 16)), c->d_queries_enc, c->d_q_off, stream));
+    QB_CUDA(cudaMemcpyAsync(d_off, h_off.data(), (n_pts + 1) * 4, cudaMemcpyHostToDevice, stream));
+    if (point_ids) {
+        QB_CUDA(cudaMemcpyAsync(d_pid, point_ids, n_pts * 4, cudaMemcpyHostToDevice, stream));
+        if (n_rows) QB_CUDA(cudaMemcpyAsync(c->d_ids, h_rows.data(), n_rows * 4, cudaMemcpyHostToDevice, stream));
+    } else {
+        QB_TRY(qb_launch_iota(c->d_ids, n_rows, stream));
+    }
+    for (uint32_t e = 0; e < nqt && n_rows; ++e) QB_TRY(launch_example(s, c->d_queries_enc, c->d_q_off, e, false, c->d_ids, n_rows, d_sims + (size_t)e * n_rows, stream));
+    if (scores) {
+        QB_TRY(qb_launch_maxsim_fold(d_sims, n_rows, nqt, d_off, nullptr, n_pts, d_scores, nullptr, stream));
+        QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, d_scores, n_pts * 4, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaStreamSynchronize(stream));  // also orders the reads of h_off / h_rows / point_ids before they go out of scope
+        memcpy(scores, hs + raw_bytes, n_pts * 4);
+    } else {
+        const uint32_t* d_del2 = nullptr;
+        if (deleted_points) {
+            const size_t words64 = (size_t)ceil_div_u64(n_points, 64);
+            QB_TRY(ensure_dev_elems(&c->d_deleted2, &c->deleted2_words, words64 * 2));
+            QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_points, words64 * 8, cudaMemcpyHostToDevice, stream));
+            d_del2 = c->d_deleted2;
+        }
+        QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)n_pts));
+        QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)top));
+        QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)8));
+        QbEmit emit{};
+        emit.cand = c->d_cand; emit.cap = n_pts; emit.dense = 1; emit.dense_base = 0; emit.deleted = nullptr; emit.deleted2 = d_del2; emit.id_base = 0;
+        QB_TRY(qb_launch_maxsim_fold(d_sims, n_rows, nqt, d_off, nullptr, n_pts, nullptr, &emit, stream));
+        QB_TRY(qb_launch_select(c->d_cand, nullptr, n_pts, n_pts, 1, top, 0, c->d_out, c->d_out_counts, nullptr, nullptr, stream));
+        QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaMemcpyAsync(hs + raw_bytes + res_bytes, c->d_out_counts, 4, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaStreamSynchronize(stream));
+        memcpy(out, hs + raw_bytes, res_bytes);
+        memcpy(out_count, hs + raw_bytes + res_bytes, 4);
+    }
+    if (counters) counters->cpu += n_rows * (uint64_t)nqt * cpu_units_per_point(s);
+    return QB_OK;
+}
+
+extern "C" qb_status qb_search_maxsim(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, const float* query_vectors, uint32_t n_query_vectors,
+                                      uint32_t top, const uint64_t* deleted_points, qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters) {
+    QB_CHECK(out && out_count, QB_ERR_INVALID, "search_maxsim: null output");
+    QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "search_maxsim: top %u outside [1,%u]", top, QB_MAX_TOP);
+    *out_count = 0;
+    return maxsim_run(s, point_offsets, n_points, query_vectors, n_query_vectors, nullptr, 0, deleted_points, top, out, out_count, nullptr, counters);
+}
+
+extern "C" qb_status qb_score_maxsim(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, const float* query_vectors, uint32_t n_query_vectors,
+                                     const uint32_t* point_ids, size_t n, float* scores) {
+    QB_CHECK(n == 0 || (point_ids && scores), QB_ERR_INVALID, "score_maxsim: null argument");
+    if (n == 0) return QB_OK;
+    return maxsim_run(s, point_offsets, n_points, query_vectors, n_query_vectors, point_ids, n, nullptr, 0, nullptr, nullptr, scores, nullptr);
 }
 
 extern "C" void qb_scorer_destroy(qb_scorer* sc) {

@@ -517,6 +517,42 @@ def postprocess_search_result(search_result: np.ndarray, original: DenseVectorSt
     return out[: n.value].copy()
 
 
+# ------------------------------------------------------------------------------------------------ multivectors
+class MultiVectorView:
+    """A multivector collection over a token-level storage: point p = rows [offsets[p], offsets[p+1]) (the flattened layout of
+    vector_storage/multi_dense).  Scores are ColBERT MaxSim (score_max_similarity, query_scorer/mod.rs:77-98)."""
+
+    def __init__(self, storage: _Storage, offsets):
+        self.storage = storage
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        assert self.offsets.ndim == 1 and self.offsets.size >= 1
+        self.n_points = self.offsets.size - 1
+
+    def _query(self, query_vectors) -> np.ndarray:
+        q = np.atleast_2d(_f32(query_vectors))
+        if q.shape[1] != self.storage.dim:
+            raise ValueError(f"query vectors have dim {q.shape[1]}, storage has {self.storage.dim}")
+        return np.ascontiguousarray(q)
+
+    def search(self, query_vectors, top: int, point_deleted=None, counters: Optional[HwCounters] = None) -> np.ndarray:
+        q = self._query(query_vectors)
+        out = np.zeros(max(top, 1), dtype=SCORED_POINT_OFFSET)
+        count = C.c_uint32()
+        bm = _bitmap(point_deleted, self.n_points)
+        check(lib().qb_search_maxsim(self.storage._h, self.offsets.ctypes.data_as(u32p), self.n_points, q.ctypes.data_as(f32p), q.shape[0], int(top),
+                                     None if bm is None else bm.ctypes.data_as(u64p), out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(count),
+                                     None if counters is None else C.byref(counters)))
+        return out[: count.value].copy()
+
+    def score_points(self, query_vectors, points: Sequence[int]) -> np.ndarray:
+        q = self._query(query_vectors)
+        ids = _ids(points)
+        scores = np.empty(ids.size, dtype=np.float32)
+        check(lib().qb_score_maxsim(self.storage._h, self.offsets.ctypes.data_as(u32p), self.n_points, q.ctypes.data_as(f32p), q.shape[0],
+                                    ids.ctypes.data_as(u32p), ids.size, scores.ctypes.data_as(f32p)))
+        return scores
+
+
 # ------------------------------------------------------------------------------------------------ quantizer encode on the device
 # Thin wrappers over the C ABI (include/qb200.h, "quantizer encode on the device"): every pointer is a raw device address.
 def sq8_multiplier(alpha: float, distance: Distance) -> np.float32:

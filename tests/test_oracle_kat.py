@@ -248,3 +248,15 @@ def test_reco_sum_scores(oracle):
     m = np.stack([sims, sims[::-1]], axis=1)  # two candidates
     out = oracle.custom_combine(oracle.RECO_SUM_SCORES, 2, 2, m)
     assert out[0] == np.float32(want) and out.shape == (2,)
+
+
+def test_maxsim_reference_kat(oracle):
+    """query_scorer/mod.rs:168-184 test_score_multi_euclidean: score(a, a) == -0.0 and score(a, b) == -19."""
+    a = np.array([[1.0, 2.0, 3.0], [3.0, 3.0, 3.0], [4.0, 5.0, 6.0]], np.float32)
+    b = np.array([[3.0, 3.0, 3.0], [4.0, 2.0, 1.0]], np.float32)
+    assert oracle.maxsim_f32(oracle.EUCLID, a, a) == np.float32(-0.0)
+    assert oracle.maxsim_f32(oracle.EUCLID, a, b) == np.float32(-19.0)
+    # the fold over a precomputed similarity matrix agrees with the direct form
+    rows = np.concatenate([a, b])
+    sims = np.stack([oracle.score_rows_f32(oracle.EUCLID, rows, q) for q in a])
+    np.testing.assert_array_equal(oracle.maxsim_fold(sims, [0, 3, 5]), np.array([-0.0, -19.0], np.float32))
