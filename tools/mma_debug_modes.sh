@@ -1,5 +1,8 @@
+# Timing experiments on the batched SQ8 tensor-core kernel (qb_sq8_mma.cu): kernel time of the main pass over 4M x 768 codes x 1024
+# queries with QB_MMA_DEBUG = 0 (normal), 1 (epilogue skipped), 4 (prefilter never passes), for cta_group::1 and ::2.
+# Results with a non-zero debug mode are INVALID as search results; this is a profiling aid (see profiles/README_r01.md).
 mkdir -p gpurun_out
-for mode in 0 4; do for cta in 1 2; do
+for mode in 0 1 4; do for cta in 1 2; do
   if [ $cta = 1 ]; then export QB_MMA_1CTA=1; else unset QB_MMA_1CTA; fi
   QB_MMA_DEBUG=$mode timeout 300 python - <<'PY'
 import os, sys, json, time
