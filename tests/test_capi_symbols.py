@@ -68,3 +68,22 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.replace("test_product_does_not_import_oracle", ""), f"{f} mentions oracle"
+
+
+def test_custom_query_flat_layouts():
+    """Host-side mirrors of RecoQuery / DiscoverQuery / ContextQuery flatten their vectors in the order qb_scorer_create_custom
+    documents (include/qb200.h) — the same order the reference's flat_iter() yields (reco_query.rs:26-28, discover_query.rs:38-42,
+    context_query.rs:94-96)."""
+    import numpy as np
+
+    from qdrant_b200 import scorer as qb
+
+    v = [np.full(4, i, np.float32) for i in range(7)]
+    vecs, n_a, n_b = qb.RecoBestScoreQuery(qb.RecoQuery([v[0], v[1]], [v[2]])).flat()
+    assert (n_a, n_b) == (2, 1) and [int(x[0]) for x in vecs] == [0, 1, 2]
+    assert qb.RecoSumScoresQuery(qb.RecoQuery([], [v[3]])).flat()[1:] == (0, 1)
+    vecs, n_a, n_b = qb.DiscoverQuery(v[6], [qb.ContextPair(v[0], v[1]), qb.ContextPair(v[2], v[3])]).flat()
+    assert (n_a, n_b) == (2, 0) and [int(x[0]) for x in vecs] == [6, 0, 1, 2, 3]
+    vecs, n_a, n_b = qb.ContextQuery([qb.ContextPair(v[4], v[5])]).flat()
+    assert (n_a, n_b) == (1, 0) and [int(x[0]) for x in vecs] == [4, 5]
+    assert int(qb.RecoBestScoreQuery.kind) == 1 and int(qb.RecoSumScoresQuery.kind) == 2 and int(qb.DiscoverQuery.kind) == 3 and int(qb.ContextQuery.kind) == 4
