@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QB200_ABI_VERSION 1
+#define QB200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define QB_API __attribute__((visibility("default")))
 #else
@@ -76,6 +76,9 @@ QB_API int32_t qb_abi_version(void);
 QB_API qb_status qb_device_count(int32_t* out);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 QB_API uint64_t qb_kernel_launch_count(void);
+/* Debugging / experiment switches (README.md lists them); the QB_* environment variables of the same names are read once,
+ * at first use, as defaults.  Not needed for normal operation. */
+QB_API qb_status qb_set_option(const char* name, int64_t value);
 
 /* ---------------------------------------------------------------- storages -------------------------- */
 /* Dense vectors as the reference stores them: row-major, `dim` elements of `dt`, rows `row_stride_bytes`
@@ -116,7 +119,13 @@ QB_API qb_status qb_storage_info(const qb_storage* s, uint32_t* dim, uint64_t* c
 /* Resident soft-delete flags (bit i = 1 => point i deleted): the storage-level `deleted` BitSlice that
  * ScorerFilters / not_deleted_checker consult (point_scorer.rs:351-352).  NULL clears. */
 QB_API qb_status qb_storage_set_deleted(qb_storage* s, const uint64_t* bitmap_words, uint64_t n_words);
-/* CUDA stream (cudaStream_t) the storage's default search context launches on — for event timing */
+/* VectorStorage::is_on_disk of the segment storage this HBM copy caches: decides whether scoring calls meter
+ * hardware_counter.vector_io_read (dim * size_of::<TElement>() per scored point for on-disk dense storages,
+ * metric_query_scorer.rs:44-48; the quantized row size for on-disk quantized data, quantized_query_scorer.rs:48,84-86).
+ * Default 0 (RAM storage: multiplier 0). */
+QB_API qb_status qb_storage_set_on_disk(qb_storage* s, int32_t on_disk);
+/* CUDA stream (cudaStream_t) of the storage's device-resident entry points (qb_search_batch_device,
+ * qb_hnsw_search_batch_device) — for event timing and stream ordering; host-facing searches use pooled streams of their own */
 QB_API void* qb_storage_stream(qb_storage* s);
 
 /* Metric::preprocess for `n` vectors (spaces/metric.rs:14; cosine = cosine_preprocess_avx arithmetic,
@@ -148,7 +157,8 @@ QB_API qb_status qb_scorer_take_counters(qb_scorer* sc, qb_hw_counters* out);
 /* BatchFilteredSearcher::{new, peek_top_iter} fused: scores every candidate point against every query and
  * keeps the `top` best per query, sorted by descending score (FixedLengthPriorityQueue::into_sorted_vec).
  *   queries        n_queries x dim raw f32 (preprocessed + encoded on the device)
- *   deleted_bitmap optional per-call soft-delete bits (bit=1 deleted), OR-ed with the resident flags
+ *   deleted_bitmap optional per-call soft-delete bits (bit=1 deleted), OR-ed with the resident flags; the caller
+ *                  provides ceil(count / 64) 64-bit words (the library reads exactly that many)
  *   id_list/n_ids  optional explicit candidate ids (a payload filter's result); NULL = all rows
  *   is_stopped     optional cancellation flag, polled between kernel launches
  *   out            n_queries x top; out_counts[q] = number of valid entries (< top when fewer candidates)
@@ -222,7 +232,9 @@ QB_API qb_status qb_rescore(qb_scorer* orig, const uint32_t* ids, size_t n, uint
 
 /* ---------------------------------------------------------------- sharded segments (multi-GPU) ------- */
 /* Rows of a sharded data set live on several GPUs (one process per GPU); ids reported by searches on this shard
- * are `local row + id_base`. */
+ * are `local row + id_base`, and every id-taking entry point (qb_score_points, qb_score_internal, qb_scorer_create_internal,
+ * qb_rescore, qb_storage_read_rows, the id_list of qb_search_batch / qb_search_custom) takes ids in that same numbering,
+ * i.e. id_base <= id < id_base + count.  Bitmaps (deleted flags) stay indexed by local row. */
 QB_API qb_status qb_storage_set_id_base(qb_storage* s, uint32_t id_base);
 /* BatchResultAggregator (lib/shard/src/search_result_aggregator.rs:50-117) on the device: merge `n_lists` per-shard
  * top-k lists per query — as all-gathered over NVLink by the caller: dev_lists[n_lists][n_queries][top],
@@ -232,7 +244,46 @@ QB_API qb_status qb_topk_merge_device(int32_t device, const qb_scored_point* dev
                                       uint32_t n_queries, uint32_t top, qb_scored_point* dev_out, uint32_t* dev_out_counts,
                                       void* dev_scratch, uint64_t scratch_bytes, void* stream);
 
+/* ---------------------------------------------------------------- HNSW graph search on the device ---- */
+/* GraphLayers::search (lib/segment/src/index/hnsw_index/graph_layers.rs:530-561) for a BATCH of queries with the
+ * traversal itself on the GPU: search_entry (greedy descent through the upper levels, :247-316) and search_on_level
+ * (beam search on level 0 with SearchContext, :108-148, search_context.rs:8-41), every hop scored with the storage's
+ * bit-exact per-pair arithmetic.  This is the throughput form of `RawScorer` under HNSW: the per-hop qb_score_points
+ * boundary stays available (qb_scorer_*), this entry removes it.
+ *
+ * links_bin = the bytes of the segment's `links.bin` in GraphLinksFormat::Plain (graph_links/header.rs:9-20,
+ * graph_links/view.rs:121-135): HeaderPlain, level offsets, reindex, neighbors, padding, offsets.  (The compressed
+ * formats are decoded by the caller, as GraphLinks::to_edges does.)  m / m0 = HnswM (hnsw_index/mod.rs:34-40), both <= 64.
+ * The graph is bound to `s` (dense f32 or SQ8; the quantized storage when the segment searches quantized) and must
+ * outlive neither it nor its searches. */
+typedef struct qb_hnsw qb_hnsw;
+QB_API qb_status qb_hnsw_create_plain(qb_storage* s, const uint8_t* links_bin, uint64_t n_bytes, uint32_t m, uint32_t m0, qb_hnsw** out);
+QB_API void qb_hnsw_destroy(qb_hnsw* g);
+QB_API qb_status qb_hnsw_info(const qb_hnsw* g, uint32_t* n_points, uint32_t* levels, uint64_t* hbm_bytes);
+/*   queries         n_queries x dim raw f32 (Metric::preprocess + encode_query on the device)
+ *   ef              beam width; max(ef, top) is used (graph_layers.rs:551)
+ *   entry_point / entry_level   GraphLayers::get_entry_point's answer (entry_points.rs; it depends on the filter, so the
+ *                   host passes it per call)
+ *   deleted_bitmap  optional filter (bit = 1: point fails ScorerFilters::check_vector), OR-ed with the resident flags;
+ *                   filtered-out links are neither scored nor traversed (point_scorer.rs:270-277)
+ *   out             n_queries x top, descending; out_counts[q] valid entries
+ * Result lists equal the reference traversal's whenever scores are distinct (ties are ordered by id). */
+QB_API qb_status qb_hnsw_search_batch(qb_hnsw* g, const float* queries, uint32_t n_queries, uint32_t top, uint32_t ef, uint32_t entry_point,
+                                      uint32_t entry_level, const uint64_t* deleted_bitmap, const volatile int32_t* is_stopped,
+                                      qb_scored_point* out, uint32_t* out_counts, qb_hw_counters* counters /* optional */);
+/* same with queries / outputs resident in HBM, enqueued on qb_storage_stream(s); no host synchronisation */
+QB_API qb_status qb_hnsw_search_batch_device(qb_hnsw* g, const float* dev_queries, uint32_t n_queries, uint32_t top, uint32_t ef, uint32_t entry_point,
+                                             uint32_t entry_level, qb_scored_point* dev_out, uint32_t* dev_counts);
+/* scorer calls (hops) and scored points since the last reset, summed over all searches on this graph (waits for them) */
+QB_API qb_status qb_hnsw_stats(qb_hnsw* g, uint64_t* hops, uint64_t* scored_points, int32_t reset);
+
 /* ---------------------------------------------------------------- profiling hooks ------------------- */
+/* Fused searches run a fast path first and rerun without it when the device reports that one of its assumptions did not
+ * hold (candidate buffer overflow, a dot product outside the f32-exact window, a survivor segment full).  searches =
+ * fused search calls on this storage, reruns = extra passes they needed: a benchmark or test that claims the fast path
+ * asserts reruns == 0. */
+QB_API qb_status qb_search_stats(qb_storage* s, uint64_t* searches, uint64_t* reruns, int32_t reset);
+
 /* When enabled, the dominant scan kernel of every search on this storage is bracketed by CUDA events on its
  * launch stream; qb_profile_read returns the number of bracketed launches and their summed duration. */
 QB_API qb_status qb_profile_enable(qb_storage* s, int32_t on);

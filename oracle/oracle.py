@@ -30,7 +30,7 @@ SCORED = np.dtype([("idx", np.uint32), ("score", np.float32)])  # #[repr(C)] Sco
 
 def ensure_built() -> None:
     so = os.path.join(_HERE, "liboracle.so")
-    need = not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "hnsw.c"))
+    need = not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "hnsw.c", "mt.c"))
     need_ref = not os.path.exists(os.path.join(_HERE, "_ref", "libsimd_utils.so")) and os.path.isdir(
         "/root/reference/lib/quantization/cpp"
     )
@@ -123,6 +123,21 @@ def lib() -> C.CDLL:
         L.qo_hnsw_search.argtypes = [C.c_void_p, f32p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.qo_hnsw_stats.restype, L.qo_hnsw_stats.argtypes = None, [C.c_void_p, u64p, u64p, C.c_int]
         L.qo_hnsw_free.restype, L.qo_hnsw_free.argtypes = None, [C.c_void_p]
+        L.qo_hnsw_build_mt.restype = C.c_void_p
+        L.qo_hnsw_build_mt.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32]
+        L.qo_hnsw_search_batch.restype = None
+        L.qo_hnsw_search_batch.argtypes = [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_uint32, C.c_void_p, u32p]
+        L.qo_hnsw_entry.restype, L.qo_hnsw_entry.argtypes = None, [C.c_void_p, u32p, u32p, u32p, u32p]
+        L.qo_hnsw_export_plain.restype, L.qo_hnsw_export_plain.argtypes = C.c_uint64, [C.c_void_p, C.c_void_p]
+        L.qo_pool_create.restype, L.qo_pool_create.argtypes = C.c_void_p, [C.c_uint32]
+        L.qo_pool_destroy.restype, L.qo_pool_destroy.argtypes = None, [C.c_void_p]
+        L.qo_pool_threads.restype, L.qo_pool_threads.argtypes = C.c_uint32, [C.c_void_p]
+        L.qo_pool_load_f32.restype, L.qo_pool_load_f32.argtypes = C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_uint64, f32p]
+        L.qo_pool_scan_f32.restype, L.qo_pool_scan_f32.argtypes = None, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_void_p, u32p]
+        L.qo_pool_scan_sq8.restype = None
+        L.qo_pool_scan_sq8.argtypes = [C.c_void_p, mp, u8p, C.c_uint64, u8p, f32p, C.c_uint32, C.c_uint32, C.c_void_p, u32p]
+        L.qo_pool_scan_pq.restype = None
+        L.qo_pool_scan_pq.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_void_p, u32p]
         _LIB = L
     return _LIB
 
@@ -478,10 +493,35 @@ class HNSW:
     """From-spec CPU HNSW (oracle/hnsw.c): graph built with CPU scoring; search() drives the traversal either with the
     CPU oracle scorer (score_points=None) or with any callable ids -> scores (e.g. a GPU RawScorer.score_points)."""
 
-    def __init__(self, base, distance: int, m: int = 16, ef_construct: int = 100, seed: int = 42):
+    def __init__(self, base, distance: int, m: int = 16, ef_construct: int = 100, seed: int = 42, threads: int = 1):
+        """threads > 1: the first 256 points serially, the rest on `threads` workers with per-point link locks (like the
+        reference's builder, hnsw/build.rs:285-355); such graphs are not deterministic."""
         self.base = _f32(base)
         self.distance = distance
-        self._h = lib().qo_hnsw_build(_p(self.base, C.c_float), self.base.shape[0], self.base.shape[1], distance, m, ef_construct, seed)
+        self._h = lib().qo_hnsw_build_mt(_p(self.base, C.c_float), self.base.shape[0], self.base.shape[1], distance, m, ef_construct, seed, threads)
+
+    def entry(self):
+        """(entry point, its level, m, m0)"""
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().qo_hnsw_entry(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return int(a.value), int(b.value), int(c.value), int(d.value)
+
+    def export_plain(self) -> np.ndarray:
+        """bytes of the reference's plain `links.bin` (graph_links/serializer.rs, GraphLinksFormat::Plain)"""
+        n = int(lib().qo_hnsw_export_plain(self._h, None))
+        out = np.zeros(n, dtype=np.uint8)
+        lib().qo_hnsw_export_plain(self._h, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def search_batch(self, queries_pre, top: int, ef: int, deleted=None, threads: int = 1):
+        """CPU-scored searches, one per thread at a time; returns a list of SCORED arrays."""
+        q = np.ascontiguousarray(np.atleast_2d(_f32(queries_pre)))
+        nq = q.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED)
+        counts = np.zeros(nq, dtype=np.uint32)
+        keep, dp = _bitmap_ptr(deleted)
+        lib().qo_hnsw_search_batch(self._h, _p(q, C.c_float), nq, top, ef, dp, threads, out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
 
     def search(self, query_pre, top: int, ef: int, score_points=None) -> np.ndarray:
         q = _f32(query_pre)
@@ -554,3 +594,48 @@ def maxsim_fold(sims, offsets) -> np.ndarray:
     out = np.empty(off.size - 1, dtype=np.float32)
     lib().qo_maxsim_fold(_p(sims, C.c_float), sims.shape[1], sims.shape[0], _p(off, C.c_uint32), off.size - 1, _p(out, C.c_float))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ many-core CPU arm (oracle/mt.c)
+class CpuPool:
+    """T pinned threads; each owns (allocates, first-touches, scans) one contiguous segment — one blocking task per segment
+    like the reference's SegmentsSearcher — with a T-way host merge.  bench.py's cpu_baseline / --impl reference legs."""
+
+    def __init__(self, threads: int | None = None):
+        self.threads = threads or (os.cpu_count() or 1)
+        self._p = lib().qo_pool_create(self.threads)
+
+    def load_f32(self, rows: int, dim: int, distance: int, seed: int = 42, src=None):
+        """src = None: seeded standard-normal rows, Metric::preprocess applied, generated by the owning threads."""
+        if src is not None:
+            src = np.ascontiguousarray(_f32(src)); assert src.shape == (rows, dim)
+        rc = lib().qo_pool_load_f32(self._p, rows, dim, distance, seed, None if src is None else _p(src, C.c_float))
+        if rc != 0:
+            raise MemoryError("CpuPool.load_f32: mmap failed")
+        self.rows, self.dim = rows, dim
+
+    def scan_f32(self, queries_pre, top: int):
+        q = np.ascontiguousarray(np.atleast_2d(_f32(queries_pre)))
+        nq = q.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED); counts = np.zeros(nq, dtype=np.uint32)
+        lib().qo_pool_scan_f32(self._p, _p(q, C.c_float), nq, top, out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
+
+    def scan_sq8(self, meta: SQ8Meta, rows: np.ndarray, q_codes: np.ndarray, q_offs: np.ndarray, top: int):
+        nq = q_codes.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED); counts = np.zeros(nq, dtype=np.uint32)
+        lib().qo_pool_scan_sq8(self._p, C.byref(meta), _p(rows, C.c_uint8), rows.shape[0], _p(q_codes, C.c_uint8), _p(q_offs, C.c_float), nq, top,
+                               out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
+
+    def scan_pq(self, codes: np.ndarray, n_centroids: int, luts: np.ndarray, top: int):
+        nq = luts.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED); counts = np.zeros(nq, dtype=np.uint32)
+        lib().qo_pool_scan_pq(self._p, _p(codes, C.c_uint8), codes.shape[0], codes.shape[1], n_centroids, _p(luts, C.c_float), nq, top,
+                              out.ctypes.data_as(C.c_void_p), _p(counts, C.c_uint32))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
+
+    def close(self):
+        if self._p:
+            lib().qo_pool_destroy(self._p)
+            self._p = None

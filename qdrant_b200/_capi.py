@@ -68,6 +68,16 @@ SIGNATURES = {
     "qb_rescore": (C.c_int32, [vp, u32p, C.c_size_t, C.c_uint32, C.POINTER(ScoredPoint), u32p]),
     "qb_storage_set_id_base": (C.c_int32, [vp, C.c_uint32]),
     "qb_topk_merge_device": (C.c_int32, [C.c_int32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]),
+    "qb_set_option": (C.c_int32, [C.c_char_p, C.c_int64]),
+    "qb_storage_set_on_disk": (C.c_int32, [vp, C.c_int32]),
+    "qb_search_stats": (C.c_int32, [vp, u64p, u64p, C.c_int32]),
+    "qb_hnsw_create_plain": (C.c_int32, [vp, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "qb_hnsw_destroy": (None, [vp]),
+    "qb_hnsw_info": (C.c_int32, [vp, u32p, u32p, u64p]),
+    "qb_hnsw_search_batch": (C.c_int32, [vp, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u64p, i32p, C.POINTER(ScoredPoint), u32p,
+                                         C.POINTER(HwCounters)]),
+    "qb_hnsw_search_batch_device": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]),
+    "qb_hnsw_stats": (C.c_int32, [vp, u64p, u64p, C.c_int32]),
     "qb_profile_enable": (C.c_int32, [vp, C.c_int32]),
     "qb_profile_read": (C.c_int32, [vp, u64p, C.POINTER(C.c_double), C.c_int32]),
 }

@@ -46,6 +46,41 @@ qb_status qb_launch_maxsim_fold(const float* d_sims, uint64_t stride, uint32_t n
 static thread_local char g_err[1024] = "";
 std::atomic<uint64_t> g_qb_launches{0};
 
+// Process-wide switches (debugging / experiments).  The environment is read ONCE, at first use; qb_set_option changes a
+// switch at run time.  Nothing on a search path calls getenv.
+QbOptions& qb_opt() {
+    static QbOptions o = [] {
+        QbOptions v;
+        auto num = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? strtoll(e, nullptr, 10) : dflt; };
+        v.disable_localk = getenv("QB_DISABLE_LOCALK") != nullptr;
+        v.disable_mma = getenv("QB_DISABLE_MMA") != nullptr;
+        v.mma_1cta = getenv("QB_MMA_1CTA") != nullptr;
+        v.mma_no_segments = getenv("QB_MMA_NO_SEGMENTS") != nullptr;
+        v.mma_debug = (int)num("QB_MMA_DEBUG", 0);
+        v.sample_rows = (uint64_t)num("QB_SAMPLE_ROWS", 0);
+        v.verbose = getenv("QB_VERBOSE") != nullptr;
+        v.pq_queries_per_pass = (int)num("QB_PQ_QUERIES", 0);
+        return v;
+    }();
+    return o;
+}
+
+extern "C" qb_status qb_set_option(const char* name, int64_t value) {
+    QB_CHECK(name, QB_ERR_INVALID, "set_option: null name");
+    QbOptions& o = qb_opt();
+    const std::string n(name);
+    if (n == "disable_localk") o.disable_localk = value != 0;
+    else if (n == "disable_mma") o.disable_mma = value != 0;
+    else if (n == "mma_1cta") o.mma_1cta = value != 0;
+    else if (n == "mma_no_segments") o.mma_no_segments = value != 0;
+    else if (n == "mma_debug") o.mma_debug = (int)value;
+    else if (n == "sample_rows") o.sample_rows = (uint64_t)value;
+    else if (n == "verbose") o.verbose = value != 0;
+    else if (n == "pq_queries_per_pass") o.pq_queries_per_pass = (int)value;
+    else { qb_set_error("set_option: unknown option '%s'", name); return QB_ERR_INVALID; }
+    return QB_OK;
+}
+
 void qb_set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -84,6 +119,18 @@ static qb_status use_device(int device) {
     return QB_OK;
 }
 
+// Point ids crossing the C ABI are the ids searches on this storage report: local row + id_base (qb_storage_set_id_base).
+// Every id-taking entry point validates the range and works on local rows.
+static qb_status localize_ids(const qb_storage* s, const uint32_t* ids, uint64_t n, uint32_t* dst, const char* who) {
+    const uint32_t base = s->id_base;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t l = ids[i] - base;
+        QB_CHECK(ids[i] >= base && l < s->count, QB_ERR_INVALID, "%s: id %u out of range [%u, %llu)", who, ids[i], base, (unsigned long long)base + s->count);
+        dst[i] = l;
+    }
+    return QB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ buffers
 qb_status qb_ensure_device(void** p, size_t* have, size_t need_bytes) {
     if (*have >= need_bytes && *p) return QB_OK;
@@ -111,18 +158,32 @@ static qb_status ensure_dev_elems(T** p, size_t* have_elems, size_t need_elems) 
     return QB_OK;
 }
 
-qb_status qb_ctx_acquire(qb_storage* s, QbSearchCtx** out) {
-    std::lock_guard<std::mutex> lk(s->mu);
-    for (QbSearchCtx* c : s->ctxs)
-        if (!c->in_use) { c->in_use = true; *out = c; return QB_OK; }
+static qb_status ctx_new(QbSearchCtx** out) {
     QbSearchCtx* c = new QbSearchCtx();
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; qb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return QB_ERR_CUDA; }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     c->in_use = true;
+    *out = c;
+    return QB_OK;
+}
+qb_status qb_ctx_acquire(qb_storage* s, QbSearchCtx** out) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (QbSearchCtx* c : s->ctxs)
+        if (!c->in_use) { c->in_use = true; *out = c; return QB_OK; }
+    QbSearchCtx* c = nullptr;
+    QB_TRY(ctx_new(&c));
     s->ctxs.push_back(c);
     *out = c;
+    return QB_OK;
+}
+// the context of the device-resident entry points (qb_search_batch_device, qb_hnsw_search_batch_device) and of qb_storage_stream:
+// its stream is the one the caller times and orders against, so it is never shared with the pooled host-facing searches
+qb_status qb_ctx_device(qb_storage* s, QbSearchCtx** out) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->dev_ctx) QB_TRY(ctx_new(&s->dev_ctx));
+    *out = s->dev_ctx;
     return QB_OK;
 }
 void qb_ctx_release(qb_storage* s, QbSearchCtx* c) {
@@ -215,7 +276,9 @@ extern "C" qb_status qb_storage_read_rows(const qb_storage* s, const uint32_t* i
     QB_CHECK(s && ids && host_out, QB_ERR_INVALID, "read_rows: null argument");
     QB_CHECK(s->kind == QB_KIND_DENSE, QB_ERR_UNSUPPORTED, "read_rows: dense storages only");
     if (n == 0) return QB_OK;
-    for (uint64_t i = 0; i < n; ++i) QB_CHECK(ids[i] < s->count, QB_ERR_INVALID, "read_rows: id %u out of range", ids[i]);
+    std::vector<uint32_t> local(n);
+    QB_TRY(localize_ids(s, ids, n, local.data(), "read_rows"));
+    ids = local.data();
     QB_TRY(use_device(s->device));
     const uint32_t rb = s->dim * s->elem_size;
     uint32_t* d_ids = nullptr; uint8_t* d_out = nullptr;
@@ -293,9 +356,9 @@ extern "C" qb_status qb_storage_create_pq(int32_t device, uint32_t dim, uint32_t
     if (!ok) { qb_set_error("create_pq: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); qb_storage_destroy(s); return QB_ERR_OOM; }
     s->hbm_bytes = cb + (size_t)n_centroids * dim * 4;
     cudaMemset(s->d_pq_codes, 0, cb);
-    cudaError_t e = cudaMemcpy(s->d_centroids, centroids, (size_t)n_centroids * dim * 4, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(s->d_centroids, centroids, (size_t)n_centroids * dim * 4, cudaMemcpyDefault);
     if (e == cudaSuccess) e = cudaMemcpy(s->d_pq_div, div_start_end, (size_t)2 * m * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && count) e = cudaMemcpy2D(s->d_pq_codes, s->pq_stride, codes, m, m, count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && count) e = cudaMemcpy2D(s->d_pq_codes, s->pq_stride, codes, m, m, count, cudaMemcpyDefault);
     if (e != cudaSuccess) { qb_set_error("create_pq: upload: %s", cudaGetErrorString(e)); qb_storage_destroy(s); return QB_ERR_CUDA; }
     *out = s;
     return QB_OK;
@@ -326,8 +389,8 @@ extern "C" qb_status qb_storage_create_bq(int32_t device, uint32_t dim, qb_bq_en
     if (ok && mean_std) ok = cudaMalloc(&s->d_mean_std, (size_t)dim * 8) == cudaSuccess;
     if (!ok) { qb_set_error("create_bq: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); qb_storage_destroy(s); return QB_ERR_OOM; }
     s->hbm_bytes = rb;
-    cudaError_t e = count ? cudaMemcpy(s->d_bq_rows, rows, (size_t)count * row_bytes, cudaMemcpyHostToDevice) : cudaSuccess;
-    if (e == cudaSuccess && mean_std) e = cudaMemcpy(s->d_mean_std, mean_std, (size_t)dim * 8, cudaMemcpyHostToDevice);
+    cudaError_t e = count ? cudaMemcpy(s->d_bq_rows, rows, (size_t)count * row_bytes, cudaMemcpyDefault) : cudaSuccess;
+    if (e == cudaSuccess && mean_std) e = cudaMemcpy(s->d_mean_std, mean_std, (size_t)dim * 8, cudaMemcpyDefault);
     if (e != cudaSuccess) { qb_set_error("create_bq: upload: %s", cudaGetErrorString(e)); qb_storage_destroy(s); return QB_ERR_CUDA; }
     *out = s;
     return QB_OK;
@@ -337,7 +400,9 @@ extern "C" void qb_storage_destroy(qb_storage* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     for (QbSearchCtx* c : s->ctxs) ctx_destroy(c);
+    ctx_destroy(s->dev_ctx);
     for (auto& pr : s->prof_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : s->prof_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(s->d_rows); cudaFree(s->d_codes); cudaFree(s->d_voff); cudaFree(s->d_pq_div); cudaFree(s->d_centroids); cudaFree(s->d_pq_codes);
     cudaFree(s->d_bq_rows); cudaFree(s->d_mean_std); cudaFree(s->d_deleted);
     cudaGetLastError();
@@ -367,13 +432,8 @@ extern "C" qb_status qb_storage_set_deleted(qb_storage* s, const uint64_t* bitma
 extern "C" void* qb_storage_stream(qb_storage* s) {
     if (!s) return nullptr;
     if (cudaSetDevice(s->device) != cudaSuccess) return nullptr;
-    {
-        std::lock_guard<std::mutex> lk(s->mu);
-        if (!s->ctxs.empty()) return s->ctxs[0]->stream;
-    }
     QbSearchCtx* c = nullptr;
-    if (qb_ctx_acquire(s, &c) != QB_OK) return nullptr;
-    qb_ctx_release(s, c);
+    if (qb_ctx_device(s, &c) != QB_OK) return nullptr;
     return c->stream;
 }
 
@@ -497,7 +557,7 @@ static SearchPlan make_plan(uint64_t n_cand, uint32_t nq, uint32_t top, bool for
         // costs < 1 % more scan work and cuts survivors 4x
         uint64_t sgoal = (uint64_t)((nq >= 32 ? 8.0 : 2.0) * sqrt((double)n_cand * (double)top));
         sgoal = round_up_u64(std::max<uint64_t>(sgoal, 8192), 1024);
-        if (const char* e = getenv("QB_SAMPLE_ROWS")) sgoal = std::max<uint64_t>(256, strtoull(e, nullptr, 10));  // tuning experiments
+        if (qb_opt().sample_rows) sgoal = std::max<uint64_t>(256, qb_opt().sample_rows);  // tuning experiments
         p.sample = std::min<uint64_t>(sgoal, n_cand / 2);
         const uint64_t expect = (uint64_t)((double)n_cand * (double)top / (double)p.sample);
         p.cap = std::max<uint64_t>(p.sample, 8 * expect + 4096);
@@ -512,8 +572,11 @@ static SearchPlan make_plan(uint64_t n_cand, uint32_t nq, uint32_t top, bool for
 static void profile_begin(qb_storage* s, QbSearchCtx* c, cudaStream_t stream, cudaEvent_t* e0, cudaEvent_t* e1) {
     *e0 = *e1 = nullptr;
     if (!s->profile) return;
-    cudaEventCreate(e0);
-    cudaEventCreate(e1);
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->prof_free.empty()) { *e0 = s->prof_free.back().first; *e1 = s->prof_free.back().second; s->prof_free.pop_back(); }
+    }
+    if (!*e0) { cudaEventCreate(e0); cudaEventCreate(e1); }
     cudaEventRecord(*e0, stream);
 }
 static void profile_end(qb_storage* s, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
@@ -535,7 +598,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
     cudaStream_t stream = c->stream;
     if (n_cand == 0) { QB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, stream)); return QB_OK; }
     // single query, small top, dense f32: one streaming scan with per-CTA top-k lists + one small select (qb_dense.cu, LOCALK)
-    if (nq == 1 && top <= 16 && !d_ids && !force_direct && s->kind == QB_KIND_DENSE && s->dtype == QB_DT_F32 && n_cand > 65536 && getenv("QB_DISABLE_LOCALK") == nullptr) {
+    if (nq == 1 && top <= 16 && !d_ids && !force_direct && s->kind == QB_KIND_DENSE && s->dtype == QB_DT_F32 && n_cand > 65536 && !qb_opt().disable_localk) {
         QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)4096));
         QbScanArgs a{};
         a.d_q_enc = c->d_queries_enc; a.nq = 1; a.row_begin = 0; a.row_end = n_cand;
@@ -552,7 +615,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
         QB_CHECK(n_slots == 0, QB_ERR_CUDA, "local top-k scan wrote %llu slots", (unsigned long long)n_slots);
     }
-    const bool mma_ok = !d_ids && !(rs_flags & RS_NO_MMA) && getenv("QB_DISABLE_MMA") == nullptr;
+    const bool mma_ok = !d_ids && !(rs_flags & RS_NO_MMA) && !qb_opt().disable_mma;
     const SearchPlan plan = make_plan(n_cand, nq, top, force_direct, mma_ok && qb_sq8_mma_block(s, nq) != 0 && !(rs_flags & RS_NO_REFINE));
     if (can_flag && plan.direct) *can_flag = false;  // full materialisation: no threshold, no counters, nothing to overflow
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)plan.q_chunk * plan.cap));
@@ -640,6 +703,18 @@ static uint64_t cpu_units_per_point(const qb_storage* s) {
     }
 }
 
+// vector_io_read per scored point: dim * size_of::<TElement>() for on-disk dense storages (metric_query_scorer.rs:44-48), the
+// quantized row size for on-disk quantized data (quantized_query_scorer.rs:48,84-86), 0 for RAM-resident storages
+static uint64_t io_units_per_point(const qb_storage* s) {
+    if (!s->on_disk) return 0;
+    switch (s->kind) {
+        case QB_KIND_DENSE: return (uint64_t)s->dim * s->elem_size;
+        case QB_KIND_SQ8: return (uint64_t)s->actual_dim + 4;
+        case QB_KIND_PQ: return s->pq_m;
+        default: return s->bq_row_bytes;
+    }
+}
+
 extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32_t n_queries, uint32_t top, const uint64_t* deleted_bitmap,
                                      const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped, qb_scored_point* out,
                                      uint32_t* out_counts, qb_hw_counters* counters) {
@@ -648,7 +723,6 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
     QB_CHECK(top >= 1, QB_ERR_INVALID, "search_batch: top must be >= 1 (FixedLengthPriorityQueue::new panics on 0)");
     QB_CHECK(top <= QB_MAX_TOP, QB_ERR_UNSUPPORTED, "search_batch: top %u > %u not supported by the fused selection", top, QB_MAX_TOP);
     if (n_queries == 0) return QB_OK;
-    if (id_list) for (uint64_t i = 0; i < n_ids; ++i) QB_CHECK(id_list[i] < s->count, QB_ERR_INVALID, "search_batch: id %u out of range", id_list[i]);
     if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
     QB_TRY(use_device(s->device));
     QbSearchCtx* c = nullptr;
@@ -659,10 +733,12 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
     const size_t raw_bytes = (size_t)n_queries * s->dim * 4;
     const size_t res_bytes = (size_t)n_queries * top * sizeof(qb_scored_point);
     const size_t cnt_bytes = (size_t)n_queries * 4;
-    // pinned staging: [queries | results | counts | overflow flag]
-    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + cnt_bytes + 16));
+    // pinned staging: [queries | results | counts | overflow flag | candidate ids]
+    const size_t ids_off = round_up_u64(raw_bytes + res_bytes + cnt_bytes + 16, 16);
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, ids_off + (id_list ? n_ids * 4 : 0)));
     uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
     memcpy(hs, queries, raw_bytes);
+    if (id_list) QB_TRY(localize_ids(s, id_list, n_ids, reinterpret_cast<uint32_t*>(hs + ids_off), "search_batch"));
     QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, raw_bytes + (size_t)n_queries * pre_stride_f(s) * 4));
     // +256 rows: the tensor-core SQ8 path reads whole query blocks (rows past n_queries are masked, never scored)
     QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)n_queries + 256) * qb_encoded_query_bytes(s)));
@@ -683,7 +759,7 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
     const uint32_t* d_ids = nullptr;
     if (id_list) {
         QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)std::max<uint64_t>(n_ids, 1)));
-        QB_CUDA(cudaMemcpyAsync(c->d_ids, id_list, n_ids * 4, cudaMemcpyHostToDevice, stream));
+        QB_CUDA(cudaMemcpyAsync(c->d_ids, hs + ids_off, n_ids * 4, cudaMemcpyHostToDevice, stream));
         d_ids = c->d_ids;
     }
     unsigned int* d_overflow = reinterpret_cast<unsigned int*>(c->d_out_counts + n_queries);
@@ -707,15 +783,17 @@ extern "C" qb_status qb_search_batch(qb_storage* s, const float* queries, uint32
         if (flags & 2u) next |= RS_NO_MMA;
         if (flags & 1u) next |= RS_FORCE_DIRECT | RS_NO_MMA;
         if (next == rs_flags) break;
-        if (getenv("QB_VERBOSE")) fprintf(stderr, "[qb200] search rerun: device flags=0x%x, mode 0x%x -> 0x%x\n", flags, rs_flags, next);
+        s->n_reruns.fetch_add(1, std::memory_order_relaxed);
+        if (qb_opt().verbose) fprintf(stderr, "[qb200] search rerun: device flags=0x%x, mode 0x%x -> 0x%x\n", flags, rs_flags, next);
         rs_flags = next;
     }
+    s->n_searches.fetch_add(1, std::memory_order_relaxed);
     memcpy(out, h_res, res_bytes);
     memcpy(out_counts, h_cnt, cnt_bytes);
     if (counters) {
         const uint64_t n_cand = id_list ? n_ids : s->count;
         counters->cpu += n_cand * (uint64_t)n_queries * cpu_units_per_point(s);
-        counters->vector_io_read += 0;  // HBM-resident storage is "not on disk": multiplier 0 (metric_query_scorer.rs:44-48)
+        counters->vector_io_read += n_cand * (uint64_t)n_queries * io_units_per_point(s);
     }
     return QB_OK;
 }
@@ -727,11 +805,7 @@ extern "C" qb_status qb_search_batch_device(qb_storage* s, const float* dev_quer
     if (n_queries == 0) return QB_OK;
     QB_TRY(use_device(s->device));
     QbSearchCtx* c = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(s->mu);
-        if (!s->ctxs.empty()) c = s->ctxs[0];
-    }
-    if (!c) { QB_TRY(qb_ctx_acquire(s, &c)); qb_ctx_release(s, c); }
+    QB_TRY(qb_ctx_device(s, &c));
     QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, (size_t)n_queries * pre_stride_f(s) * 4 + 256));
     QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)n_queries + 256) * qb_encoded_query_bytes(s)));
     QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
@@ -756,9 +830,11 @@ extern "C" qb_status qb_search_batch_device(qb_storage* s, const float* dev_quer
         if (flags & 2u) next |= RS_NO_MMA;
         if (flags & 1u) next |= RS_FORCE_DIRECT | RS_NO_MMA;
         if (next == rs_flags) break;
-        if (getenv("QB_VERBOSE")) fprintf(stderr, "[qb200] search rerun: device flags=0x%x, mode 0x%x -> 0x%x\n", flags, rs_flags, next);
+        s->n_reruns.fetch_add(1, std::memory_order_relaxed);
+        if (qb_opt().verbose) fprintf(stderr, "[qb200] search rerun: device flags=0x%x, mode 0x%x -> 0x%x\n", flags, rs_flags, next);
         rs_flags = next;
     }
+    s->n_searches.fetch_add(1, std::memory_order_relaxed);
     return QB_OK;
 }
 
@@ -800,7 +876,7 @@ extern "C" qb_status qb_scorer_create(qb_storage* s, const float* query, qb_scor
 extern "C" qb_status qb_scorer_create_internal(qb_storage* s, uint32_t point_id, qb_scorer** out) {
     QB_CHECK(s && out, QB_ERR_INVALID, "scorer_create_internal: null argument");
     *out = nullptr;
-    QB_CHECK(point_id < s->count, QB_ERR_INVALID, "scorer_create_internal: id %u out of range", point_id);
+    QB_TRY(localize_ids(s, &point_id, 1, &point_id, "scorer_create_internal"));
     QB_CHECK(s->kind != QB_KIND_PQ, QB_ERR_UNSUPPORTED, "PQ has no internal query encoding (encode_internal_vector = None, encoded_vectors_pq.rs:624-627)");
     QB_TRY(use_device(s->device));
     qb_scorer* sc = nullptr;
@@ -872,7 +948,6 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
     QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "search_custom: top %u outside [1,%u]", top, QB_MAX_TOP);
     uint32_t ne = 0;
     QB_TRY(check_custom(kind, n_a, n_b, &ne));
-    if (id_list) for (uint64_t i = 0; i < n_ids; ++i) QB_CHECK(id_list[i] < s->count, QB_ERR_INVALID, "search_custom: id %u out of range", id_list[i]);
     const uint64_t n = id_list ? n_ids : s->count;
     *out_count = 0;
     if (n == 0) return QB_OK;
@@ -886,9 +961,11 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
     struct Rel { qb_storage* s; QbSearchCtx* c; ~Rel() { qb_ctx_release(s, c); } } rel{s, c};
     cudaStream_t stream = c->stream;
     const size_t raw_bytes = (size_t)ne * s->dim * 4, res_bytes = (size_t)top * sizeof(qb_scored_point);
-    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + 16));
+    const size_t ids_off = round_up_u64(raw_bytes + res_bytes + 16, 16);
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, ids_off + (id_list ? n_ids * 4 : 0)));
     uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
     memcpy(hs, vectors, raw_bytes);
+    if (id_list) QB_TRY(localize_ids(s, id_list, n_ids, reinterpret_cast<uint32_t*>(hs + ids_off), "search_custom"));
     QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, round_up_u64(raw_bytes, 16) + (size_t)ne * pre_stride_f(s) * 4));
     QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)ne + 256) * qb_encoded_query_bytes(s)));
     QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)ne));
@@ -907,7 +984,7 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
         QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_bitmap, words64 * 8, cudaMemcpyHostToDevice, stream));
         d_del2 = c->d_deleted2;
     }
-    if (id_list) QB_CUDA(cudaMemcpyAsync(c->d_ids, id_list, n * 4, cudaMemcpyHostToDevice, stream));
+    if (id_list) QB_CUDA(cudaMemcpyAsync(c->d_ids, hs + ids_off, n * 4, cudaMemcpyHostToDevice, stream));
     else QB_TRY(qb_launch_iota(c->d_ids, n, stream));
     float* d_sims = reinterpret_cast<float*>(c->d_mma);
     for (uint32_t e = 0; e < ne; ++e) {
@@ -923,7 +1000,7 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
     QB_CUDA(cudaStreamSynchronize(stream));
     memcpy(out, hs + raw_bytes, res_bytes);
     memcpy(out_count, hs + raw_bytes + res_bytes, 4);
-    if (counters) counters->cpu += n * (uint64_t)ne * cpu_units_per_point(s);
+    if (counters) { counters->cpu += n * (uint64_t)ne * cpu_units_per_point(s); counters->vector_io_read += n * (uint64_t)ne * io_units_per_point(s); }
     return QB_OK;
 }
 
@@ -1098,10 +1175,9 @@ extern "C" qb_status qb_score_points(qb_scorer* sc, const uint32_t* ids, size_t 
     QB_CHECK(sc && (n == 0 || (ids && scores)), QB_ERR_INVALID, "score_points: null argument");
     if (n == 0) return QB_OK;
     qb_storage* s = sc->st;
-    for (size_t i = 0; i < n; ++i) QB_CHECK(ids[i] < s->count, QB_ERR_INVALID, "score_points: id %u out of range (count %llu)", ids[i], (unsigned long long)s->count);
     QB_TRY(use_device(s->device));
     QB_TRY(scorer_reserve(sc, n));
-    memcpy(sc->h_ids, ids, n * 4);
+    QB_TRY(localize_ids(s, ids, n, sc->h_ids, "score_points"));
     if (n <= 2048) {
         QB_TRY(scorer_launch(sc, reinterpret_cast<const uint32_t*>(sc->m_ids), n, reinterpret_cast<float*>(sc->m_scores)));
     } else {
@@ -1111,7 +1187,8 @@ extern "C" qb_status qb_score_points(qb_scorer* sc, const uint32_t* ids, size_t 
     }
     QB_CUDA(cudaStreamSynchronize(sc->stream));
     memcpy(scores, sc->h_scores, n * 4);
-    sc->hw.cpu += (uint64_t)n * cpu_units_per_point(s);
+    sc->hw.cpu += (uint64_t)n * cpu_units_per_point(s) * (sc->custom_kind ? sc->n_examples : 1);
+    sc->hw.vector_io_read += (uint64_t)n * io_units_per_point(s);
     return QB_OK;
 }
 
@@ -1121,7 +1198,11 @@ extern "C" qb_status qb_score_internal(qb_scorer* sc, uint32_t a, uint32_t b, fl
     QB_CHECK(sc && score, QB_ERR_INVALID, "score_internal: null argument");
     QB_CHECK(!sc->custom_kind, QB_ERR_UNSUPPORTED, "score_internal: custom scorers compare against several vectors (custom_query_scorer.rs:111-113: unimplemented!)");
     qb_storage* s = sc->st;
-    QB_CHECK(a < s->count && b < s->count, QB_ERR_INVALID, "score_internal: id out of range (the reference panics)");
+    {
+        uint32_t ab[2] = {a, b};
+        QB_TRY(localize_ids(s, ab, 2, ab, "score_internal (the reference panics)"));
+        a = ab[0]; b = ab[1];
+    }
     QB_TRY(use_device(s->device));
     QB_TRY(scorer_reserve(sc, 1));
     if (s->kind == QB_KIND_PQ) {
@@ -1129,8 +1210,9 @@ extern "C" qb_status qb_score_internal(qb_scorer* sc, uint32_t a, uint32_t b, fl
     } else {
         // point `a` becomes the query (MetricQueryScorer::score_internal; SQ8 encode_internal_vector; BQ binary)
         qb_scorer* tmp = nullptr;
-        QB_TRY(qb_scorer_create_internal(s, a, &tmp));
-        qb_status st = qb_score_points(tmp, &b, 1, score);
+        const uint32_t ga = a + s->id_base, gb = b + s->id_base;   // the public entry points take reported (global) ids
+        QB_TRY(qb_scorer_create_internal(s, ga, &tmp));
+        qb_status st = qb_score_points(tmp, &gb, 1, score);
         qb_scorer_destroy(tmp);
         sc->hw.cpu += cpu_units_per_point(s);
         return st;
@@ -1155,17 +1237,16 @@ extern "C" qb_status qb_rescore(qb_scorer* orig, const uint32_t* ids, size_t n, 
     *out_count = 0;
     if (n == 0) return QB_OK;
     qb_storage* s = orig->st;
-    for (size_t i = 0; i < n; ++i) QB_CHECK(ids[i] < s->count, QB_ERR_INVALID, "rescore: id %u out of range", ids[i]);
     QB_TRY(use_device(s->device));
     QB_TRY(scorer_reserve(orig, std::max<size_t>(n, (size_t)top * 2 + 8)));
-    memcpy(orig->h_ids, ids, n * 4);
+    QB_TRY(localize_ids(s, ids, n, orig->h_ids, "rescore"));
     QB_CUDA(cudaMemcpyAsync(orig->d_ids, orig->h_ids, n * 4, cudaMemcpyHostToDevice, orig->stream));
     // score into candidate keys, select top on the device (postprocess_search_result: sort_unstable desc + truncate)
     unsigned long long* d_cand = nullptr;
     QB_CUDA(cudaMalloc(&d_cand, n * 8 + top * sizeof(qb_scored_point) + 64));
     QbScanArgs a{};
     a.d_q_enc = orig->d_query; a.d_q_off = orig->d_q_off; a.nq = 1; a.row_begin = 0; a.row_end = n; a.d_ids = orig->d_ids;
-    a.emit.cand = d_cand; a.emit.cap = n; a.emit.dense = 1; a.emit.dense_base = 0;
+    a.emit.cand = d_cand; a.emit.cap = n; a.emit.dense = 1; a.emit.dense_base = 0; a.emit.id_base = s->id_base;
     qb_status st = QB_OK;
     if (s->kind == QB_KIND_BQ) st = QB_ERR_UNSUPPORTED;  // rescoring always uses the original (dense) vectors
     else st = qb_launch_scan(s, a, orig->stream);
@@ -1181,6 +1262,7 @@ extern "C" qb_status qb_rescore(qb_scorer* orig, const uint32_t* ids, size_t n, 
     cudaFree(d_cand);
     if (e != cudaSuccess) { qb_set_error("rescore: %s", cudaGetErrorString(e)); return QB_ERR_CUDA; }
     orig->hw.cpu += (uint64_t)n * cpu_units_per_point(s);
+    orig->hw.vector_io_read += (uint64_t)n * io_units_per_point(s);
     return st;
 }
 
@@ -1243,12 +1325,109 @@ extern "C" qb_status qb_profile_read(qb_storage* s, uint64_t* launches, double* 
             s->prof_ms += ms;
             s->prof_launches += 1;
         }
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        s->prof_free.push_back(pr);
     }
     s->prof_pending.clear();
     if (launches) *launches = s->prof_launches;
     if (total_ms) *total_ms = s->prof_ms;
     if (reset) { s->prof_launches = 0; s->prof_ms = 0.0; }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_search_stats(qb_storage* s, uint64_t* searches, uint64_t* reruns, int32_t reset) {
+    QB_CHECK(s, QB_ERR_INVALID, "search_stats: null storage");
+    if (searches) *searches = s->n_searches.load();
+    if (reruns) *reruns = s->n_reruns.load();
+    if (reset) { s->n_searches = 0; s->n_reruns = 0; }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_storage_set_on_disk(qb_storage* s, int32_t on_disk) {
+    QB_CHECK(s, QB_ERR_INVALID, "set_on_disk: null storage");
+    s->on_disk = on_disk != 0;
+    return QB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ HNSW on the device
+extern "C" qb_status qb_hnsw_search_batch(qb_hnsw* g, const float* queries, uint32_t n_queries, uint32_t top, uint32_t ef, uint32_t entry_point,
+                                          uint32_t entry_level, const uint64_t* deleted_bitmap, const volatile int32_t* is_stopped, qb_scored_point* out,
+                                          uint32_t* out_counts, qb_hw_counters* counters) {
+    QB_CHECK(g && out && out_counts, QB_ERR_INVALID, "hnsw_search_batch: null argument");
+    QB_CHECK(n_queries == 0 || queries, QB_ERR_INVALID, "hnsw_search_batch: null queries");
+    QB_CHECK(top >= 1 && top <= 4096, QB_ERR_INVALID, "hnsw_search_batch: top %u outside [1,4096]", top);
+    if (n_queries == 0) return QB_OK;
+    if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+    qb_storage* s = g->st;
+    QB_TRY(use_device(s->device));
+    std::lock_guard<std::mutex> glk(g->mu);
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_acquire(s, &c));
+    struct Rel { qb_storage* s; QbSearchCtx* c; ~Rel() { qb_ctx_release(s, c); } } rel{s, c};
+    cudaStream_t stream = c->stream;
+    const size_t raw_bytes = (size_t)n_queries * s->dim * 4, res_bytes = (size_t)n_queries * top * sizeof(qb_scored_point), cnt_bytes = (size_t)n_queries * 4;
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + cnt_bytes + 16));
+    uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
+    memcpy(hs, queries, raw_bytes);
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, raw_bytes + (size_t)n_queries * pre_stride_f(s) * 4));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)n_queries + 256) * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
+    QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)n_queries * top));
+    QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)n_queries + 4));
+    QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
+    float* d_pre = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + raw_bytes);
+    QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), n_queries, d_pre, c->d_queries_enc, c->d_q_off, stream));
+    const uint32_t* d_del2 = nullptr;
+    if (deleted_bitmap) {
+        const uint64_t words64 = ceil_div_u64(s->count, 64);
+        QB_TRY(ensure_dev_elems(&c->d_deleted2, &c->deleted2_words, (size_t)words64 * 2));
+        QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_bitmap, words64 * 8, cudaMemcpyHostToDevice, stream));
+        d_del2 = c->d_deleted2;
+    }
+    QB_TRY(qb_hnsw_launch(g, c->d_queries_enc, c->d_q_off, n_queries, top, ef, entry_point, entry_level, d_del2, c->d_out, c->d_out_counts, stream));
+    QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaMemcpyAsync(hs + raw_bytes + res_bytes, c->d_out_counts, cnt_bytes, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaStreamSynchronize(stream));
+    memcpy(out, hs + raw_bytes, res_bytes);
+    memcpy(out_counts, hs + raw_bytes + res_bytes, cnt_bytes);
+    if (counters) {
+        const uint64_t before = g->evals;
+        QB_TRY(qb_hnsw_read_stats(g, stream));
+        counters->cpu += (g->evals - before) * cpu_units_per_point(s);
+        counters->vector_io_read += (g->evals - before) * io_units_per_point(s);
+    }
+    if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_hnsw_search_batch_device(qb_hnsw* g, const float* dev_queries, uint32_t n_queries, uint32_t top, uint32_t ef, uint32_t entry_point,
+                                                 uint32_t entry_level, qb_scored_point* dev_out, uint32_t* dev_counts) {
+    QB_CHECK(g && dev_queries && dev_out && dev_counts, QB_ERR_INVALID, "hnsw_search_batch_device: null argument");
+    QB_CHECK(top >= 1 && top <= 4096, QB_ERR_INVALID, "hnsw_search_batch_device: top %u outside [1,4096]", top);
+    if (n_queries == 0) return QB_OK;
+    qb_storage* s = g->st;
+    QB_TRY(use_device(s->device));
+    std::lock_guard<std::mutex> glk(g->mu);
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_device(s, &c));
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, (size_t)n_queries * pre_stride_f(s) * 4 + 256));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)n_queries + 256) * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
+    QB_TRY(prepare_queries(s, dev_queries, n_queries, reinterpret_cast<float*>(c->d_queries_raw), c->d_queries_enc, c->d_q_off, c->stream));
+    cudaEvent_t e0, e1;
+    profile_begin(s, c, c->stream, &e0, &e1);
+    QB_TRY(qb_hnsw_launch(g, c->d_queries_enc, c->d_q_off, n_queries, top, ef, entry_point, entry_level, nullptr, dev_out, dev_counts, c->stream));
+    profile_end(s, c->stream, e0, e1);
+    return QB_OK;
+}
+
+extern "C" qb_status qb_hnsw_stats(qb_hnsw* g, uint64_t* hops, uint64_t* scored_points, int32_t reset) {
+    QB_CHECK(g, QB_ERR_INVALID, "hnsw_stats: null graph");
+    QB_TRY(use_device(g->st->device));
+    std::lock_guard<std::mutex> glk(g->mu);
+    QB_CUDA(cudaDeviceSynchronize());
+    QB_TRY(qb_hnsw_read_stats(g, 0));
+    if (hops) *hops = g->hops;
+    if (scored_points) *scored_points = g->evals;
+    if (reset) { g->hops = 0; g->evals = 0; }
     return QB_OK;
 }

@@ -41,6 +41,14 @@ extern std::atomic<uint64_t> g_qb_launches;
         if (_s != QB_OK) return _s;     \
     } while (0)
 
+struct QbOptions {
+    bool disable_localk = false, disable_mma = false, mma_1cta = false, mma_no_segments = false, verbose = false;
+    int mma_debug = 0;
+    int pq_queries_per_pass = 0;   // 0 = automatic
+    uint64_t sample_rows = 0;
+};
+QbOptions& qb_opt();
+
 #define QB_LAUNCHED() (g_qb_launches.fetch_add(1, std::memory_order_relaxed))
 
 static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
@@ -49,17 +57,19 @@ static inline uint64_t round_up_u64(uint64_t a, uint64_t b) { return ceil_div_u6
 // ------------------------------------------------------------------------------------------------
 // candidate keys: (orderable(score) << 32) | ~id  — descending u64 order == (score desc, id asc).
 // ScoredPointOffset orders by OrderedFloat(score) only (lib/common/common/src/types.rs:21-25); the id
-// tie-break is ours and makes results independent of CTA scheduling.  -0.0 is canonicalised to +0.0
-// (OrderedFloat treats them as equal).  Key 0 is reserved as "empty".
+// tie-break is ours and makes results independent of CTA scheduling.  Scores keep their bit pattern: -0.0 is NOT folded
+// into +0.0 (OrderedFloat calls them equal, so ranking -0.0 just below +0.0 is one of the orders the reference allows, and
+// a returned -0.0 stays -0.0); every NaN maps to one key above +inf (OrderedFloat: NaN is the greatest value and equal
+// to itself) and comes back as the canonical quiet NaN.  Key 0 is reserved as "empty".
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t qb_orderable(float s) {
     uint32_t u;
 #ifdef __CUDA_ARCH__
-    u = __float_as_uint(s + 0.0f);
+    u = __float_as_uint(s);
 #else
-    float t = s + 0.0f;
-    memcpy(&u, &t, 4);
+    memcpy(&u, &s, 4);
 #endif
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0xFFC00000u;  // NaN (either sign): above +inf; decodes to 0x7FC00000
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __host__ __device__ __forceinline__ float qb_unorderable(uint32_t o) {
@@ -110,7 +120,7 @@ __device__ __forceinline__ void qb_emit(const QbEmit& e, uint32_t q, unsigned lo
         unsigned long long key = qb_is_deleted(e, id) ? 0ull : qb_pack_key(score, id + e.id_base);
         e.cand[(unsigned long long)q * e.cap + (slot - e.dense_base)] = key;
     } else {
-        if (score >= e.thr[q] && !qb_is_deleted(e, id)) {
+        if (!(score < e.thr[q]) && !qb_is_deleted(e, id)) {   // NaN ranks highest: it passes
             unsigned int pos = atomicAdd(&e.cnt[q], 1u);
             if (pos < e.cap) e.cand[(unsigned long long)q * e.cap + pos] = qb_pack_key(score, id + e.id_base);
         }

@@ -19,90 +19,11 @@
 // map is needed), completion on mbarriers; 8 consumer warps each own every 8th slot, read rows and the query from
 // shared memory with conflict-free 128-bit loads and emit candidates that pass the per-query threshold.
 #include "qb_internal.h"
+#include "qb_score.cuh"
 
 namespace {
 
-enum { M_DOT = 0, M_EUCLID = 1, M_MANHATTAN = 2 };
-
-__device__ __forceinline__ float4 shfl_xor4(float4 v, int m) {
-    v.x = __shfl_xor_sync(0xFFFFFFFFu, v.x, m);
-    v.y = __shfl_xor_sync(0xFFFFFFFFu, v.y, m);
-    v.z = __shfl_xor_sync(0xFFFFFFFFu, v.z, m);
-    v.w = __shfl_xor_sync(0xFFFFFFFFu, v.w, m);
-    return v;
-}
-__device__ __forceinline__ float4 add4(float4 a, float4 b) {
-    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
-}
-
-template <int METRIC>
-__device__ __forceinline__ float elem_step(float q, float v, float acc) {
-    if (METRIC == M_DOT) return __fmaf_rn(q, v, acc);
-    float d = __fsub_rn(q, v);
-    if (METRIC == M_EUCLID) return __fmaf_rn(d, d, acc);
-    return __fadd_rn(fabsf(d), acc);
-}
-template <int METRIC>
-__device__ __forceinline__ float tail_step(float q, float v, float r) {
-    if (METRIC == M_DOT) return __fadd_rn(r, __fmul_rn(q, v));
-    float d = __fsub_rn(q, v);
-    if (METRIC == M_EUCLID) return __fadd_rn(r, __fmul_rn(d, d));
-    return __fadd_rn(r, fabsf(d));
-}
-
-// AVX tier (dim >= 32).  `row` and `qry` are 16-B aligned; t = lane & 7.  All 8 lanes of the group return r.
-template <int METRIC>
-__device__ __forceinline__ float score_avx_group8(const float* __restrict__ row, const float* __restrict__ qry, uint32_t dim, int t) {
-    const uint32_t nblk = dim >> 5;
-    const float4* r4 = reinterpret_cast<const float4*>(row) + t;
-    const float4* q4 = reinterpret_cast<const float4*>(qry) + t;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (uint32_t b = 0; b < nblk; ++b) {
-        float4 v = r4[b * 8];
-        float4 q = q4[b * 8];
-        acc.x = elem_step<METRIC>(q.x, v.x, acc.x);
-        acc.y = elem_step<METRIC>(q.y, v.y, acc.y);
-        acc.z = elem_step<METRIC>(q.z, v.z, acc.z);
-        acc.w = elem_step<METRIC>(q.w, v.w, acc.w);
-    }
-    acc = add4(acc, shfl_xor4(acc, 2));  // (P0+P1), (P2+P3)        four_way_hsum, simple_avx.rs:21-28
-    acc = add4(acc, shfl_xor4(acc, 4));  // (P0+P1)+(P2+P3) = T[l]
-    acc = add4(acc, shfl_xor4(acc, 1));  // T[i+4]+T[i] = L[i]       hsum256_ps_avx, simple_avx.rs:10-16
-    float r = __fadd_rn(__fadd_rn(acc.x, acc.y), __fadd_rn(acc.z, acc.w));
-    for (uint32_t i = nblk << 5; i < dim; ++i) r = tail_step<METRIC>(qry[i], row[i], r);
-    return (METRIC == M_DOT) ? r : -r;
-}
-
-// SSE tier (16 <= dim < 32, one 16-block, unfused mul+add) and scalar tier (dim < 16); one thread per pair.
-template <int METRIC>
-__device__ __forceinline__ float score_small(const float* __restrict__ row, const float* __restrict__ qry, uint32_t dim) {
-    float r;
-    uint32_t start;
-    if (dim >= 16) {
-        float p[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float q = qry[i], v = row[i];
-            if (METRIC == M_DOT) p[i] = __fadd_rn(__fmul_rn(q, v), 0.0f);
-            else {
-                float d = __fsub_rn(q, v);
-                p[i] = (METRIC == M_EUCLID) ? __fadd_rn(__fmul_rn(d, d), 0.0f) : __fadd_rn(fabsf(d), 0.0f);
-            }
-        }
-        float h[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)  // hsum128_ps_sse: (x0+x2)+(x1+x3), simple_sse.rs:13-17
-            h[a] = __fadd_rn(__fadd_rn(p[4 * a], p[4 * a + 2]), __fadd_rn(p[4 * a + 1], p[4 * a + 3]));
-        r = __fadd_rn(__fadd_rn(__fadd_rn(h[0], h[1]), h[2]), h[3]);
-        start = 16;
-    } else {
-        r = -0.0f;  // Rust's f32 Sum folds from -0.0
-        start = 0;
-    }
-    for (uint32_t i = start; i < dim; ++i) r = tail_step<METRIC>(qry[i], row[i], r);
-    return (METRIC == M_DOT) ? r : -r;
-}
+using namespace qbs;
 
 // ------------------------------------------------------------------------------------------------
 // streaming scan kernel
@@ -240,7 +161,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(con
                         __syncwarp();            // the bookkeeping (the kernel lives on bytes in flight: hold time is bandwidth)
                         if (lane == 0) qb_mbar_arrive(&empty[s]);
                     }
-                    if (valid && t == 0 && sc >= wthr) lk_push(emit.deleted, emit.deleted2, emit.id_base, sc, (uint32_t)(r0 + rin), lk_queue + cw * 4, &lk_count[cw]);
+                    if (valid && t == 0 && !(sc < wthr)) lk_push(emit.deleted, emit.deleted2, emit.id_base, sc, (uint32_t)(r0 + rin), lk_queue + cw * 4, &lk_count[cw]);
                     __syncwarp();
                     const unsigned int n_queued = *reinterpret_cast<volatile unsigned int*>(&lk_count[cw]);
                     if (n_queued) {

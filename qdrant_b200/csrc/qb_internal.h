@@ -4,7 +4,7 @@
 
 enum QbKind { QB_KIND_DENSE = 0, QB_KIND_SQ8 = 1, QB_KIND_PQ = 2, QB_KIND_BQ = 3 };
 
-constexpr uint32_t QB_MAX_TOP = 4096;          // fused top-k limit (select kernel sorts <= 4096 keys in smem)
+constexpr uint32_t QB_MAX_TOP = 1u << 20;      // fused top-k limit; <= 4096 sorts in shared memory, larger tops sort in a global scratch (qb_topk.cu)
 constexpr uint32_t QB_SELECT_THREADS = 1024;
 
 // A search context: one CUDA stream + the scratch a brute-force scan needs.  Contexts are pooled per
@@ -75,9 +75,15 @@ struct qb_storage {
     // ---- soft deletes
     uint32_t* d_deleted = nullptr;   // resident bits (32-bit words), or null
 
+    // ---- hardware counters: the reference meters vector_io_read only for on-disk storages (metric_query_scorer.rs:44-48)
+    bool on_disk = false;
+
     // ---- contexts / profiling
     std::mutex mu;
-    std::vector<QbSearchCtx*> ctxs;
+    std::vector<QbSearchCtx*> ctxs;       // pool for the host-facing searches (one per concurrent call)
+    QbSearchCtx* dev_ctx = nullptr;       // reserved for qb_storage_stream / the *_device entry points; never handed out by the pool
+    std::atomic<uint64_t> n_searches{0}, n_reruns{0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
     bool profile = false;
     uint64_t prof_launches = 0;
     double prof_ms = 0.0;
@@ -103,11 +109,35 @@ struct qb_scorer {
     qb_hw_counters hw = {0, 0};
 };
 
+// A device-resident HNSW graph bound to a storage (qb_hnsw.cu)
+struct qb_hnsw {
+    qb_storage* st = nullptr;
+    uint32_t n_points = 0, m = 0, m0 = 0, levels = 0;
+    uint32_t* d_links0 = nullptr;
+    uint64_t* d_level_offsets = nullptr;
+    uint32_t* d_reindex = nullptr;
+    uint32_t* d_neighbors = nullptr;
+    uint64_t* d_offsets = nullptr;
+    uint64_t hbm_bytes = 0;
+    // search scratch (one batch at a time per graph handle; mu serialises)
+    std::mutex mu;
+    uint32_t* d_visited = nullptr; uint64_t visited_words = 0; unsigned visited_slots = 0;
+    uint32_t* d_vlog = nullptr; uint32_t vlog_cap = 0;
+    unsigned int* d_work = nullptr;
+    unsigned long long* d_stats = nullptr;
+    uint64_t hops = 0, evals = 0;
+};
+
+qb_status qb_hnsw_launch(qb_hnsw* g, const void* d_q_enc, const float* d_q_off, uint32_t nq, uint32_t top, uint32_t ef, uint32_t entry, uint32_t entry_level,
+                         const uint32_t* d_deleted2, qb_scored_point* d_out, uint32_t* d_counts, cudaStream_t stream);
+qb_status qb_hnsw_read_stats(qb_hnsw* g, cudaStream_t stream);
+
 // ---------------------------------------------------------------- helpers (qb_api.cu)
 qb_status qb_ensure_device(void** p, size_t* have, size_t need_bytes);
 qb_status qb_ensure_pinned(void** p, size_t* have, size_t need_bytes);
 qb_status qb_ctx_acquire(qb_storage* s, QbSearchCtx** out);
 void qb_ctx_release(qb_storage* s, QbSearchCtx* c);
+qb_status qb_ctx_device(qb_storage* s, QbSearchCtx** out);
 
 // ---------------------------------------------------------------- kernels' host launchers
 // All launchers enqueue on `stream` and never synchronise.

@@ -18,6 +18,7 @@
 //   PQ   four f32 lanes, lane k sums chunks j = k (mod 4) in ascending j; (s0+s2)+(s1+s3); tail sequential.
 //   BQ   popcounts are integers; the float epilogue of calculate_metric is restated literally.
 #include "qb_internal.h"
+#include "qb_score.cuh"
 
 namespace {
 
@@ -92,51 +93,7 @@ __global__ void __launch_bounds__(256) sq8_group_kernel(const Sq8Params p, const
         const float v_off = p.voff[row];
         for (uint32_t q = 0; q < p.nq; ++q) {
             const uint4* qp = reinterpret_cast<const uint4*>(p.q_codes + (size_t)q * p.ad);
-            float score;
-            if (p.l1) {
-                unsigned int acc = 0;
-                for (uint32_t c = t; c < n_chunks; c += 8) {
-                    uint4 v = __ldg(rp + c), w = __ldg(qp + c);
-                    acc += __vsadu4(v.x, w.x) + __vsadu4(v.y, w.y) + __vsadu4(v.z, w.z) + __vsadu4(v.w, w.w);
-                }
-                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
-                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
-                score = (float)acc;  // impl_score_l1_avx returns (float)sum, cpp/avx2.c:117-121
-            } else if (!LANEX) {
-                int acc = 0;
-                for (uint32_t c = t; c < n_chunks; c += 8) {
-                    uint4 v = __ldg(rp + c), w = __ldg(qp + c);
-                    acc = __dp4a((int)v.x, (int)w.x, acc);
-                    acc = __dp4a((int)v.y, (int)w.y, acc);
-                    acc = __dp4a((int)v.z, (int)w.z, acc);
-                    acc = __dp4a((int)v.w, (int)w.w, acc);
-                }
-                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
-                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-                acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
-                score = (float)acc;  // exact: total < 2^24 (see header)
-            } else {
-                // lane partition of impl_score_dot_avx: byte pair j of every 16-B chunk accumulates into i32 lane j
-                int ln[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                for (uint32_t c = t; c < n_chunks; c += 8) {
-                    uint4 v = __ldg(rp + c), w = __ldg(qp + c);
-                    ln[0] = __dp4a((int)v.x, (int)(w.x & 0x0000FFFFu), ln[0]); ln[1] = __dp4a((int)v.x, (int)(w.x & 0xFFFF0000u), ln[1]);
-                    ln[2] = __dp4a((int)v.y, (int)(w.y & 0x0000FFFFu), ln[2]); ln[3] = __dp4a((int)v.y, (int)(w.y & 0xFFFF0000u), ln[3]);
-                    ln[4] = __dp4a((int)v.z, (int)(w.z & 0x0000FFFFu), ln[4]); ln[5] = __dp4a((int)v.z, (int)(w.z & 0xFFFF0000u), ln[5]);
-                    ln[6] = __dp4a((int)v.w, (int)(w.w & 0x0000FFFFu), ln[6]); ln[7] = __dp4a((int)v.w, (int)(w.w & 0xFFFF0000u), ln[7]);
-                }
-#pragma unroll
-                for (int l = 0; l < 8; ++l) {
-                    ln[l] += __shfl_xor_sync(0xFFFFFFFFu, ln[l], 1);
-                    ln[l] += __shfl_xor_sync(0xFFFFFFFFu, ln[l], 2);
-                    ln[l] += __shfl_xor_sync(0xFFFFFFFFu, ln[l], 4);
-                }
-                // HSUM256_PS (cpp/avx2.c:7-14): ((l0+l4)+(l2+l6)) + ((l1+l5)+(l3+l7))
-                float x0 = __fadd_rn((float)ln[4], (float)ln[0]), x1 = __fadd_rn((float)ln[5], (float)ln[1]);
-                float x2 = __fadd_rn((float)ln[6], (float)ln[2]), x3 = __fadd_rn((float)ln[7], (float)ln[3]);
-                score = __fadd_rn(__fadd_rn(x0, x2), __fadd_rn(x1, x3));
-            }
+            const float score = qbs::sq8_raw_group8<LANEX>(rp, qp, n_chunks, t, p.l1);
             // postprocess_score: multiplier * score + query_offset + vector_offset (encoded_vectors_u8.rs:101-103)
             const float sc = __fadd_rn(__fadd_rn(__fmul_rn(p.multiplier, score), p.q_off[q]), v_off);
             if (valid && t == 0) {

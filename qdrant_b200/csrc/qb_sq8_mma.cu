@@ -575,7 +575,7 @@ uint32_t block_for(const qb_storage* s, uint32_t nq, bool two) {
 uint32_t qb_sq8_mma_block(const qb_storage* s, uint32_t nq) {
     if (s->kind != QB_KIND_SQ8 || s->qdist == QB_QD_L1) return 0;
     if (nq < 32 || s->count < 4 * 128) return 0;
-    if (!getenv("QB_MMA_1CTA") && !(s->sm_count & 1))
+    if (!qb_opt().mma_1cta && !(s->sm_count & 1))
         if (const uint32_t b2 = block_for(s, nq, true)) return b2 | 0x80000000u;
     return block_for(s, nq, false);
 }
@@ -600,7 +600,7 @@ qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_
     p.voff = s->d_voff; p.n_rows = row_end; p.ad = ad; p.n_blk = n_blk; p.n_qblocks = n_qblocks; p.nq = nq;
     p.multiplier = s->multiplier; p.q_off = d_q_off; p.flags = d_flags;
     p.check_exact = ((uint64_t)ad * 127ull * 127ull >= (1ull << 24)) ? 1 : 0;
-    p.debug = getenv("QB_MMA_DEBUG") ? atoi(getenv("QB_MMA_DEBUG")) : 0;
+    p.debug = qb_opt().mma_debug;
     if (!emit.dense && s->multiplier > 0.0f && !(p.debug & 2)) {
         QB_CHECK(d_scratch && scratch_bytes >= qb_sq8_mma_scratch_bytes(s, nq_pad), QB_ERR_INVALID, "sq8_mma_scan: scratch too small");
         uint8_t* sc = reinterpret_cast<uint8_t*>(d_scratch);
@@ -622,7 +622,7 @@ qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_
     if (workers > n_tiles) workers = (uint32_t)n_tiles;
     p.n_workers = workers;
     const uint32_t n_seg = two ? 2 * workers : workers;  // CTAs that ever see a given query
-    if (!emit.dense && seg_len && !getenv("QB_MMA_NO_SEGMENTS")) {
+    if (!emit.dense && seg_len && !qb_opt().mma_no_segments) {
         uint64_t seg = (emit.cap / n_seg) & ~15ull;
         if (seg > 512) seg = 512;
         if (seg >= 64) {

@@ -197,6 +197,75 @@ qb_select_kernel(const unsigned long long* cand, const unsigned int* __restrict_
     if (threadIdx.x == 0) out_counts[q] = s_valid;
 }
 
+// top > SORT_CAP (oversampled tops: limit x oversampling easily exceeds 4096, vector_index_search_common.rs:27-46).  Same exact
+// MSB radix select for the top-th key, then the selected keys are gathered into a global scratch row of p2 >= top slots and
+// bitonic-sorted there.  One CTA per query; off the headline paths, so simplicity over speed.
+__global__ void __launch_bounds__(QB_SELECT_THREADS)
+qb_select_large_kernel(const unsigned long long* cand, const unsigned int* __restrict__ cnt, unsigned long long cap, unsigned long long fixed_n, uint32_t top,
+                       unsigned long long* __restrict__ scratch, uint32_t p2, qb_scored_point* __restrict__ out, uint32_t* __restrict__ out_counts,
+                       unsigned int* __restrict__ overflow) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_kk, s_fill, s_short;
+    const uint32_t q = blockIdx.x;
+    unsigned long long n;
+    if (fixed_n) n = fixed_n;
+    else {
+        unsigned int c = cnt[q];
+        if (c > cap) { if (threadIdx.x == 0 && overflow) atomicOr(overflow, 1u); c = (unsigned int)cap; }
+        n = c;
+    }
+    const unsigned long long* keys = cand + (unsigned long long)q * cap;
+    unsigned long long* buf = scratch + (unsigned long long)q * p2;
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_kk = top; s_short = 0u; s_fill = 0u; }
+    unsigned long long mask = 0ull;
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = keys[i];
+            if (key != 0ull && (key & mask) == prefix) atomicAdd(&hist[(unsigned int)((key >> shift) & 255ull)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int kk = s_kk, cum = 0;
+            int d = 255;
+            for (; d >= 0; --d) { if (cum + hist[d] >= kk) break; cum += hist[d]; }
+            if (d < 0) s_short = 1u;                      // fewer than `top` non-empty keys: keep them all
+            else { s_kk = kk - cum; s_prefix = prefix | ((unsigned long long)d << shift); }
+        }
+        mask |= (255ull << shift);
+        __syncthreads();
+        if (s_short) break;
+    }
+    const unsigned long long kth = s_short ? 1ull : s_prefix;
+    for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) buf[i] = 0ull;
+    __syncthreads();
+    for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long key = keys[i];
+        if (key >= kth && key != 0ull) { const unsigned int p = atomicAdd(&s_fill, 1u); if (p < p2) buf[p] = key; }
+    }
+    __syncthreads();
+    bitonic_sort_desc(buf, (int)p2);
+    unsigned int valid = 0;
+    for (uint32_t i = threadIdx.x; i < top; i += blockDim.x) {
+        const unsigned long long k = buf[i];
+        qb_scored_point sp;
+        if (k != 0ull) { sp.idx = qb_key_id(k); sp.score = qb_key_score(k); valid++; }
+        else { sp.idx = 0; sp.score = 0.0f; }
+        out[(unsigned long long)q * top + i] = sp;
+    }
+    __shared__ unsigned int s_valid;
+    if (threadIdx.x == 0) s_valid = 0u;
+    __syncthreads();
+    if (valid) atomicAdd(&s_valid, valid);
+    __syncthreads();
+    if (threadIdx.x == 0) out_counts[q] = s_valid;
+}
+
 __global__ void qb_fill_u32_kernel(unsigned int* p, unsigned int v, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -209,6 +278,18 @@ qb_status qb_launch_select(const unsigned long long* d_cand, const unsigned int*
                            uint32_t* d_out_counts, float* d_thr, unsigned int* d_overflow, cudaStream_t stream) {
     QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_UNSUPPORTED, "top=%u outside [1,%u]", top, QB_MAX_TOP);
     if (nq == 0) return QB_OK;
+    if (mode == 0 && top > (uint32_t)SORT_CAP) {
+        uint32_t p2 = 1;
+        while (p2 < top) p2 <<= 1;
+        unsigned long long* scratch = nullptr;
+        QB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)nq * p2 * 8, stream));
+        qb_select_large_kernel<<<nq, QB_SELECT_THREADS, 0, stream>>>(d_cand, d_cnt, cap, fixed_n, top, scratch, p2, d_out, d_out_counts, d_overflow);
+        QB_LAUNCHED();
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(scratch, stream);
+        if (e != cudaSuccess) { qb_set_error("select (large top): %s", cudaGetErrorString(e)); return QB_ERR_CUDA; }
+        return QB_OK;
+    }
     qb_select_kernel<<<nq, QB_SELECT_THREADS, 0, stream>>>(d_cand, d_cnt, cap, fixed_n, top, mode, d_out, d_out_counts, d_thr,
                                                           d_overflow);
     QB_LAUNCHED();

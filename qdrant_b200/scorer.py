@@ -83,6 +83,8 @@ def _bitmap(point_deleted, count: int) -> Optional[np.ndarray]:
         return None
     m = np.asarray(point_deleted)
     if m.dtype == np.uint64:
+        if m.size < (count + 63) // 64:   # the library reads ceil(count / 64) words
+            raise ValueError(f"deleted bitmap has {m.size} words, need {(count + 63) // 64}")
         return np.ascontiguousarray(m)
     bits = np.zeros(((count + 63) // 64) * 64, dtype=bool)
     bits[: m.size] = m.astype(bool)
@@ -271,6 +273,16 @@ class _Storage:
 
     def stream_ptr(self) -> int:
         return int(lib().qb_storage_stream(self._h) or 0)
+
+    def set_on_disk(self, on_disk: bool) -> None:
+        """VectorStorage::is_on_disk of the storage this copy caches (decides vector_io_read metering)."""
+        check(lib().qb_storage_set_on_disk(self._h, 1 if on_disk else 0))
+
+    def search_stats(self, reset: bool = False) -> tuple[int, int]:
+        """(fused searches, reruns after a broken fast-path assumption)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib().qb_search_stats(self._h, C.byref(a), C.byref(b), 1 if reset else 0))
+        return int(a.value), int(b.value)
 
     def profile(self, on: bool) -> None:
         check(lib().qb_profile_enable(self._h, 1 if on else 0))
@@ -497,6 +509,16 @@ class BatchFilteredSearcher:
         return self.storage.search_batch(self.queries, self.top, point_deleted=self.point_deleted, id_list=ids, is_stopped=is_stopped)
 
 
+def rescore(original_scorer: RawScorer, ids, top: int) -> np.ndarray:
+    """The rescoring step of postprocess_search_result (vector_index_search_common.rs:74-91) for a scorer that already exists:
+    score `ids` with the original-vector scorer, sort descending, truncate to `top`."""
+    ids = _ids(ids)
+    out = np.zeros(max(int(top), 1), dtype=SCORED_POINT_OFFSET)
+    n = C.c_uint32()
+    check(lib().qb_rescore(original_scorer._h, ids.ctypes.data_as(u32p), ids.size, int(top), out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(n)))
+    return out[: n.value].copy()
+
+
 def get_oversampled_top(top: int, quantized: bool, oversampling: Optional[float]) -> int:
     """vector_index_search_common.rs:27-45."""
     if quantized and oversampling is not None and oversampling > 1.0:
@@ -592,3 +614,52 @@ def pq_encode_rows(rows_ptr: int, count: int, dim: int, chunk: int, centroids, o
     c = _f32(centroids)
     assert c.ndim == 2 and c.shape[1] == dim
     check(lib().qb_pq_encode_rows_device(device, dim, chunk, c.shape[0], c.ctypes.data_as(f32p), count, vp(rows_ptr), row_stride_bytes, vp(out_ptr), vp(stream)))
+
+
+def set_option(name: str, value: int) -> None:
+    """Debugging / experiment switches of the library (qb_set_option)."""
+    check(lib().qb_set_option(name.encode(), int(value)))
+
+
+class HnswGraph:
+    """GraphLayers::search with the traversal on the device (qb_hnsw_*): a graph in the reference's plain links.bin layout
+    bound to a storage (dense f32 or SQ8); search() answers a batch of queries in one call."""
+
+    def __init__(self, storage: _Storage, links_bin, m: int, m0: int):
+        self._storage = storage
+        self._h = vp()
+        blob = np.ascontiguousarray(links_bin, dtype=np.uint8)
+        h = vp()
+        check(lib().qb_hnsw_create_plain(storage._h, blob.ctypes.data_as(u8p), blob.size, int(m), int(m0), C.byref(h)))
+        self._h = h
+
+    def search(self, queries, top: int, ef: int, entry_point: int, entry_level: int, point_deleted=None, counters: Optional[HwCounters] = None):
+        q = np.atleast_2d(_f32(queries))
+        if q.shape[1] != self._storage.dim:
+            raise ValueError(f"queries have dim {q.shape[1]}, storage has {self._storage.dim}")
+        nq = q.shape[0]
+        out = np.zeros((nq, max(top, 1)), dtype=SCORED_POINT_OFFSET)
+        counts = np.zeros(nq, dtype=np.uint32)
+        bm = _bitmap(point_deleted, self._storage.count)
+        check(lib().qb_hnsw_search_batch(self._h, q.ctypes.data_as(f32p), nq, int(top), int(ef), int(entry_point), int(entry_level),
+                                         None if bm is None else bm.ctypes.data_as(u64p), None, out.ctypes.data_as(C.POINTER(ScoredPoint)),
+                                         counts.ctypes.data_as(u32p), None if counters is None else C.byref(counters)))
+        return [out[i, : counts[i]].copy() for i in range(nq)]
+
+    def stats(self, reset: bool = True) -> tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib().qb_hnsw_stats(self._h, C.byref(a), C.byref(b), 1 if reset else 0))
+        return int(a.value), int(b.value)
+
+    def close(self):
+        if self._h:
+            lib().qb_hnsw_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        if sys.is_finalizing():
+            return
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_python_binding_covers_header(capi):
     assert sorted(capi.SIGNATURES.keys()) == header_functions()
-    assert capi.lib().qb_abi_version() == 1
+    assert capi.lib().qb_abi_version() == 2
 
 
 def test_no_silent_cpu_fallback(capi):

@@ -202,9 +202,7 @@ def test_bq_search_batch_and_rescore(qb, oracle):
                                            ("Cosine", 70_000, 1536, 40), ("Cosine", 66_000, 768, 256)])
 def test_sq8_batched_tensor_core_path(qb, oracle, dist, n, dim, nq):
     """Batched SQ8 search (tcgen05 kind::i8 GEMM + fused epilogue/filter) == oracle peek_top_iter, bit-exact, and
-    == the CUDA-core path (QB_DISABLE_MMA=1)."""
-    import os
-
+    == the CUDA-core path (option disable_mma)."""
     d = getattr(qb.Distance, dist)
     dt, inv = qparams(qb, d)
     base, queries = gen(oracle, qb, d, n, dim, nq=nq)
@@ -213,11 +211,18 @@ def test_sq8_batched_tensor_core_path(qb, oracle, dist, n, dim, nq):
     enc = [sq.encode_query(oracle.preprocess_f32(int(d), q)) for q in queries]
     codes = np.stack([e[0] for e in enc]); offs = np.array([e[1] for e in enc], np.float32)
     deleted = np.random.default_rng(4).random(n) < 0.05
-    os.environ.pop("QB_DISABLE_MMA", None)
+    qb.set_option("disable_mma", 0)
+    st.search_stats(reset=True)
     got = st.search_batch(queries, 10, point_deleted=deleted)
-    os.environ["QB_DISABLE_MMA"] = "1"
-    got_cc = st.search_batch(queries, 10, point_deleted=deleted)
-    os.environ.pop("QB_DISABLE_MMA", None)
+    searches, reruns = st.search_stats(reset=True)
+    # the tensor-core fast path itself produced the answer: no "assumption broken" rerun on the exact CUDA-core / full-materialisation paths
+    # (only dim > 1040 can leave the f32-exact window: flag 2 -> lane-exact kernel)
+    assert searches == 1 and (reruns == 0 or dim > 1040), (searches, reruns)
+    qb.set_option("disable_mma", 1)
+    try:
+        got_cc = st.search_batch(queries, 10, point_deleted=deleted)
+    finally:
+        qb.set_option("disable_mma", 0)
     want = sq.scan(codes, offs, 10, deleted=pack_bitmap(deleted))
     for i in range(nq):
         np.testing.assert_array_equal(got[i], got_cc[i])

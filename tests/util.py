@@ -13,11 +13,16 @@ def assert_topk_equal(got, want, all_scores=None, what=""):
     assert got.size == want.size, f"{what}: count {got.size} != {want.size}"
     if got.size == 0:
         return
-    gs, ws = got["score"], want["score"]
-    assert np.array_equal(gs.view(np.uint32) if False else gs, ws), f"{what}: scores differ\n got {gs[:10]}\nwant {ws[:10]}"
-    assert np.all(gs[:-1] >= gs[1:]), f"{what}: not sorted descending"
+    gs, ws = np.ascontiguousarray(got["score"]), np.ascontiguousarray(want["score"])
+    # BIT PATTERNS, not values: -0.0 must come back as -0.0.  NaN payloads are not observable through f32 comparison (x86 produces
+    # the negative default NaN, the GPU the canonical positive one), so NaNs only have to sit at the same positions.
+    nan = np.isnan(ws)
+    assert np.array_equal(np.isnan(gs), nan), f"{what}: NaN positions differ\n got {gs[:10]}\nwant {ws[:10]}"
+    assert np.array_equal(gs.view(np.uint32)[~nan], ws.view(np.uint32)[~nan]), f"{what}: score bits differ\n got {gs[:10]}\nwant {ws[:10]}"
+    fin = gs[~nan]
+    assert np.all(fin[:-1] >= fin[1:]) and (not nan.any() or nan[: int(nan.sum())].all()), f"{what}: not sorted descending (NaN first, OrderedFloat)"
     boundary = gs[-1]
-    for sc in np.unique(gs):
+    for sc in np.unique(gs[~nan]):
         gi = set(got["idx"][gs == sc].tolist())
         wi = set(want["idx"][ws == sc].tolist())
         assert len(gi) == int(np.sum(gs == sc)), f"{what}: duplicate ids"
