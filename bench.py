@@ -2,7 +2,7 @@
 """bench.py — BASELINE.json headline: queries/s (+ GB/s scanned) of single-query brute-force cosine search over
 10M x 768 f32 vectors, sharded over N B200s, next to the reference's CPU path on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config all|c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A step = one query (BASELINE configs[1]: single-query streaming scan) answered over the WHOLE data set: every rank
@@ -16,6 +16,11 @@ scans its shard (10M/N rows, strong scaling), local top-10 lists are all-gathere
   cpu_baseline: the oracle's restatement of the reference's AVX2+FMA path (peek_top_iter loop) on this box's cores,
            on a bounded sample of the same rows, extrapolated to 10M rows.
 `--impl reference` times only that CPU path and prints the same JSON shape.
+
+The default run (`--config all`) prints ONE JSON line: the C2 headline fields above plus `configs.{c3,c4,c5}` — the other
+BASELINE configs measured in the same process (each with value / e2e / roofline / parity / cpu_baseline): C3 10Mx768 SQ8 batch
+1024 on the int8 tensor cores, C4 one 6.25M-row PQ shard per GPU, C5 HNSW M=16 ef=128 with the traversal on the device.
+At N > 1 only the sharded configs (C2, C4) run.
 """
 from __future__ import annotations
 
@@ -38,7 +43,7 @@ N_ROWS = 10_000_000
 DIM = 768
 TOP = 10
 N_QUERIES = 100
-CPU_SAMPLE_ROWS = 1_000_000
+CPU_SAMPLE_ROWS = 0          # 0 = the full data set when host RAM allows, else ~8 GB
 METRIC = "queries/sec, 10Mx768 f32 brute-force cosine top-10, single query (GB/s scanned = value * 30.72)"
 
 
@@ -52,8 +57,10 @@ def parse():
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--cpu-sample-rows", type=int, default=CPU_SAMPLE_ROWS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
-                    help="c2 = headline (single-query f32 cosine, default); c3 = 10Mx768 SQ8 cosine, 1024-query batch on the int8 tensor cores")
+    ap.add_argument("--config", default="all", choices=["all", "c2", "c3", "c4", "c5"],
+                    help="all = C2 headline + configs.{c3,c4,c5} in one line (default); cN = that config alone")
+    ap.add_argument("--c5-rows", type=int, default=1_000_000, help="points of the HNSW index (BASELINE says 10M; the graph is built on the host cores inside the run)")
+    ap.add_argument("--c5-queries", type=int, default=4096)
     ap.add_argument("--batch", type=int, default=1024, help="queries per batch (c3)")
     return ap.parse_args()
 
@@ -137,53 +144,69 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_scan_threads(base: np.ndarray, queries_pre: np.ndarray, top: int, threads: int, pool: cf.ThreadPoolExecutor):
-    """T equal segments scanned concurrently (one blocking task per segment, segments_searcher.rs:255) + host merge
-    (BatchResultAggregator) — the oracle's C loop releases the GIL inside ctypes."""
+def c2_config(rows: int, dim: int) -> dict:
+    return {"workload": f"{rows}x{dim} f32 cosine brute-force, single query, top {TOP} (BASELINE configs[1])", "rows": rows, "dim": dim, "top": TOP}
+
+
+def cpu_rows_that_fit(total_rows: int, dim: int, want: int) -> int:
+    """The full data set when the host has the RAM for it (30.7 GB at 10M x 768), else ~8 GB of it."""
+    if want:
+        return min(want, total_rows)
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    full = total_rows * dim * 4
+    if avail > full * 1.4 + (8 << 30):
+        return total_rows
+    return min(total_rows, max(100_000, (8 << 30) // (dim * 4)))
+
+
+def cpu_reference_run(queries_pre: np.ndarray, steps: int, warmup: int, total_rows: int, dim: int, sample_rows: int = 0):
+    """The reference's CPU path for C2 on this box's cores: T pinned threads, each owning (allocating, first-touching, scanning)
+    one contiguous segment — one blocking task per segment, segments_searcher.rs:255 — every task the peek_top_iter loop of the
+    oracle (AVX2+FMA dot, 64-id chunks, binary heap), lists merged on the host.  All of it inside oracle/mt.c: no Python per
+    segment.  Rows are generated by the owning threads (seeded standard normal, cosine-preprocessed): same shape, dtype and
+    distribution as the GPU arm's rows."""
     from oracle import oracle as o
-    from qdrant_b200.sharded import merge_topk_host, shard_ranges
 
-    rng = shard_ranges(base.shape[0], threads)
-
-    def seg(r):
-        b, e = r
-        res = o.scan_f32(o.COSINE, base, queries_pre, top, row_begin=b, row_end=e)
-        return res
-
-    parts = list(pool.map(seg, rng))
-    return [merge_topk_host([p[i] for p in parts], top) for i in range(queries_pre.shape[0])]
-
-
-def cpu_reference_run(base: np.ndarray, queries_pre: np.ndarray, steps: int, warmup: int, total_rows: int):
     threads = os.cpu_count() or 1
-    pool = cf.ThreadPoolExecutor(max_workers=threads)
+    rows = cpu_rows_that_fit(total_rows, dim, sample_rows)
+    pool = o.CpuPool(threads)
+    t0 = time.perf_counter()
+    pool.load_f32(rows, dim, o.COSINE, seed=42)
+    load_s = time.perf_counter() - t0
     nq = queries_pre.shape[0]
     for i in range(warmup):
-        cpu_scan_threads(base, queries_pre[i % nq : i % nq + 1], TOP, threads, pool)
+        pool.scan_f32(queries_pre[i % nq : i % nq + 1], TOP)
     t0 = time.perf_counter()
     for i in range(steps):
-        cpu_scan_threads(base, queries_pre[i % nq : i % nq + 1], TOP, threads, pool)
-    dt = time.perf_counter() - t0
-    pool.shutdown()
-    ms_sample = dt / steps * 1e3
-    # a full-data-set query costs total_rows / sample_rows times a sample query (linear scan)
-    scale = total_rows / base.shape[0]
-    qps_full = 1.0 / (dt / steps * scale)
-    return {"value": qps_full, "unit": "queries/s", "cores": threads, "kind": "port",
-            "sample": f"{base.shape[0]} of {total_rows} rows x {base.shape[1]} f32 (same rows the GPU scans), {steps} single-query scans, "
-                      f"{threads} threads over {threads} equal segments + host merge, {ms_sample:.1f} ms/sample-scan, extrapolated linearly to {total_rows} rows",
-            "ms_per_sample_scan": ms_sample, "gb_per_s": base.shape[0] * base.shape[1] * 4 / (dt / steps) / 1e9}
-
-
-def gen_cpu_rows(n: int, dim: int, seed: int = 42) -> np.ndarray:
-    from oracle import oracle as o
-
-    rng = np.random.default_rng(seed)
-    out = np.empty((n, dim), dtype=np.float32)
-    step = 100_000
-    for b in range(0, n, step):
-        e = min(b + step, n)
-        out[b:e] = o.preprocess_rows_f32(o.COSINE, rng.standard_normal((e - b, dim), dtype=np.float32))
+        res = pool.scan_f32(queries_pre[i % nq : i % nq + 1], TOP)
+    dt = (time.perf_counter() - t0) / steps
+    assert res[0].size == TOP and np.all(res[0]["score"][:-1] >= res[0]["score"][1:])
+    pool.close()
+    # one thread, one segment (how the reference scans a single segment): the many-thread figure must be a multiple of it
+    one = o.CpuPool(1)
+    r1 = min(rows, 400_000)
+    one.load_f32(r1, dim, o.COSINE, seed=42)
+    one.scan_f32(queries_pre[:1], TOP)
+    t0 = time.perf_counter()
+    for i in range(3):
+        one.scan_f32(queries_pre[i % nq : i % nq + 1], TOP)
+    dt1 = (time.perf_counter() - t0) / 3
+    one.close()
+    gbs, gbs1 = rows * dim * 4 / dt / 1e9, r1 * dim * 4 / dt1 / 1e9
+    scale = total_rows / rows
+    out = {"value": 1.0 / (dt * scale), "unit": "queries/s", "cores": threads, "kind": "port", "threads": threads,
+           "rows_scanned_per_query": rows, "same_config": rows == total_rows, "ms_per_scan": dt * 1e3, "gb_per_s": gbs, "gb_per_s_1thread": gbs1,
+           "speedup_vs_1thread": gbs / gbs1, "load_s": load_s,
+           "sample": (f"{'the full' if rows == total_rows else 'first'} {rows} of {total_rows} rows x {dim} f32, {steps} single-query scans, {threads} pinned threads each "
+                      f"scanning its own first-touched segment (oracle/mt.c) + host merge: {dt * 1e3:.1f} ms/scan = {gbs:.1f} GB/s ({gbs / gbs1:.1f}x the 1-thread "
+                      f"{gbs1:.1f} GB/s)" + ("" if rows == total_rows else f", extrapolated linearly to {total_rows} rows"))}
+    if threads >= 8 and gbs < 4 * gbs1:
+        out["note"] = f"{threads}-thread scan is only {gbs / gbs1:.1f}x one thread: host DRAM bandwidth (not cores) bounds this arm"
     return out
 
 
@@ -194,17 +217,15 @@ def main_reference(args):
     from oracle import oracle as o
 
     o.ensure_built()
-    rows = min(args.cpu_sample_rows, args.rows)
-    base = gen_cpu_rows(rows, args.dim)
     q = np.random.default_rng(43).standard_normal((N_QUERIES, args.dim)).astype(np.float32)
     qp = np.stack([o.preprocess_f32(o.COSINE, x) for x in q])
-    r = cpu_reference_run(base, qp, args.steps, max(args.warmup, 3), args.rows)
+    W = max(args.warmup, 3)
+    r = cpu_reference_run(qp, args.steps, W, args.rows, args.dim, args.cpu_sample_rows)
     ms = 1e3 / r["value"]
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.rows}x{args.dim} f32 cosine brute-force, single query, top {TOP} (CPU: AVX2+FMA restatement of the reference path, "
-                                   f"bounded sample extrapolated)", "rows": args.rows, "dim": args.dim, "top": TOP},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": c2_config(args.rows, args.dim),
+            "cpu_baseline": r,
             "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gb_per_s_scanned": r["gb_per_s"]}
     print(json.dumps(line))
@@ -212,7 +233,8 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def main_ours(args):
+def dist_ctx():
+    """(world, rank, local_rank, device); initialises the NCCL process group once under torchrun."""
     import torch
     import torch.distributed as dist
 
@@ -223,9 +245,18 @@ def main_ours(args):
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local_rank, dev
+
+
+def main_ours(args):
+    """C2, the headline.  Returns the JSON line as a dict on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank, local_rank, dev = dist_ctx()
 
     from qdrant_b200 import scorer as qb
     from qdrant_b200._capi import lib
@@ -312,19 +343,42 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
+    # ---- parity inside the bench (the driver sees it): every rank checks its shard's fused scan against the oracle on the very rows
+    # the GPU holds (a prefix read back from HBM), and at N > 1 rank 0 re-merges the ranks' LOCAL lists on the host
+    # (BatchResultAggregator restated in numpy) and compares with what the device exchange + merge produced.
+    parity = {"checked": False}
+    if not args.no_cpu:
+        from oracle import oracle as o
+        from qdrant_b200.sharded import merge_topk_host
+
+        rows = min(200_000, n_local)
+        ids = np.arange(rows, dtype=np.uint32) + np.uint32(b)
+        base = st.get_dense(ids)
+        qp0 = o.preprocess_f32(o.COSINE, queries[0])
+        got = st.search_batch(queries[0], TOP, id_list=ids)[0]
+        want = o.scan_f32(o.COSINE, base, qp0[None], TOP)[0]
+        assert np.array_equal(got["score"].view(np.uint32), want["score"].view(np.uint32)), "bench parity spot-check failed: GPU scan != oracle scan"
+        assert np.array_equal(got["idx"], want["idx"] + np.uint32(b))
+        parity = {"checked": True, "rows_checked_per_rank": rows, "scan_vs_oracle": "bit-exact"}
+        if world > 1:
+            searcher.d_queries[:1].copy_(d_all_q[:1])
+            searcher.search_device(1)
+            merged = searcher.results_host(1)[0]
+            local = st.search_batch(queries[0], TOP)[0]          # this rank's own top-k through the plain C-ABI call (global ids)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, local)
+            if rank == 0:
+                want_m = merge_topk_host(gathered, TOP)
+                assert np.array_equal(merged, want_m), "sharded search != host merge of the shards' lists"
+                parity["sharded_equals_merge_of_shards"] = True
+    searches, reruns = st.search_stats()
+    assert reruns == 0, f"{reruns} fallback reruns in the C2 path"
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rows = min(args.cpu_sample_rows, n_local)
-        base = st.get_dense(np.arange(rows, dtype=np.uint32))  # the very rows the GPU scans
-        from oracle import oracle as o
-
         qp = np.stack([o.preprocess_f32(o.COSINE, x) for x in queries])
-        cpu = cpu_reference_run(base, qp, steps=10, warmup=3, total_rows=args.rows)
-        # parity spot-check inside the bench: GPU top-k over the sample prefix == CPU scan of the same rows
-        got = st.search_batch(queries[0], TOP, id_list=np.arange(rows, dtype=np.uint32))[0]
-        want = o.scan_f32(o.COSINE, base, qp[0:1], TOP)[0]
-        assert np.array_equal(got["score"], want["score"]), "bench parity spot-check failed"
+        cpu = cpu_reference_run(qp, steps=5, warmup=2, total_rows=args.rows, dim=args.dim, sample_rows=args.cpu_sample_rows)
 
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
         qps = K / (dev_ms / 1e3)
@@ -337,9 +391,8 @@ def main_ours(args):
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.rows}x{args.dim} f32 cosine brute-force, single query, top {TOP} (BASELINE configs[1])",
-                       "rows": args.rows, "dim": args.dim, "top": TOP, "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}, NCCL all-gather of top-k",
-                       "l2": "inputs larger than L2 (shard = %.1f GB >> 126 MB), no flush needed" % (algo_bytes / 1e9)},
+            "config": dict(c2_config(args.rows, args.dim), rows_per_gpu=n_local, parallelism=f"row-sharded x{world}, top-k exchange over NVLink + device merge",
+                           l2="inputs larger than L2 (shard = %.1f GB >> 126 MB), no flush needed" % (algo_bytes / 1e9)),
             "gb_per_s_scanned": qps * args.rows * args.dim * 4 / 1e9,
             "e2e": {"value": K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": args.dim * 4, "d2h_bytes_per_step": TOP * 8 + 4,
                     "ms_per_step": e2e_ms / K},
@@ -349,18 +402,17 @@ def main_ours(args):
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms, "launches_timed": n_prof},
         }
+        line["parity"] = parity
+        line["fallback_reruns"] = reruns
         if cpu is not None:
-            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
-    # orderly teardown: torch tensors / streams first, then the storage, then the process group
+            line["cpu_baseline"] = cpu
+    # orderly teardown: torch tensors / streams first, then the storage (the process group outlives this config)
+    searcher.close()
     del searcher, d_all_q
     torch.cuda.synchronize()
     st.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    sys.stdout.flush()
-    return 0
+    torch.cuda.empty_cache()
+    return line if rank == 0 else None
 
 
 # ------------------------------------------------------------------------------------------------ C3: batched SQ8 (1 GPU)
@@ -375,6 +427,7 @@ def main_c3(args):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     n, dim, nq, top = args.rows, args.dim, args.batch, TOP
+    args = argparse.Namespace(**dict(vars(args), steps=min(args.steps, 10)))   # a step is a 1024-query batch (~6 ms); 10 is plenty
     ad = dim + (16 - dim % 16) % 16
     chunk = 500_000
 
@@ -453,12 +506,17 @@ def main_c3(args):
     for _ in range(K):
         res = st.search_batch(queries, top)
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    searches, reruns = st.search_stats(reset=True)
+    assert reruns == 0, f"C3: {reruns} fallback reruns in {searches} searches — the tensor-core fast path did not produce these results"
     # the tensor-core path must agree with the lane-exact CUDA-core path (bit-exact), on a slice of the batch
-    os.environ["QB_DISABLE_MMA"] = "1"
-    res_cc = st.search_batch(queries[:48], top)
-    os.environ.pop("QB_DISABLE_MMA", None)
+    qb.set_option("disable_mma", 1)
+    try:
+        res_cc = st.search_batch(queries[:48], top)
+    finally:
+        qb.set_option("disable_mma", 0)
     for a, b in zip(res[:48], res_cc):
         assert np.array_equal(a, b), "tensor-core and CUDA-core SQ8 paths disagree"
+    parity = {"checked": True, "tensor_core_equals_cuda_core": "bit-exact on 48 queries x all rows", "fallback_reruns": reruns}
 
     cpu = None
     if not args.no_cpu:
@@ -467,27 +525,25 @@ def main_c3(args):
         meta = o.SQ8Meta(dim, ad, float(alpha), float(offset), float(multiplier), o.QD_DOT, 0)
         sq = o.SQ8(meta, h_sample)
         enc = [sq.encode_query(o.preprocess_f32(o.COSINE, q)) for q in queries]
-        codes = np.stack([e[0] for e in enc]); offs = np.array([e[1] for e in enc], np.float32)
-        threads = os.cpu_count() or 1
-        from qdrant_b200.sharded import shard_ranges
-        import ctypes as C
-
-        def seg(r):
-            b, e = r
-            out = np.zeros((nq, top), dtype=o.SCORED); cnt = np.zeros(nq, dtype=np.uint32)
-            o.lib().qo_scan_sq8(C.byref(meta), h_sample.ctypes.data_as(C.POINTER(C.c_uint8)), b, e, codes.ctypes.data_as(C.POINTER(C.c_uint8)),
-                                offs.ctypes.data_as(C.POINTER(C.c_float)), nq, top, None, out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.POINTER(C.c_uint32)))
-            return out
-        with cf.ThreadPoolExecutor(max_workers=threads) as pool:
-            list(pool.map(seg, shard_ranges(sample_rows, threads)))
-            t0 = time.perf_counter()
-            reps = 3
-            for _ in range(reps):
-                list(pool.map(seg, shard_ranges(sample_rows, threads)))
-            dt = (time.perf_counter() - t0) / reps
+        codes = np.ascontiguousarray(np.stack([e[0] for e in enc])); offs = np.array([e[1] for e in enc], np.float32)
+        # oracle == GPU on the sample rows (same codes, same query encodings): bit-exact scores
+        want = sq.scan(codes[:8], offs[:8], top)
+        got = st.search_batch(queries[:8], top, id_list=np.arange(sample_rows, dtype=np.uint32))
+        for a_, b_ in zip(got, want):
+            assert np.array_equal(a_["score"].view(np.uint32), b_["score"].view(np.uint32)), "C3 parity spot-check failed: GPU SQ8 scan != oracle"
+        parity["scan_vs_oracle"] = f"bit-exact on 8 queries x {sample_rows} rows"
+        pool = o.CpuPool()
+        pool.scan_sq8(meta, h_sample, codes, offs, top)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            pool.scan_sq8(meta, h_sample, codes, offs, top)
+        dt = (time.perf_counter() - t0) / reps
+        threads = pool.threads
+        pool.close()
         cpu = {"value": nq / (dt * n / sample_rows), "unit": "queries/s", "cores": threads, "kind": "reference+port",
-               "sample": f"{sample_rows} of {n} rows x {nq} queries: impl_score_dot_avx arithmetic + postprocess + heap (oracle qo_scan_sq8), {threads} threads over row "
-                         f"segments, {dt*1e3:.0f} ms per sample batch, extrapolated linearly to {n} rows"}
+               "sample": f"{sample_rows} of {n} rows x {nq} queries: impl_score_dot_avx arithmetic + postprocess + heap (oracle qo_scan_sq8), {threads} pinned threads over row "
+                         f"segments (oracle/mt.c), {dt*1e3:.0f} ms per sample batch, extrapolated linearly to {n} rows (compute-bound: every row meets every query)"}
     # MEASURED_PEAKS.json has no int8 figure (its tensor number is cuBLAS bf16, 1645.8 TF/s); the denominator here is the stricter
     # one: the tcgen05.mma kind::i8 issue rate measured on this pool by tools/mma_rate.cu (8190 MAC/clk/SM x 148 SMs x 1.965 GHz)
     peak_i8 = 4539.0
@@ -513,11 +569,13 @@ def main_c3(args):
                          "peak_source": "measured tcgen05.mma kind::i8 issue rate (profiles/mma_rate_r01.jsonl, tools/mma_rate.cu); MEASURED_PEAKS.json holds no int8 figure "
                                         "(2 x its cuBLAS bf16 number would be 3291.6)", "avg_launch_ms": kern_ms,
                          "launches_timed": n_prof, "algorithmic_ops_per_launch": ops}}
+    line["parity"] = parity
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
     st.close()
-    return 0
+    del d_q, d_out, d_cnt
+    torch.cuda.empty_cache()
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ C4: PQ LUT scorer
@@ -532,11 +590,8 @@ def main_c4(args):
     from qdrant_b200._capi import check, lib, vp
     from qdrant_b200.sharded import ShardedSegmentSearcher
 
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local_rank, dev = dist_ctx()
+    args = argparse.Namespace(**dict(vars(args), steps=min(args.steps, 5)))   # a step is a 256-query batch over the shard
     total_rows, dim, chunk, nq, top = 50_000_000, 1536, 16, 256, TOP
     if args.rows != N_ROWS:
         total_rows = args.rows
@@ -546,6 +601,8 @@ def main_c4(args):
     codes = rng.integers(0, 256, (n_local, m), dtype=np.uint8)
     cents = np.random.default_rng(7).standard_normal((256, dim)).astype(np.float32) * 0.05
     st = qb.ProductQuantizedVectors(codes, cents, chunk, dim, qb.Distance.Dot, device=local_rank)
+    sample_rows = min(200_000, n_local)
+    h_sample = np.ascontiguousarray(codes[:sample_rows])
     del codes
     queries = np.random.default_rng(45).standard_normal((nq, dim)).astype(np.float32)
     searcher = ShardedSegmentSearcher(st, id_base=rank * n_local, top=top, max_queries=nq, device=dev)
@@ -591,6 +648,29 @@ def main_c4(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    searches, reruns = st.search_stats(reset=True)
+    parity, cpu = {"checked": False, "fallback_reruns": reruns}, None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as o
+
+        pq = o.PQ(dim, chunk, cents, h_sample, o.QD_DOT, False)
+        luts = np.ascontiguousarray(np.stack([pq.encode_query(q).reshape(-1) for q in queries]))   # Dot: Metric::preprocess is the identity
+        ids = np.arange(sample_rows, dtype=np.uint32) + np.uint32(rank * n_local)
+        got = st.search_batch(queries[:4], top, id_list=ids)
+        pool = o.CpuPool()
+        want = pool.scan_pq(h_sample, 256, luts[:4], top)
+        for a_, b_ in zip(got, want):
+            assert np.array_equal(a_["score"].view(np.uint32), b_["score"].view(np.uint32)), "C4 parity spot-check failed: GPU PQ scan != oracle (LUT build + score_point_sse order)"
+        parity = {"checked": True, "scan_vs_oracle": f"bit-exact on 4 queries x {sample_rows} rows (device LUT build + scan)", "fallback_reruns": reruns}
+        pool.scan_pq(h_sample, 256, luts, top)
+        t0 = time.perf_counter()
+        pool.scan_pq(h_sample, 256, luts, top)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nq / (dt * n_local / sample_rows) , "unit": "queries/s", "cores": pool.threads, "kind": "port",
+               "sample": f"{sample_rows} of {n_local} rows x {nq} queries: score_point_sse summation order + heap (oracle qo_scan_pq), {pool.threads} pinned threads over row segments, "
+                         f"{dt*1e3:.0f} ms per sample batch, extrapolated linearly to one {n_local}-row shard (per-GPU figure; x{world} shards for the whole job)"}
+        pool.close()
+    line = None
     if rank == 0:
         lookups = float(nq) * n_local * m
         kern_ms = prof_ms / max(n_prof, 1)
@@ -607,66 +687,165 @@ def main_c4(args):
                              "peak": smem_peak_glookups, "unit": "Glookup/s", "frac": (lookups / (kern_ms / 1e3) / 1e9 / smem_peak_glookups) if n_prof else None, "traffic": None,
                              "peak_source": "148 SMs x 32 banks x clocks.max.sm (conflict-free 4-B shared-memory gathers); no such figure in MEASURED_PEAKS.json",
                              "avg_launch_ms": kern_ms, "launches_timed": n_prof, "hbm_gb_per_s": (float(nq) * n_local * m / (kern_ms / 1e3) / 1e9) if n_prof else None}}
-        print(json.dumps(line))
+        line["parity"] = parity
+        if cpu:
+            line["cpu_baseline"] = cpu
+    searcher.close()
     del searcher
     torch.cuda.synchronize()
     st.close()
+    torch.cuda.empty_cache()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ C5: HNSW, traversal on the device
+def main_c5(args):
+    """BASELINE configs[4]: HNSW (M=16, ef=128) graph search on the GPU scorer, recall@10 vs the CPU HNSW.
+    The traversal itself runs on the device (qb_hnsw_search_batch: one persistent CTA per in-flight query, graph links in HBM);
+    the CPU arm is the reference traversal (oracle/hnsw.c restating graph_layers.rs) on ALL host cores, one search per thread,
+    over the SAME graph.  A step = one batch of --c5-queries queries.  The graph is built inside the run by the oracle's
+    multi-threaded builder (the reference builds with rayon + per-point locks too), so the index size is bounded by build
+    time: --c5-rows (default 1M of BASELINE's 10M) and the line says so."""
+    import torch
+
+    from oracle import oracle as o
+    from qdrant_b200 import scorer as qb
+    from qdrant_b200._capi import check, lib, vp
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n, dim, top, ef, nq = args.c5_rows, args.dim, TOP, 128, args.c5_queries
+    threads = os.cpu_count() or 1
+    # clustered synthetic data (1024 Gaussian clusters): i.i.d. Gaussian vectors in 768-d are the degenerate worst case for any
+    # graph index (all points nearly equidistant, recall ~0.1), which says nothing about the scorer under test.  Generated on the
+    # device, normalised with the reference's cosine preprocess, then copied to the host for the CPU builder.
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    centers = torch.randn((1024, dim), generator=g, device=dev)
+    base_d = torch.empty((n, dim), dtype=torch.float32, device=dev)
+    for r0 in range(0, n, 250_000):
+        cn = min(250_000, n - r0)
+        idx = torch.randint(0, 1024, (cn,), generator=g, device=dev)
+        x = centers[idx] + 0.5 * torch.randn((cn, dim), generator=g, device=dev)
+        check(lib().qb_metric_preprocess_device(0, int(qb.Distance.Cosine), dim, cn, vp(x.data_ptr()), dim * 4))
+        base_d[r0 : r0 + cn] = x
+    qi = torch.randint(0, 1024, (nq,), generator=g, device=dev)
+    queries = (centers[qi] + 0.5 * torch.randn((nq, dim), generator=g, device=dev)).cpu().numpy()
+    base = base_d.cpu().numpy()
+    st = qb.DenseVectorStorage(None, qb.Distance.Cosine, count=n, dim=dim)
+    st.write_rows_device(0, n, base_d.data_ptr(), dim * 4)
+    del base_d, centers
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    graph = o.HNSW(base, o.COSINE, m=16, ef_construct=100, seed=42, threads=threads)
+    build_s = time.perf_counter() - t0
+    entry, entry_level, m, m0 = graph.entry()
+    hg = qb.HnswGraph(st, graph.export_plain(), m, m0)
+    qp = o.preprocess_rows_f32(o.COSINE, queries)
+    d_q = torch.from_numpy(queries).to(dev)
+    d_out = torch.empty((nq, top), dtype=torch.int64, device=dev)
+    d_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.ExternalStream(st.stream_ptr(), device=dev)
+
+    def step_device():
+        check(lib().qb_hnsw_search_batch_device(hg._h, vp(d_q.data_ptr()), nq, top, ef, entry, entry_level, vp(d_out.data_ptr()), vp(d_cnt.data_ptr())))
+
+    W, K = 3, max(3, min(args.steps, 10))
+    for _ in range(W):
+        step_device()
+    torch.cuda.synchronize()
+    hg.stats(reset=True)
+    st.profile(True)
+    launches0 = int(lib().qb_kernel_launch_count())
+    clocks = ClockSampler(0)
+    clocks.start(); time.sleep(0.3); clocks.mark()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = int(lib().qb_kernel_launch_count()) - launches0
+    n_prof, prof_ms = st.profile_read(reset=True)
+    st.profile(False)
+    clk = clocks.stop()
+    hops, evals = hg.stats(reset=True)
+    hops /= K * nq; evals /= K * nq
+    gpu = hg.search(queries, top, ef, entry, entry_level)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        gpu = hg.search(queries, top, ef, entry, entry_level)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    # ---- CPU arm: the reference traversal with the CPU scorer, same graph, all cores (one search per thread at a time)
+    graph.search_batch(qp[:256], top, ef, threads=threads)
+    t0 = time.perf_counter()
+    cpu = graph.search_batch(qp, top, ef, threads=threads)
+    cpu_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    graph.search_batch(qp[:128], top, ef, threads=1)
+    cpu1_s = (time.perf_counter() - t0) / 128
+    # ---- parity: identical lists (scores bit-equal; ids equal except inside equal-score runs) => recall difference 0
+    same = sum(int(np.array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32)) and
+                   (np.array_equal(a["idx"], b["idx"]) or np.array_equal(np.sort(a["idx"]), np.sort(b["idx"])))) for a, b in zip(gpu, cpu))
+    ne = min(nq, 500)
+    exact = st.search_batch(queries[:ne], top)
+
+    def recall(res):
+        return float(np.mean([np.mean(r["score"] >= e["score"][-1]) for r, e in zip(res[:ne], exact)]))
+    r_cpu, r_gpu = recall(cpu), recall(gpu)
+    assert same == nq, f"C5: device traversal differs from the CPU traversal on {nq - same} of {nq} queries"
+    assert abs(r_cpu - r_gpu) <= 1e-4
+    peak, peak_src = peaks()
+    kern_ms = prof_ms / max(n_prof, 1)
+    algo_bytes = evals * nq * dim * 4      # every scored point is one dim*4-byte row read
+    achieved = algo_bytes / (kern_ms / 1e3) / 1e9 if n_prof else None
+    line = {"metric": f"queries/sec, HNSW M=16 ef={ef} top-{top}, {n}x{dim} cosine, traversal + scoring on the GPU (BASELINE configs[4]; {n} of its 10M points)",
+            "value": nq * K / (dev_ms / 1e3), "unit": "queries/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (1024 Gaussian clusters)",
+            "config": {"workload": f"HNSW graph search, {nq} concurrent queries per batch, {hops:.0f} hops / {evals:.0f} scored points per query", "rows": n, "dim": dim, "ef": ef, "m": m,
+                       "batch": nq, "graph_build_s": build_s, "graph_build_threads": threads, "l2": f"vectors {n * dim * 4 / 1e9:.1f} GB >> 126 MB L2"},
+            "e2e": {"value": nq * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top * 8 + nq * 4, "ms_per_step": e2e_ms / K},
+            "gpu_launches": launches, "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel (random 3-KB row reads)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms, "launches_timed": n_prof},
+            "cpu_baseline": {"value": nq / cpu_s, "unit": "queries/s", "cores": threads, "kind": "port", "single_thread_qps": 1.0 / cpu1_s,
+                             "sample": f"same {nq} queries, same graph, reference traversal + AVX2 f32 scorer (oracle/hnsw.c), {threads} threads each running one search at a time"},
+            "parity": {"checked": True, "identical_result_lists": same, "of": nq, "recall_at_10": {"cpu_traversal": r_cpu, "gpu_traversal": r_gpu, "vs_exact_on": ne}},
+            "recall_at_10": {"cpu_traversal": r_cpu, "gpu_traversal": r_gpu}}
+    hg.close(); graph.close()
+    del d_q, d_out, d_cnt
+    st.close()
+    torch.cuda.empty_cache()
+    return line
+
+
+def main_all(args):
+    """Default run: C2 headline + configs.{c3,c4,c5} in ONE JSON line (rank 0)."""
+    import torch.distributed as dist
+
+    world, rank, _, _ = dist_ctx()
+    line = main_ours(args) if args.config in ("all", "c2") else None
+    extras = {}
+    if args.config == "all":
+        small = args.rows != N_ROWS     # debug sizes: shrink the other configs along
+        sub = argparse.Namespace(**vars(args))
+        if small:
+            sub.c5_rows = min(args.c5_rows, max(20_000, args.rows // 10)); sub.c5_queries = min(args.c5_queries, 512)
+        if world == 1:
+            extras["c3"] = main_c3(sub)
+        extras["c4"] = main_c4(sub)
+        if world == 1:
+            extras["c5"] = main_c5(sub)
+    elif args.config != "c2":
+        line = {"c3": main_c3, "c4": main_c4, "c5": main_c5}[args.config](args)
+    if rank == 0 and line is not None:
+        if extras:
+            line["configs"] = extras
+        print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
-
-
-# ------------------------------------------------------------------------------------------------ C5: HNSW through the GPU RawScorer
-def main_c5(args):
-    """BASELINE configs[4]: HNSW (M=16, ef=128) graph search with the GPU RawScorer vs the CPU scorer, recall@10 parity.
-    The 10M-point graph of the config cannot be built by a single-threaded CPU builder in bench time, so this line uses a
-    REDUCED graph (default 50K x 768, --rows to change) and says so; it reports q/s both ways and both recalls.  Traversal
-    is the oracle's from-spec CPU HNSW (the reference keeps traversal on the CPU); one RawScorer::score_points call per hop."""
-    from oracle import oracle as o
-    from qdrant_b200 import scorer as qb
-
-    n = args.rows if args.rows != N_ROWS else 50_000
-    dim, top, ef, nq = args.dim, TOP, 128, 200
-    # clustered synthetic data (1024 Gaussian clusters): i.i.d. Gaussian vectors in 768-d are the degenerate worst case for any
-    # graph index (all points nearly equidistant, recall ~0.1), which says nothing about the scorer under test
-    rng = np.random.default_rng(42)
-    centers = rng.standard_normal((1024, dim)).astype(np.float32)
-    base = centers[rng.integers(0, 1024, n)] + 0.5 * rng.standard_normal((n, dim)).astype(np.float32)
-    base = o.preprocess_rows_f32(o.COSINE, base)
-    qrng = np.random.default_rng(43)
-    queries = (centers[qrng.integers(0, 1024, nq)] + 0.5 * qrng.standard_normal((nq, dim))).astype(np.float32)
-    t0 = time.perf_counter()
-    graph = o.HNSW(base, o.COSINE, m=16, ef_construct=100, seed=42)
-    build_s = time.perf_counter() - t0
-    st = qb.DenseVectorStorage(base, qb.Distance.Cosine)
-    qps = [o.preprocess_f32(o.COSINE, q) for q in queries]
-    exact = [r for r in st.search_batch(queries, top)]
-    t0 = time.perf_counter()
-    cpu = [graph.search(qp, top, ef) for qp in qps]
-    cpu_s = time.perf_counter() - t0
-    graph.stats(reset=True)
-    scorers = [st.build_raw_scorer(q) for q in queries]
-    t0 = time.perf_counter()
-    gpu = [graph.search(qp, top, ef, score_points=sc.score_points) for qp, sc in zip(qps, scorers)]
-    gpu_s = time.perf_counter() - t0
-    calls, evals = graph.stats()
-
-    def recall(res):
-        return float(np.mean([np.mean(r["score"] >= e["score"][-1]) for r, e in zip(res, exact)]))
-    same = all(np.array_equal(a, b) for a, b in zip(cpu, gpu))
-    line = {"metric": f"queries/sec, HNSW M=16 ef={ef} top-{top}, {n}x{dim} cosine (REDUCED from 10M; BASELINE configs[4]), GPU RawScorer per hop",
-            "value": nq / gpu_s, "unit": "queries/s", "n_gpus": 1, "steps": nq, "warmup": 0, "ms_per_step": gpu_s / nq * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": f"HNSW traversal on CPU, scoring through qb_score_points ({calls / nq:.0f} calls, {evals / nq:.0f} evaluations per query)",
-                                                                                  "rows": n, "dim": dim, "ef": ef, "graph_build_s": build_s},
-            "e2e": {"value": nq / gpu_s, "unit": "queries/s", "h2d_bytes_per_step": int(evals / nq * 4), "d2h_bytes_per_step": int(evals / nq * 4)},
-            "cpu_baseline": {"value": nq / cpu_s, "unit": "queries/s", "cores": 1, "kind": "port", "sample": f"same {nq} queries, same graph, oracle f32 scorer, single thread"},
-            "recall_at_10": {"cpu_scorer": recall(cpu), "gpu_scorer": recall(gpu), "identical_result_lists": bool(same)},
-            "note": "per-hop GPU scoring is launch/sync-latency bound (<= 32 ids per call, serial dependence); the gate is recall parity, not speed"}
-    print(json.dumps(line))
-    for sc in scorers:
-        sc.close()
-    st.close()
     return 0
 
 
@@ -674,4 +853,4 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         sys.exit(main_reference(a))
-    sys.exit({"c3": main_c3, "c4": main_c4, "c5": main_c5}.get(a.config, main_ours)(a))
+    sys.exit(main_all(a))

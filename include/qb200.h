@@ -58,7 +58,7 @@ typedef enum { QB_QD_COSINE = 0, QB_QD_DOT = 1, QB_QD_L1 = 2, QB_QD_L2 = 3 } qb_
 typedef enum { QB_BQ_ONE_BIT = 0, QB_BQ_TWO_BITS = 1, QB_BQ_ONE_AND_HALF_BITS = 2 } qb_bq_encoding;
 typedef enum { QB_BQQ_SAME_AS_STORAGE = 0, QB_BQQ_SCALAR4 = 1, QB_BQQ_SCALAR8 = 2 } qb_bq_query_encoding;
 /* QueryVector variants beyond Nearest (lib/segment/src/data_types/vectors.rs QueryVector; vector_storage/query/*.rs) */
-typedef enum { QB_QUERY_RECO_BEST_SCORE = 1, QB_QUERY_RECO_SUM_SCORES = 2, QB_QUERY_DISCOVER = 3, QB_QUERY_CONTEXT = 4 } qb_query_kind;
+typedef enum { QB_QUERY_RECO_BEST_SCORE = 1, QB_QUERY_RECO_SUM_SCORES = 2, QB_QUERY_DISCOVER = 3, QB_QUERY_CONTEXT = 4, QB_QUERY_FEEDBACK_NAIVE = 5 } qb_query_kind;
 
 /* #[repr(C)] ScoredPointOffset — lib/common/common/src/types.rs:12-17 */
 typedef struct { uint32_t idx; float score; } qb_scored_point;
@@ -193,6 +193,16 @@ QB_API qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const float
                                   const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
                                   qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters /* optional */);
 
+/* QueryVector::FeedbackNaive — FeedbackQuery (vector_storage/query/feedback_query.rs:150-226, dispatched at raw_scorer.rs:322-323,
+ * 376-377): score = a * sim(target) + sum over context pairs of partial_computation * (sim(positive) - sim(negative)), f32, the
+ * product rounded before the add.  vectors = target, then n_pairs (positive, negative) pairs; `partial` = the pairs'
+ * partial_computation values exactly as FeedbackQuery::new derived them (confidence^b * c, feedback_query.rs:121-146 — host
+ * arithmetic on the feedback scores, done once per query by the caller). */
+QB_API qb_status qb_scorer_create_feedback(qb_storage* s, const float* vectors, uint32_t n_pairs, float a, const float* partial, qb_scorer** out);
+QB_API qb_status qb_search_feedback(qb_storage* s, const float* vectors, uint32_t n_pairs, float a, const float* partial, uint32_t top,
+                                    const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
+                                    qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters /* optional */);
+
 /* ---------------------------------------------------------------- multivector MaxSim -- */
 /* ColBERT MaxSim, score_max_similarity (vector_storage/query_scorer/mod.rs:77-98) as used by MultiMetricQueryScorer
  * (multi_metric_query_scorer.rs) and the quantized multivector storage: a point is a run of consecutive vectors of `s`
@@ -243,6 +253,31 @@ QB_API qb_status qb_storage_set_id_base(qb_storage* s, uint32_t id_base);
 QB_API qb_status qb_topk_merge_device(int32_t device, const qb_scored_point* dev_lists, const uint32_t* dev_counts, uint32_t n_lists,
                                       uint32_t n_queries, uint32_t top, qb_scored_point* dev_out, uint32_t* dev_out_counts,
                                       void* dev_scratch, uint64_t scratch_bytes, void* stream);
+
+/* A sharded search as ONE collective per shard.  The reference runs one blocking task per segment and merges the
+ * tasks' lists on the host (segments_searcher.rs:255 -> BatchResultAggregator, search_result_aggregator.rs:50-117); here the
+ * task of every shard calls qb_multi_search_batch with the same queries, the `n_queries x top x 8 B` lists cross GPUs through
+ * peer-mapped exchange buffers over NVLink (no NCCL call, no host hop) and every caller receives the merged top-k.
+ *   - one qb_comm per shard / GPU: qb_comm_create(device, rank, world, ...).
+ *   - shards in ONE process (threads): qb_comm_connect_local(all comms) enables peer access and wires them up.
+ *   - shards in separate processes (one per GPU): each publishes qb_comm_local_handle (64 bytes, a CUDA IPC handle), the host
+ *     gathers the `world` handles by whatever transport it has, and every rank calls qb_comm_connect(handles).
+ *   - every rank must issue the same sequence of qb_multi_search_batch* calls (same n_queries / top), like any collective.
+ *   world x max_top <= 4096. */
+typedef struct qb_comm qb_comm;
+QB_API qb_status qb_comm_create(int32_t device, int32_t rank, int32_t world, uint32_t max_queries, uint32_t max_top, qb_comm** out);
+QB_API qb_status qb_comm_local_handle(qb_comm* c, uint8_t* handle_out /* 64 bytes */);
+QB_API qb_status qb_comm_connect(qb_comm* c, const uint8_t* handles /* world x 64 bytes, indexed by rank */);
+QB_API qb_status qb_comm_connect_local(qb_comm* const* comms, int32_t n);
+QB_API void qb_comm_destroy(qb_comm* c);
+/* qb_search_batch over this rank's shard (ids = local row + id_base) + exchange + merge: out = the global top-k, on every rank */
+QB_API qb_status qb_multi_search_batch(qb_comm* c, qb_storage* shard, const float* queries, uint32_t n_queries, uint32_t top,
+                                       const uint64_t* deleted_bitmap, const volatile int32_t* is_stopped, qb_scored_point* out,
+                                       uint32_t* out_counts, qb_hw_counters* counters /* optional */);
+/* same with queries / outputs resident in HBM, enqueued on qb_storage_stream(shard) without host synchronisation on the exact
+ * single-pass paths; dev_local / dev_local_counts (n_queries x top, n_queries) receive the shard's own lists */
+QB_API qb_status qb_multi_search_batch_device(qb_comm* c, qb_storage* shard, const float* dev_queries, uint32_t n_queries, uint32_t top,
+                                              qb_scored_point* dev_local, uint32_t* dev_local_counts, qb_scored_point* dev_out, uint32_t* dev_counts);
 
 /* ---------------------------------------------------------------- HNSW graph search on the device ---- */
 /* GraphLayers::search (lib/segment/src/index/hnsw_index/graph_layers.rs:530-561) for a BATCH of queries with the

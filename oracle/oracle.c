@@ -1062,6 +1062,29 @@ API float qo_custom_score(int kind, uint32_t n_a, uint32_t n_b, const float* sim
         return sum;
     }
 }
+/* FeedbackQuery::score_by, vector_storage/query/feedback_query.rs:204-226: sims = [target, pos0, neg0, pos1, neg1, ...] */
+API float qo_feedback_score(uint32_t n_pairs, float a, const float* partial, const float* sims, uint64_t stride) {
+    float score = a * sims[0];
+    for (uint32_t e = 0; e < n_pairs; e++) {
+        float delta = sims[(1 + 2 * e) * stride] - sims[(2 + 2 * e) * stride];
+        score += partial[e] * delta;      /* -ffp-contract=off: product rounded, then added, like rustc */
+    }
+    return score;
+}
+/* NaiveFeedbackCoefficients::extract_context_pairs (feedback_query.rs:114-146) with margin 0: every ordered pair (i, j), i != j, in
+ * itertools' permutations(2) order, whose score difference exceeds the margin; partial = confidence^b * c.  Returns the pair count. */
+API uint32_t qo_feedback_pairs(const float* scores, uint32_t n, float b, float c, uint32_t* pos, uint32_t* neg, float* partial) {
+    uint32_t k = 0;
+    if (n < 2) return 0;
+    for (uint32_t i = 0; i < n; i++)
+        for (uint32_t j = 0; j < n; j++) {
+            if (i == j) continue;
+            float confidence = scores[i] - scores[j];
+            if (confidence <= 0.0f) continue;
+            pos[k] = i; neg[k] = j; partial[k] = powf(confidence, b) * c; k++;
+        }
+    return k;
+}
 /* sims: [examples][stride], one column per candidate */
 API void qo_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* sims, uint64_t stride, uint64_t n, float* out) {
     for (uint64_t i = 0; i < n; i++) out[i] = qo_custom_score(kind, n_a, n_b, sims + i, stride);

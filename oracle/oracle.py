@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         L.qo_scaled_fast_sigmoid.restype, L.qo_scaled_fast_sigmoid.argtypes = C.c_float, [C.c_float]
         L.qo_custom_score.restype, L.qo_custom_score.argtypes = C.c_float, [C.c_int, C.c_uint32, C.c_uint32, f32p, C.c_uint64]
         L.qo_custom_combine.restype, L.qo_custom_combine.argtypes = None, [C.c_int, C.c_uint32, C.c_uint32, f32p, C.c_uint64, C.c_uint64, f32p]
+        L.qo_feedback_score.restype, L.qo_feedback_score.argtypes = C.c_float, [C.c_uint32, C.c_float, f32p, f32p, C.c_uint64]
+        L.qo_feedback_pairs.restype, L.qo_feedback_pairs.argtypes = C.c_uint32, [f32p, C.c_uint32, C.c_float, C.c_float, u32p, u32p, f32p]
         L.qo_preprocess_f32.restype, L.qo_preprocess_f32.argtypes = None, [C.c_int, f32p, f32p, C.c_size_t]
         L.qo_postprocess_f32.restype, L.qo_postprocess_f32.argtypes = C.c_float, [C.c_int, C.c_float]
         for name in ("dot", "cosine", "euclid", "manhattan"):
@@ -577,6 +579,25 @@ def custom_combine(kind: int, n_a: int, n_b: int, sims) -> np.ndarray:
     out = np.empty(sims.shape[1], dtype=np.float32)
     lib().qo_custom_combine(kind, n_a, n_b, _p(sims, C.c_float), sims.shape[1], sims.shape[1], _p(out, C.c_float))
     return out
+
+
+def feedback_pairs(scores, b: float, c: float):
+    """extract_context_pairs with margin 0 (feedback_query.rs:114-146): (positive index, negative index, partial_computation) per pair."""
+    sc = _f32(scores).reshape(-1)
+    n = sc.size
+    cap = max(n * (n - 1), 1)
+    pos, neg, part = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.float32)
+    k = lib().qo_feedback_pairs(_p(sc, C.c_float), n, np.float32(b), np.float32(c), _p(pos, C.c_uint32), _p(neg, C.c_uint32), _p(part, C.c_float))
+    return pos[:k].copy(), neg[:k].copy(), part[:k].copy()
+
+
+def feedback_score(a: float, partial, sims) -> np.ndarray:
+    """FeedbackQuery::score_by per candidate; sims: [1 + 2 * pairs, candidates] (target, pos0, neg0, ...)."""
+    sims = np.ascontiguousarray(np.atleast_2d(_f32(sims)))
+    part = _f32(partial).reshape(-1)
+    assert sims.shape[0] == 1 + 2 * part.size
+    return np.array([lib().qo_feedback_score(part.size, np.float32(a), _p(part, C.c_float) if part.size else None, _p(sims[:, i].copy(), C.c_float), 1)
+                     for i in range(sims.shape[1])], dtype=np.float32)
 
 
 # ------------------------------------------------------------------------------------------------ multivector MaxSim

@@ -58,6 +58,8 @@ SIGNATURES = {
     "qb_search_batch_device": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp]),
     "qb_scorer_create_custom": (C.c_int32, [vp, C.c_int, f32p, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "qb_search_custom": (C.c_int32, [vp, C.c_int, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, C.c_uint64, i32p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
+    "qb_scorer_create_feedback": (C.c_int32, [vp, f32p, C.c_uint32, C.c_float, f32p, C.POINTER(vp)]),
+    "qb_search_feedback": (C.c_int32, [vp, f32p, C.c_uint32, C.c_float, f32p, C.c_uint32, u64p, u32p, C.c_uint64, i32p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
     "qb_sq8_find_alpha_offset_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, f32p, f32p]),
     "qb_sq8_encode_rows_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]),
     "qb_bq_row_bytes": (C.c_uint32, [C.c_uint32, C.c_int]),
@@ -71,6 +73,13 @@ SIGNATURES = {
     "qb_set_option": (C.c_int32, [C.c_char_p, C.c_int64]),
     "qb_storage_set_on_disk": (C.c_int32, [vp, C.c_int32]),
     "qb_search_stats": (C.c_int32, [vp, u64p, u64p, C.c_int32]),
+    "qb_comm_create": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "qb_comm_local_handle": (C.c_int32, [vp, u8p]),
+    "qb_comm_connect": (C.c_int32, [vp, u8p]),
+    "qb_comm_connect_local": (C.c_int32, [C.POINTER(vp), C.c_int32]),
+    "qb_comm_destroy": (None, [vp]),
+    "qb_multi_search_batch": (C.c_int32, [vp, vp, f32p, C.c_uint32, C.c_uint32, u64p, i32p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
+    "qb_multi_search_batch_device": (C.c_int32, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "qb_hnsw_create_plain": (C.c_int32, [vp, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "qb_hnsw_destroy": (None, [vp]),
     "qb_hnsw_info": (C.c_int32, [vp, u32p, u32p, u64p]),

@@ -36,8 +36,8 @@ qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stre
 qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
 
 uint32_t qb_custom_examples(int kind, uint32_t n_a, uint32_t n_b);
-qb_status qb_launch_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* d_sims, uint64_t stride, uint64_t n, float* d_scores, const uint32_t* d_ids,
-                                   const QbEmit* emit, cudaStream_t stream);
+qb_status qb_launch_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* d_coef, const float* d_sims, uint64_t stride, uint64_t n, float* d_scores,
+                                   const uint32_t* d_ids, const QbEmit* emit, cudaStream_t stream);
 qb_status qb_launch_iota(uint32_t* d, uint64_t n, cudaStream_t stream);
 qb_status qb_launch_maxsim_fold(const float* d_sims, uint64_t stride, uint32_t n_query_tokens, const uint32_t* d_row_offsets, const uint32_t* d_point_ids,
                                 uint64_t n_points, float* d_scores, const QbEmit* emit, cudaStream_t stream);
@@ -905,15 +905,16 @@ static qb_status launch_example(const qb_storage* s, const void* d_enc, const fl
                                 float* d_scores, cudaStream_t stream);
 
 static qb_status check_custom(qb_query_kind kind, uint32_t n_a, uint32_t n_b, uint32_t* n_examples) {
-    QB_CHECK(kind >= QB_QUERY_RECO_BEST_SCORE && kind <= QB_QUERY_CONTEXT, QB_ERR_INVALID, "custom query: unknown kind %d", (int)kind);
-    QB_CHECK((kind != QB_QUERY_DISCOVER && kind != QB_QUERY_CONTEXT) || n_b == 0, QB_ERR_INVALID, "custom query: n_b must be 0 for discover / context (n_a = pairs)");
+    QB_CHECK(kind >= QB_QUERY_RECO_BEST_SCORE && kind <= QB_QUERY_FEEDBACK_NAIVE, QB_ERR_INVALID, "custom query: unknown kind %d", (int)kind);
+    QB_CHECK((kind != QB_QUERY_DISCOVER && kind != QB_QUERY_CONTEXT && kind != QB_QUERY_FEEDBACK_NAIVE) || n_b == 0, QB_ERR_INVALID, "custom query: n_b must be 0 for discover / context (n_a = pairs)");
     const uint32_t e = qb_custom_examples((int)kind, n_a, n_b);
     QB_CHECK(e >= 1 && e <= 4096, QB_ERR_INVALID, "custom query: %u example vectors (need 1..4096)", e);
     *n_examples = e;
     return QB_OK;
 }
 
-extern "C" qb_status qb_scorer_create_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, qb_scorer** out) {
+static qb_status scorer_create_custom_impl(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, const float* coef, uint32_t n_coef,
+                                           qb_scorer** out) {
     QB_CHECK(s && vectors && out, QB_ERR_INVALID, "scorer_create_custom: null argument");
     *out = nullptr;
     uint32_t ne = 0;
@@ -933,6 +934,10 @@ extern "C" qb_status qb_scorer_create_custom(qb_storage* s, qb_query_kind kind, 
         st = QB_ERR_CUDA;
     } else {
         st = prepare_queries(s, d_raw, ne, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_raw) + raw), sc->d_query, sc->d_q_off, sc->stream);
+        if (st == QB_OK && n_coef) {
+            if (cudaMalloc(&sc->d_coef, (size_t)n_coef * 4 + 256) != cudaSuccess) st = QB_ERR_OOM;
+            else if (cudaMemcpyAsync(sc->d_coef, coef, (size_t)n_coef * 4, cudaMemcpyHostToDevice, sc->stream) != cudaSuccess) st = QB_ERR_CUDA;
+        }
         if (st == QB_OK && cudaStreamSynchronize(sc->stream) != cudaSuccess) st = QB_ERR_CUDA;
     }
     cudaFree(d_raw);
@@ -941,9 +946,28 @@ extern "C" qb_status qb_scorer_create_custom(qb_storage* s, qb_query_kind kind, 
     return QB_OK;
 }
 
-extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, uint32_t top,
-                                      const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
-                                      qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters) {
+extern "C" qb_status qb_scorer_create_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, qb_scorer** out) {
+    QB_CHECK(kind != QB_QUERY_FEEDBACK_NAIVE, QB_ERR_INVALID, "scorer_create_custom: feedback queries carry coefficients, use qb_scorer_create_feedback");
+    return scorer_create_custom_impl(s, kind, vectors, n_a, n_b, nullptr, 0, out);
+}
+
+// [a, partial_computation...] as one host array
+static std::vector<float> feedback_coef(float a, const float* partial, uint32_t n_pairs) {
+    std::vector<float> c(1 + n_pairs);
+    c[0] = a;
+    for (uint32_t i = 0; i < n_pairs; ++i) c[1 + i] = partial[i];
+    return c;
+}
+
+extern "C" qb_status qb_scorer_create_feedback(qb_storage* s, const float* vectors, uint32_t n_pairs, float a, const float* partial, qb_scorer** out) {
+    QB_CHECK(n_pairs == 0 || partial, QB_ERR_INVALID, "scorer_create_feedback: null partial computations");
+    const std::vector<float> c = feedback_coef(a, partial, n_pairs);
+    return scorer_create_custom_impl(s, QB_QUERY_FEEDBACK_NAIVE, vectors, n_pairs, 0, c.data(), (uint32_t)c.size(), out);
+}
+
+static qb_status search_custom_impl(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, const float* coef, uint32_t n_coef, uint32_t top,
+                                    const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
+                                    qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters) {
     QB_CHECK(s && vectors && out && out_count, QB_ERR_INVALID, "search_custom: null argument");
     QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "search_custom: top %u outside [1,%u]", top, QB_MAX_TOP);
     uint32_t ne = 0;
@@ -973,7 +997,7 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
     QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)8));
     QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)n));
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)n));
-    QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, (size_t)ne * n * 4));
+    QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, (size_t)ne * n * 4 + (size_t)n_coef * 4 + 256));
     QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
     QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), ne,
                            reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + round_up_u64(raw_bytes, 16)), c->d_queries_enc, c->d_q_off, stream));
@@ -993,7 +1017,13 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
     }
     QbEmit emit{};
     emit.cand = c->d_cand; emit.cap = n; emit.dense = 1; emit.dense_base = 0; emit.deleted = s->d_deleted; emit.deleted2 = d_del2; emit.id_base = s->id_base;
-    QB_TRY(qb_launch_custom_combine((int)kind, n_a, n_b, d_sims, n, n, nullptr, c->d_ids, &emit, stream));
+    const float* d_coef = nullptr;
+    if (n_coef) {   // coefficients ride behind the similarity matrix
+        float* dc = d_sims + (size_t)ne * n;
+        QB_CUDA(cudaMemcpyAsync(dc, coef, (size_t)n_coef * 4, cudaMemcpyHostToDevice, stream));
+        d_coef = dc;
+    }
+    QB_TRY(qb_launch_custom_combine((int)kind, n_a, n_b, d_coef, d_sims, n, n, nullptr, c->d_ids, &emit, stream));
     QB_TRY(qb_launch_select(c->d_cand, nullptr, n, n, 1, top, 0, c->d_out, c->d_out_counts, nullptr, nullptr, stream));
     QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
     QB_CUDA(cudaMemcpyAsync(hs + raw_bytes + res_bytes, c->d_out_counts, 4, cudaMemcpyDeviceToHost, stream));
@@ -1002,6 +1032,22 @@ extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const f
     memcpy(out_count, hs + raw_bytes + res_bytes, 4);
     if (counters) { counters->cpu += n * (uint64_t)ne * cpu_units_per_point(s); counters->vector_io_read += n * (uint64_t)ne * io_units_per_point(s); }
     return QB_OK;
+}
+
+extern "C" qb_status qb_search_custom(qb_storage* s, qb_query_kind kind, const float* vectors, uint32_t n_a, uint32_t n_b, uint32_t top,
+                                      const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
+                                      qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters) {
+    QB_CHECK(kind != QB_QUERY_FEEDBACK_NAIVE, QB_ERR_INVALID, "search_custom: feedback queries carry coefficients, use qb_search_feedback");
+    return search_custom_impl(s, kind, vectors, n_a, n_b, nullptr, 0, top, deleted_bitmap, id_list, n_ids, is_stopped, out, out_count, counters);
+}
+
+extern "C" qb_status qb_search_feedback(qb_storage* s, const float* vectors, uint32_t n_pairs, float a, const float* partial, uint32_t top,
+                                        const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids, const volatile int32_t* is_stopped,
+                                        qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters) {
+    QB_CHECK(n_pairs == 0 || partial, QB_ERR_INVALID, "search_feedback: null partial computations");
+    const std::vector<float> c = feedback_coef(a, partial, n_pairs);
+    return search_custom_impl(s, QB_QUERY_FEEDBACK_NAIVE, vectors, n_pairs, 0, c.data(), (uint32_t)c.size(), top, deleted_bitmap, id_list, n_ids, is_stopped, out,
+                              out_count, counters);
 }
 
 // ------------------------------------------------------------------------------------------------ multivector MaxSim
@@ -1117,7 +1163,7 @@ extern "C" void qb_scorer_destroy(qb_scorer* sc) {
     if (!sc) return;
     cudaSetDevice(sc->st->device);
     if (sc->stream) cudaStreamSynchronize(sc->stream);
-    cudaFree(sc->d_query); cudaFree(sc->d_q_off); cudaFree(sc->d_ids); cudaFree(sc->d_scores); cudaFree(sc->d_sims);
+    cudaFree(sc->d_query); cudaFree(sc->d_q_off); cudaFree(sc->d_ids); cudaFree(sc->d_scores); cudaFree(sc->d_sims); cudaFree(sc->d_coef);
     if (sc->h_ids) cudaFreeHost(sc->h_ids);
     if (sc->h_scores) cudaFreeHost(sc->h_scores);
     if (sc->stream) cudaStreamDestroy(sc->stream);
@@ -1168,7 +1214,7 @@ static qb_status scorer_launch(qb_scorer* sc, const uint32_t* d_ids, uint64_t n,
     }
     for (uint32_t e = 0; e < sc->n_examples; ++e)
         QB_TRY(launch_example(s, sc->d_query, sc->d_q_off, e, false, d_ids, n, sc->d_sims + (size_t)e * sc->sims_cap, sc->stream));
-    return qb_launch_custom_combine(sc->custom_kind, sc->n_a, sc->n_b, sc->d_sims, sc->sims_cap, n, d_scores, nullptr, nullptr, sc->stream);
+    return qb_launch_custom_combine(sc->custom_kind, sc->n_a, sc->n_b, sc->d_coef, sc->d_sims, sc->sims_cap, n, d_scores, nullptr, nullptr, sc->stream);
 }
 
 extern "C" qb_status qb_score_points(qb_scorer* sc, const uint32_t* ids, size_t n, float* scores) {
@@ -1430,4 +1476,102 @@ extern "C" qb_status qb_hnsw_stats(qb_hnsw* g, uint64_t* hops, uint64_t* scored_
     if (scored_points) *scored_points = g->evals;
     if (reset) { g->hops = 0; g->evals = 0; }
     return QB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ sharded search: one collective call per shard
+// The reference runs one blocking task per segment and aggregates their lists (segments_searcher.rs:255, search_result_aggregator.rs:50-117);
+// here every shard's task calls qb_multi_search_batch with the same queries, and the aggregation happens on the GPUs (qb_comm.cu).
+extern "C" qb_status qb_multi_search_batch(qb_comm* cm, qb_storage* s, const float* queries, uint32_t n_queries, uint32_t top, const uint64_t* deleted_bitmap,
+                                           const volatile int32_t* is_stopped, qb_scored_point* out, uint32_t* out_counts, qb_hw_counters* counters) {
+    QB_CHECK(cm && s && out && out_counts, QB_ERR_INVALID, "multi_search_batch: null argument");
+    QB_CHECK(n_queries == 0 || queries, QB_ERR_INVALID, "multi_search_batch: null queries");
+    QB_CHECK(top >= 1, QB_ERR_INVALID, "multi_search_batch: top must be >= 1");
+    QB_CHECK(cm->device == s->device, QB_ERR_INVALID, "multi_search_batch: communicator on device %d, shard on device %d", cm->device, s->device);
+    if (n_queries == 0) return QB_OK;
+    QB_TRY(use_device(s->device));
+    std::lock_guard<std::mutex> clk(cm->mu);
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_acquire(s, &c));
+    struct Rel { qb_storage* s; QbSearchCtx* c; ~Rel() { qb_ctx_release(s, c); } } rel{s, c};
+    cudaStream_t stream = c->stream;
+    const size_t raw_bytes = (size_t)n_queries * s->dim * 4, res_bytes = (size_t)n_queries * top * sizeof(qb_scored_point), cnt_bytes = (size_t)n_queries * 4;
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + cnt_bytes + 32));
+    uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
+    memcpy(hs, queries, raw_bytes);
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, raw_bytes + (size_t)n_queries * pre_stride_f(s) * 4));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)n_queries + 256) * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)n_queries));
+    QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)n_queries * top));
+    QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)n_queries + 4));
+    if (cm->local_cap < (size_t)n_queries * top) {
+        cudaFree(cm->d_local); cudaFree(cm->d_local_cnt); cm->d_local = nullptr; cm->d_local_cnt = nullptr; cm->local_cap = 0;
+        QB_CUDA(cudaMalloc(&cm->d_local, (size_t)n_queries * top * sizeof(qb_scored_point)));
+        QB_CUDA(cudaMalloc(&cm->d_local_cnt, ((size_t)n_queries * top + 4) * 4));
+        cm->local_cap = (size_t)n_queries * top;
+    }
+    QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
+    float* d_pre = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + raw_bytes);
+    QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), n_queries, d_pre, c->d_queries_enc, c->d_q_off, stream));
+    const uint32_t* d_del2 = nullptr;
+    if (deleted_bitmap) {
+        const uint64_t words64 = ceil_div_u64(s->count, 64);
+        QB_TRY(ensure_dev_elems(&c->d_deleted2, &c->deleted2_words, (size_t)words64 * 2));
+        QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_bitmap, words64 * 8, cudaMemcpyHostToDevice, stream));
+        d_del2 = c->d_deleted2;
+    }
+    unsigned int* d_overflow = reinterpret_cast<unsigned int*>(cm->d_local_cnt + (size_t)n_queries * top);
+    uint8_t* h_res = hs + raw_bytes;
+    uint8_t* h_cnt = h_res + res_bytes;
+    uint32_t rs_flags = 0;
+    qb_status st_local = QB_OK;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        QB_CUDA(cudaMemsetAsync(d_overflow, 0, 4, stream));
+        bool can_flag = true;
+        st_local = run_search(s, c, n_queries, top, nullptr, 0, d_del2, is_stopped, rs_flags, cm->d_local, cm->d_local_cnt, d_overflow, &can_flag);
+        if (st_local != QB_OK || !can_flag) break;
+        QB_CUDA(cudaMemcpyAsync(h_cnt + cnt_bytes, d_overflow, 4, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaStreamSynchronize(stream));
+        unsigned int flags = 0;
+        memcpy(&flags, h_cnt + cnt_bytes, 4);
+        uint32_t next = rs_flags;
+        if (flags & 8u) next |= RS_NO_SEGMENTS;
+        if (flags & 2u) next |= RS_NO_MMA;
+        if (flags & 1u) next |= RS_FORCE_DIRECT | RS_NO_MMA;
+        if (next == rs_flags) break;
+        s->n_reruns.fetch_add(1, std::memory_order_relaxed);
+        rs_flags = next;
+    }
+    s->n_searches.fetch_add(1, std::memory_order_relaxed);
+    // a rank that failed locally still joins the exchange (with empty lists) so that its peers do not wait for it
+    if (st_local != QB_OK) QB_CUDA(cudaMemsetAsync(cm->d_local_cnt, 0, (size_t)n_queries * 4, stream));
+    QB_TRY(qb_comm_exchange_merge(cm, cm->d_local, cm->d_local_cnt, n_queries, top, c->d_out, c->d_out_counts, stream));
+    QB_CUDA(cudaMemcpyAsync(h_res, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaMemcpyAsync(h_cnt, c->d_out_counts, cnt_bytes, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaMemcpyAsync(h_cnt + cnt_bytes + 8, cm->d_error, 4, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaStreamSynchronize(stream));
+    unsigned int xerr = 0;
+    memcpy(&xerr, h_cnt + cnt_bytes + 8, 4);
+    QB_CHECK(xerr == 0, QB_ERR_CUDA, "multi_search_batch: a peer rank never joined the exchange (timeout)");
+    if (st_local != QB_OK) return st_local;
+    memcpy(out, h_res, res_bytes);
+    memcpy(out_counts, h_cnt, cnt_bytes);
+    if (counters) {
+        counters->cpu += s->count * (uint64_t)n_queries * cpu_units_per_point(s);
+        counters->vector_io_read += s->count * (uint64_t)n_queries * io_units_per_point(s);
+    }
+    return QB_OK;
+}
+
+// device-resident form: queries / outputs in HBM, enqueued on qb_storage_stream(s).  dev_local / dev_local_counts receive this shard's own
+// lists (n_queries x top) and must stay valid until the stream has run the exchange.
+extern "C" qb_status qb_multi_search_batch_device(qb_comm* cm, qb_storage* s, const float* dev_queries, uint32_t n_queries, uint32_t top, qb_scored_point* dev_local,
+                                                  uint32_t* dev_local_counts, qb_scored_point* dev_out, uint32_t* dev_counts) {
+    QB_CHECK(cm && s && dev_queries && dev_local && dev_local_counts && dev_out && dev_counts, QB_ERR_INVALID, "multi_search_batch_device: null argument");
+    QB_CHECK(cm->device == s->device, QB_ERR_INVALID, "multi_search_batch_device: communicator and shard on different devices");
+    if (n_queries == 0) return QB_OK;
+    QB_TRY(qb_search_batch_device(s, dev_queries, n_queries, top, dev_local, dev_local_counts));
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_device(s, &c));
+    std::lock_guard<std::mutex> clk(cm->mu);
+    return qb_comm_exchange_merge(cm, dev_local, dev_local_counts, n_queries, top, dev_out, dev_counts, c->stream);
 }

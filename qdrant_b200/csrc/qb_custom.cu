@@ -9,6 +9,7 @@
 //   RecoSumScores  query/reco_query.rs:116-133   sequential f32 sums, positives minus negatives
 //   Discover       query/discover_query.rs:16-76 rank = sum of total_cmp(positive, negative) per pair, + sigmoid(target)
 //   Context        query/context_query.rs:52-62,111-119   sum over pairs of fast_sigmoid(min(p - n - EPSILON, 0))
+//   Feedback       query/feedback_query.rs:204-226 a * sim(target) + sum over pairs of partial_computation * (sim(pos) - sim(neg))
 //   MaxSim         query_scorer/mod.rs:77-98     multivectors: sum over query tokens of the best similarity to a point's tokens
 // fast_sigmoid = x / (1 + |x|), scaled_fast_sigmoid = 0.5 * (fast_sigmoid(x) + 1)   (lib/common/common/src/math.rs:7-18)
 #include "qb_internal.h"
@@ -25,8 +26,16 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdiv_rn(x, __f
 __device__ __forceinline__ float scaled_fast_sigmoid(float x) { return __fmul_rn(0.5f, __fadd_rn(fast_sigmoid(x), 1.0f)); }
 
 // sims: [n_examples][stride] similarities, example-major
-__device__ __forceinline__ float combine(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ sims, uint64_t stride, uint64_t i) {
+__device__ __forceinline__ float combine(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ coef, const float* __restrict__ sims, uint64_t stride, uint64_t i) {
     switch (kind) {
+        case QB_QUERY_FEEDBACK_NAIVE: {  // coef = [a, partial_computation of pair 0, 1, ...]; `score += partial * delta` is a multiply then an add in Rust
+            float score = __fmul_rn(coef[0], sims[i]);
+            for (uint32_t e = 0; e < n_a; ++e) {
+                const float delta = __fsub_rn(sims[(1 + 2 * e) * stride + i], sims[(2 + 2 * e) * stride + i]);
+                score = __fadd_rn(score, __fmul_rn(coef[1 + e], delta));
+            }
+            return score;
+        }
         case QB_QUERY_RECO_BEST_SCORE: {
             float max_p = __int_as_float(0xff800000), max_n = __int_as_float(0xff800000);
             for (uint32_t e = 0; e < n_a; ++e) { const float s = sims[e * stride + i]; if (total_cmp(s, max_p) > 0) max_p = s; }
@@ -55,10 +64,10 @@ __device__ __forceinline__ float combine(int kind, uint32_t n_a, uint32_t n_b, c
     }
 }
 
-__global__ void custom_combine_kernel(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ sims, uint64_t stride, uint64_t n, float* __restrict__ scores,
+__global__ void custom_combine_kernel(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ coef, const float* __restrict__ sims, uint64_t stride, uint64_t n, float* __restrict__ scores,
                                       const uint32_t* __restrict__ ids, QbEmit emit, int to_keys) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float sc = combine(kind, n_a, n_b, sims, stride, i);
+        const float sc = combine(kind, n_a, n_b, coef, sims, stride, i);
         if (to_keys) qb_emit(emit, 0, i, ids ? ids[i] : (uint32_t)i, sc);
         else scores[i] = sc;
     }
@@ -94,20 +103,21 @@ uint32_t qb_custom_examples(int kind, uint32_t n_a, uint32_t n_b) {
     switch (kind) {
         case QB_QUERY_RECO_BEST_SCORE:
         case QB_QUERY_RECO_SUM_SCORES: return n_a + n_b;
-        case QB_QUERY_DISCOVER: return 1 + 2 * n_a;
+        case QB_QUERY_DISCOVER:
+        case QB_QUERY_FEEDBACK_NAIVE: return 1 + 2 * n_a;
         case QB_QUERY_CONTEXT: return 2 * n_a;
         default: return 0;
     }
 }
 
 // scores (to_keys = 0) or dense-mode candidate keys for query slot 0 of `emit` (to_keys = 1; ids = null means row i)
-qb_status qb_launch_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* d_sims, uint64_t stride, uint64_t n, float* d_scores, const uint32_t* d_ids,
+qb_status qb_launch_custom_combine(int kind, uint32_t n_a, uint32_t n_b, const float* d_coef, const float* d_sims, uint64_t stride, uint64_t n, float* d_scores, const uint32_t* d_ids,
                                    const QbEmit* emit, cudaStream_t stream) {
     if (n == 0) return QB_OK;
     QbEmit e{};
     if (emit) e = *emit;
     const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div_u64(n, 256), 148ull * 16);
-    custom_combine_kernel<<<grid, 256, 0, stream>>>(kind, n_a, n_b, d_sims, stride, n, d_scores, d_ids, e, emit ? 1 : 0);
+    custom_combine_kernel<<<grid, 256, 0, stream>>>(kind, n_a, n_b, d_coef, d_sims, stride, n, d_scores, d_ids, e, emit ? 1 : 0);
     QB_LAUNCHED();
     QB_CUDA(cudaGetLastError());
     return QB_OK;

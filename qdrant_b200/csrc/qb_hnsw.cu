@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
         if (tid == 0) { s_cur = p.entry; s_cur_score = sm.sc[0]; ++hops; ++evals; }
         __syncthreads();
         for (uint32_t lvl = p.entry_level; lvl >= 1; --lvl) {
+            // search_entry_on_level re-scores its entry point on every level (graph_layers.rs:298-301): same value, but the scorer call
+            // and the scored point are metered, so they are counted here too
+            if (tid == 0 && lvl != p.entry_level) { ++hops; ++evals; }
             for (;;) {
                 const uint32_t cur = s_cur;
                 // links of `cur` on this level: neighbors[offsets[idx] .. offsets[idx + 1]), idx = level_offsets[lvl] + reindex[cur] (view.rs:203-215)

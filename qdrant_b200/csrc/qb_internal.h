@@ -106,6 +106,7 @@ struct qb_scorer {
     // custom queries (recommend / discover / context): d_query holds n_examples encoded queries, d_q_off their SQ8 offsets
     int custom_kind = 0;  uint32_t n_a = 0, n_b = 0, n_examples = 1;
     float* d_sims = nullptr;  size_t sims_cap = 0;          // [n_examples][cap] per-example similarities
+    float* d_coef = nullptr;                                // feedback query: [a, partial_computation per pair]
     qb_hw_counters hw = {0, 0};
 };
 
@@ -131,6 +132,23 @@ struct qb_hnsw {
 qb_status qb_hnsw_launch(qb_hnsw* g, const void* d_q_enc, const float* d_q_off, uint32_t nq, uint32_t top, uint32_t ef, uint32_t entry, uint32_t entry_level,
                          const uint32_t* d_deleted2, qb_scored_point* d_out, uint32_t* d_counts, cudaStream_t stream);
 qb_status qb_hnsw_read_stats(qb_hnsw* g, cudaStream_t stream);
+
+// One rank of a sharded search (qb_comm.cu): an exchange buffer every peer maps + the peers' buffers
+constexpr uint32_t QB_MAX_WORLD = 16;
+struct qb_comm {
+    int device = 0, rank = 0, world = 1, sm_count = 148;
+    uint32_t max_q = 0, max_top = 0;
+    void* d_buf = nullptr; uint64_t bytes = 0;
+    uint8_t* peers[QB_MAX_WORLD] = {};
+    bool ipc_opened[QB_MAX_WORLD] = {};
+    bool connected = false;
+    uint32_t seq = 0;
+    unsigned int* d_error = nullptr;
+    qb_scored_point* d_local = nullptr; uint32_t* d_local_cnt = nullptr; size_t local_cap = 0;   // this shard's lists (host-facing entry)
+    std::mutex mu;
+};
+qb_status qb_comm_exchange_merge(qb_comm* c, const qb_scored_point* d_local, const uint32_t* d_local_cnt, uint32_t nq, uint32_t top, qb_scored_point* d_out,
+                                 uint32_t* d_out_cnt, cudaStream_t stream);
 
 // ---------------------------------------------------------------- helpers (qb_api.cu)
 qb_status qb_ensure_device(void** p, size_t* have, size_t need_bytes);

@@ -17,6 +17,8 @@
 //        (encoded_vectors_u8.rs:101-103).
 //   PQ   four f32 lanes, lane k sums chunks j = k (mod 4) in ascending j; (s0+s2)+(s1+s3); tail sequential.
 //   BQ   popcounts are integers; the float epilogue of calculate_metric is restated literally.
+#include <cooperative_groups.h>
+
 #include "qb_internal.h"
 #include "qb_score.cuh"
 
@@ -259,6 +261,87 @@ __global__ void __launch_bounds__(1024, 1) pq_scan2_kernel(const PqParams p, con
             qb_emit(emit, q, cand, row, sa);
             if (two) qb_emit(emit, q + 1, cand, row, sb);
         }
+    }
+}
+
+// Four queries per pass on a CTA PAIR (thread-block cluster of 2): the four LUTs are interleaved as float4, so ONE 16-byte shared
+// load serves four queries and — more to the point on random codes — a quarter-warp's 8 gathers spread over 8 sixteen-byte bank
+// groups collide far less than 32 four-byte gathers over 32 banks (expected serialisation ~2.4x instead of ~3.5x).  Four
+// interleaved LUTs are 4 x m x 256 x 4 B = 384 KB at m = 96: CTA 0 holds chunks [0, m/2), CTA 1 chunks [m/2, m).  CTA 0 runs the
+// first half of every row's four-lane accumulation, hands the 16 partial sums (4 lanes x 4 queries) to CTA 1 through DISTRIBUTED
+// SHARED MEMORY (double-buffered, one cluster barrier per 256-row tile), CTA 1 continues the very same f32 chains — lane k keeps
+// adding chunks j = k (mod 4) in ascending j — and finishes with (s0+s2)+(s1+s3): score_point_sse's order exactly
+// (encoded_vectors_pq.rs:411-443).  Requires m % 32 == 0 (16-byte code loads per half), m <= 96 (LUT half <= 192 KB).
+// The launcher walks the code plane in L2-sized row blocks and runs ALL query quads over a block before moving on, so HBM
+// sees every code byte once per batch instead of once per query group.
+constexpr int PQ4_THREADS = 256;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_scan4_kernel(const PqParams p, const QbEmit emit) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) float lut_s[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();
+    const uint32_t K = p.n_centroids, mh = p.m >> 1, j0 = rank * mh;
+    float4* lut4 = reinterpret_cast<float4*>(lut_s);                 // [mh][K]
+    float4* hand = lut4 + (size_t)mh * K;                            // [2 stages][4][PQ4_THREADS]   (CTA 1's copy is the one in use)
+    float4* hand_remote = cluster.map_shared_rank(hand, 1);          // CTA 0 writes into CTA 1's buffer
+    const int tid = threadIdx.x;
+    const uint64_t n = p.end - p.begin;
+    const uint64_t n_tiles = (n + PQ4_THREADS - 1) / PQ4_THREADS;
+    const uint32_t cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const size_t lut_elems = (size_t)p.m * K;
+    for (uint32_t q0 = 0; q0 < p.nq; q0 += 4) {
+        // ---- interleaved LUT half of this CTA: lut4[jl][c] = (lut_q0, lut_q0+1, lut_q0+2, lut_q0+3)[j0 + jl][c]
+        const float* l0 = p.luts + (size_t)q0 * lut_elems + (size_t)j0 * K;
+        const float* l1 = (q0 + 1 < p.nq) ? l0 + lut_elems : l0;
+        const float* l2 = (q0 + 2 < p.nq) ? l0 + 2 * lut_elems : l0;
+        const float* l3 = (q0 + 3 < p.nq) ? l0 + 3 * lut_elems : l0;
+        for (uint32_t i = tid; i < mh * K; i += PQ4_THREADS) lut4[i] = make_float4(l0[i], l1[i], l2[i], l3[i]);
+        __syncthreads();
+        uint32_t it = 0;
+        for (uint64_t t = cid; t < n_tiles; t += n_clusters, ++it) {
+            const uint64_t ci = t * PQ4_THREADS + tid;
+            const bool valid = ci < n;
+            const uint64_t cand = p.begin + (valid ? ci : 0);
+            const uint8_t* code = p.codes + (size_t)cand * p.stride + j0;
+            float4 s0, s1, s2, s3;
+            float4* hb = (rank == 0 ? hand_remote : hand) + (size_t)(it & 1u) * 4 * PQ4_THREADS;
+            if (rank == 0) {
+                s0 = s1 = s2 = s3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                cluster.sync();                                       // tile `it` of CTA 0 has landed in hand[it & 1]
+                s0 = hb[0 * PQ4_THREADS + tid]; s1 = hb[1 * PQ4_THREADS + tid]; s2 = hb[2 * PQ4_THREADS + tid]; s3 = hb[3 * PQ4_THREADS + tid];
+            }
+            for (uint32_t j = 0; j < mh; j += 16) {
+                const uint4 cw = *reinterpret_cast<const uint4*>(code + j);
+                const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4* l = lut4 + (size_t)(j + 4 * k) * K;
+                    const float4 a = l[w[k] & 255u], b = l[K + ((w[k] >> 8) & 255u)], c = l[2 * K + ((w[k] >> 16) & 255u)], d = l[3 * K + (w[k] >> 24)];
+                    s0.x = __fadd_rn(s0.x, a.x); s0.y = __fadd_rn(s0.y, a.y); s0.z = __fadd_rn(s0.z, a.z); s0.w = __fadd_rn(s0.w, a.w);
+                    s1.x = __fadd_rn(s1.x, b.x); s1.y = __fadd_rn(s1.y, b.y); s1.z = __fadd_rn(s1.z, b.z); s1.w = __fadd_rn(s1.w, b.w);
+                    s2.x = __fadd_rn(s2.x, c.x); s2.y = __fadd_rn(s2.y, c.y); s2.z = __fadd_rn(s2.z, c.z); s2.w = __fadd_rn(s2.w, c.w);
+                    s3.x = __fadd_rn(s3.x, d.x); s3.y = __fadd_rn(s3.y, d.y); s3.z = __fadd_rn(s3.z, d.z); s3.w = __fadd_rn(s3.w, d.w);
+                }
+            }
+            if (rank == 0) {
+                hb[0 * PQ4_THREADS + tid] = s0; hb[1 * PQ4_THREADS + tid] = s1; hb[2 * PQ4_THREADS + tid] = s2; hb[3 * PQ4_THREADS + tid] = s3;
+                cluster.sync();                                       // release tile `it` to CTA 1 (and: CTA 1 is done with hand[(it + 1) & 1])
+            } else if (valid) {
+                const uint32_t row = (uint32_t)cand;
+                const float r0 = __fadd_rn(__fadd_rn(s0.x, s2.x), __fadd_rn(s1.x, s3.x));
+                const float r1 = __fadd_rn(__fadd_rn(s0.y, s2.y), __fadd_rn(s1.y, s3.y));
+                const float r2 = __fadd_rn(__fadd_rn(s0.z, s2.z), __fadd_rn(s1.z, s3.z));
+                const float r3 = __fadd_rn(__fadd_rn(s0.w, s2.w), __fadd_rn(s1.w, s3.w));
+                qb_emit(emit, q0, cand, row, r0);
+                if (q0 + 1 < p.nq) qb_emit(emit, q0 + 1, cand, row, r1);
+                if (q0 + 2 < p.nq) qb_emit(emit, q0 + 2, cand, row, r2);
+                if (q0 + 3 < p.nq) qb_emit(emit, q0 + 3, cand, row, r3);
+            }
+        }
+        // both CTAs meet before the LUTs / hand-off buffers are reused by the next quad (and before either may exit: a CTA's shared
+        // memory must outlive its peer's last remote access)
+        cluster.sync();
     }
 }
 
@@ -518,7 +601,23 @@ static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cu
     if (n == 0 || p.nq == 0) return QB_OK;
     p.codes = s->d_pq_codes; p.stride = s->pq_stride; p.m = s->pq_m; p.n_centroids = s->n_centroids;
     const size_t lut_bytes = (size_t)s->pq_m * s->n_centroids * sizeof(float);
-    if (p.emit_mode && p.nq >= 2 && 2 * lut_bytes <= 224 * 1024 && n >= 65536) {
+    const int qpp = qb_opt().pq_queries_per_pass;   // 0 = automatic; 1 / 2 / 4 force a kernel (experiments)
+    const size_t smem4 = 2 * lut_bytes + (size_t)2 * 4 * PQ4_THREADS * 16;   // interleaved LUT half (4 queries x m/2 chunks) + hand-off stages
+    if (p.emit_mode && !p.ids && (qpp == 0 || qpp == 4) && p.nq >= 3 && s->pq_m % 32 == 0 && smem4 <= 227 * 1024 && n >= 65536 && s->sm_count >= 2) {
+        // batched scans: four queries per pass on CTA pairs; row blocks sized to stay in L2 while every query quad visits them
+        QB_CUDA(cudaFuncSetAttribute(pq_scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        const uint64_t block_rows = std::max<uint64_t>(65536, (48ull << 20) / s->pq_stride);
+        const unsigned grid = (unsigned)(s->sm_count & ~1);
+        for (uint64_t b0 = p.begin; b0 < p.end; b0 += block_rows) {
+            PqParams pb = p;
+            pb.begin = b0; pb.end = std::min<uint64_t>(p.end, b0 + block_rows);
+            pq_scan4_kernel<<<grid, PQ4_THREADS, smem4, stream>>>(pb, e);
+            QB_LAUNCHED();
+        }
+        QB_CUDA(cudaGetLastError());
+        return QB_OK;
+    }
+    if (p.emit_mode && (qpp == 0 || qpp == 2 || qpp == 4) && p.nq >= 2 && 2 * lut_bytes <= 224 * 1024 && n >= 65536) {
         // batched scans: two queries per pass (interleaved LUTs)
         QB_CUDA(cudaFuncSetAttribute(pq_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         uint64_t blocks2 = ceil_div_u64(n, 1024);

@@ -104,6 +104,7 @@ class QueryKind(enum.IntEnum):  # QueryVector variants beyond Nearest (data_type
     RecommendSumScores = 2
     Discover = 3
     Context = 4
+    FeedbackNaive = 5
 
 
 class RecoQuery:
@@ -157,6 +158,23 @@ class ContextQuery:
 
     def flat(self):
         return [v for p in self.pairs for v in (p.positive, p.negative)], len(self.pairs), 0
+
+
+class FeedbackQuery:
+    """vector_storage/query/feedback_query.rs:150-226 — the scoring form of NaiveFeedbackQuery: a target, context pairs with their
+    partial_computation (confidence^b * c, derived from the feedback scores by the host exactly as FeedbackQuery::new does) and the
+    coefficient `a`."""
+    kind = QueryKind.FeedbackNaive
+
+    def __init__(self, target, pairs: Sequence[ContextPair], partial_computations, a: float):
+        self.target = np.asarray(target, dtype=np.float32)
+        self.pairs = list(pairs)
+        self.partial = np.ascontiguousarray(partial_computations, dtype=np.float32).reshape(-1)
+        self.a = float(a)
+        assert self.partial.size == len(self.pairs)
+
+    def flat(self):
+        return [self.target] + [v for p in self.pairs for v in (p.positive, p.negative)], len(self.pairs), 0
 
 
 class RawScorer:
@@ -237,7 +255,11 @@ class _Storage:
         """new_raw_scorer for QueryVector::{RecommendBestScore, RecommendSumScores, Discover, Context} (raw_scorer.rs:228-333)."""
         m, n_a, n_b = self._flat_custom(query)
         h = vp()
-        check(lib().qb_scorer_create_custom(self._h, int(query.kind), m.ctypes.data_as(f32p), n_a, n_b, C.byref(h)))
+        if query.kind == QueryKind.FeedbackNaive:
+            check(lib().qb_scorer_create_feedback(self._h, m.ctypes.data_as(f32p), n_a, C.c_float(query.a),
+                                                  query.partial.ctypes.data_as(f32p) if n_a else None, C.byref(h)))
+        else:
+            check(lib().qb_scorer_create_custom(self._h, int(query.kind), m.ctypes.data_as(f32p), n_a, n_b, C.byref(h)))
         return RawScorer(self, h.value)
 
     def search_custom(self, query, top: int, point_deleted=None, id_list=None, counters: Optional[HwCounters] = None):
@@ -247,11 +269,13 @@ class _Storage:
         count = C.c_uint32()
         bm = _bitmap(point_deleted, self.count)
         ids = None if id_list is None else _ids(id_list)
-        check(lib().qb_search_custom(
-            self._h, int(query.kind), m.ctypes.data_as(f32p), n_a, n_b, int(top),
-            None if bm is None else bm.ctypes.data_as(u64p),
-            None if ids is None else ids.ctypes.data_as(u32p), 0 if ids is None else ids.size, None,
-            out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(count), None if counters is None else C.byref(counters)))
+        tail = (None if bm is None else bm.ctypes.data_as(u64p), None if ids is None else ids.ctypes.data_as(u32p), 0 if ids is None else ids.size, None,
+                out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(count), None if counters is None else C.byref(counters))
+        if query.kind == QueryKind.FeedbackNaive:
+            check(lib().qb_search_feedback(self._h, m.ctypes.data_as(f32p), n_a, C.c_float(query.a), query.partial.ctypes.data_as(f32p) if n_a else None,
+                                           int(top), *tail))
+        else:
+            check(lib().qb_search_custom(self._h, int(query.kind), m.ctypes.data_as(f32p), n_a, n_b, int(top), *tail))
         return out[: count.value].copy()
 
     def _raw_internal_scorer(self, point_id: int) -> RawScorer:

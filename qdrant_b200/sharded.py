@@ -3,8 +3,10 @@
 The reference searches independent segments on separate blocking tasks and merges their top-k lists on the host
 (SegmentsSearcher, lib/collection/src/collection_manager/segments_searcher.rs:212-345 -> BatchResultAggregator,
 lib/shard/src/search_result_aggregator.rs:50-117).  Here every rank holds one shard in HBM, runs the fused scan
-locally, and the ONLY exchange is an all-gather of `n_queries x top x 8 B` per rank over NCCL/NVLink, followed by
-a device-side merge (qb_topk_merge_device).  torch is used for device buffers, streams and torch.distributed only.
+locally, and the ONLY exchange is `n_queries x top x 8 B` per rank: written by the library's exchange kernel straight into
+every peer's mapped buffer over NVLink and merged there (qb_comm_* / qb_multi_search_batch*, qdrant_b200/csrc/qb_comm.cu).
+torch.distributed only carries the 64-byte IPC handles at start-up; torch is otherwise used for device buffers and streams.
+`exchange="nccl"` keeps the round-1 path (two NCCL all-gathers + qb_topk_merge_device) for comparison.
 """
 from __future__ import annotations
 
@@ -41,11 +43,24 @@ def merge_topk_host(lists, top: int) -> np.ndarray:
 
 
 class ShardedSegmentSearcher:
-    def __init__(self, storage: _Storage, id_base: int, top: int, max_queries: int, device: torch.device):
+    def __init__(self, storage: _Storage, id_base: int, top: int, max_queries: int, device: torch.device, exchange: str = "peer"):
         self.storage, self.top, self.max_queries, self.device = storage, int(top), int(max_queries), device
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         check(lib().qb_storage_set_id_base(storage._h, int(id_base)))
+        self.comm = vp()
+        self.exchange = exchange if self.world > 1 else "none"
+        if self.exchange == "peer":
+            h = vp()
+            check(lib().qb_comm_create(device.index, self.rank, self.world, self.max_queries, self.top, C.byref(h)))
+            self.comm = h
+            mine = (C.c_uint8 * 64)()
+            check(lib().qb_comm_local_handle(self.comm, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine))      # 64 bytes per rank, once
+            blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+            check(lib().qb_comm_connect(self.comm, blob))
+            dist.barrier()
         self.stream = torch.cuda.ExternalStream(storage.stream_ptr(), device=device)
         nq, k, w = self.max_queries, self.top, self.world
         # ScoredPointOffset = 8 bytes -> int64 tensors as opaque 8-byte records
@@ -63,6 +78,11 @@ class ShardedSegmentSearcher:
 
     # ---- device-resident step: queries already in self.d_queries[:nq]; results land in self.d_out / d_out_cnt
     def search_device(self, nq: int) -> None:
+        if self.exchange == "peer":
+            # local fused scan + select, then ONE kernel: push this shard's lists into every peer's buffer, wait for theirs, merge
+            check(lib().qb_multi_search_batch_device(self.comm, self.storage._h, vp(self.d_queries.data_ptr()), nq, self.top, vp(self.d_local.data_ptr()),
+                                                     vp(self.d_local_cnt.data_ptr()), vp(self.d_out.data_ptr()), vp(self.d_out_cnt.data_ptr())))
+            return
         with torch.cuda.stream(self.stream):
             check(lib().qb_search_batch_device(self.storage._h, vp(self.d_queries.data_ptr()), nq, self.top,
                                                vp(self.d_local.data_ptr()), vp(self.d_local_cnt.data_ptr())))
@@ -84,6 +104,14 @@ class ShardedSegmentSearcher:
         assert nq <= self.max_queries
         if self.world == 1:
             return self.storage.search_batch(q, self.top)  # the plain C-ABI call (qb_search_batch)
+        if self.exchange == "peer":
+            # the C-ABI collective with HOST buffers: H2D of the queries, scan, exchange + merge, D2H of the merged lists, all inside
+            from ._capi import ScoredPoint, f32p, u32p
+            out = np.zeros((nq, self.top), dtype=SCORED_POINT_OFFSET)
+            counts = np.zeros(nq, dtype=np.uint32)
+            check(lib().qb_multi_search_batch(self.comm, self.storage._h, q.ctypes.data_as(f32p), nq, self.top, None, None,
+                                              out.ctypes.data_as(C.POINTER(ScoredPoint)), counts.ctypes.data_as(u32p), None))
+            return [out[i, : counts[i]].copy() for i in range(nq)]
         self.h_queries[:nq].copy_(torch.from_numpy(q))
         with torch.cuda.stream(self.stream):
             self.d_queries[:nq].copy_(self.h_queries[:nq], non_blocking=True)
@@ -95,6 +123,20 @@ class ShardedSegmentSearcher:
         rec = self.h_out.numpy().view(SCORED_POINT_OFFSET).reshape(self.max_queries, self.top)
         cnt = self.h_out_cnt.numpy()
         return [rec[i, : cnt[i]].copy() for i in range(nq)]
+
+    def close(self):
+        if self.comm:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier()          # no rank unmaps its buffer while a peer may still write into it
+            lib().qb_comm_destroy(self.comm)
+            self.comm = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def results_host(self, nq: int):
         """Copy the device results of the last search_device() to the host (synchronises)."""

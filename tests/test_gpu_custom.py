@@ -30,13 +30,29 @@ def make_queries(qb, rng, dim):
         qb.DiscoverQuery(v(), [qb.ContextPair(v(), v()), qb.ContextPair(v(), v()), qb.ContextPair(v(), v())]),
         qb.DiscoverQuery(v(), []),
         qb.ContextQuery([qb.ContextPair(v(), v()), qb.ContextPair(v(), v())]),
+        feedback_query(qb, rng, dim, 4),
+        feedback_query(qb, rng, dim, 1),     # fewer than two feedback items: no pairs, score = a * sim(target)
     ]
+
+
+def feedback_query(qb, rng, dim, n_items):
+    """NaiveFeedbackQuery -> FeedbackQuery the way the reference builds it (feedback_query.rs:121-172): every ordered pair of feedback
+    items whose score difference is positive becomes a context pair with partial_computation = confidence^b * c."""
+    from oracle import oracle as o
+
+    items = [rng.standard_normal(dim).astype(np.float32) for _ in range(n_items)]
+    scores = rng.random(n_items).astype(np.float32)
+    a, b, c = 0.9, 1.5, 0.4
+    pos, neg, part = o.feedback_pairs(scores, b, c)
+    return qb.FeedbackQuery(rng.standard_normal(dim).astype(np.float32), [qb.ContextPair(items[i], items[j]) for i, j in zip(pos, neg)], part, a)
 
 
 def oracle_scores(oracle, query, sim_rows):
     """sim_rows(example_vector) -> similarities of every candidate to that example (np.float32 array)."""
     vecs, n_a, n_b = query.flat()
     sims = np.stack([sim_rows(v) for v in vecs])
+    if int(query.kind) == 5:   # FeedbackQuery::score_by (feedback_query.rs:204-226)
+        return oracle.feedback_score(query.a, query.partial, sims)
     return oracle.custom_combine(int(query.kind), n_a, n_b, sims)
 
 

@@ -4,7 +4,7 @@ equal) and identical scorer-call / scored-point counts => recall difference 0 (n
 import numpy as np
 import pytest
 
-from tests.util import assert_topk_equal
+from tests.util import assert_topk_equal, pack_bitmap
 
 pytestmark = pytest.mark.gpu
 
@@ -62,7 +62,7 @@ def test_device_traversal_with_filter(qb, oracle):
     deleted[entry] = False                    # get_entry_point would pick another entry for a filtered-out one (host logic)
     st = qb.DenseVectorStorage(base, qb.Distance.Cosine)
     hg = qb.HnswGraph(st, blob, m, m0)
-    want = g.search_batch(qp, 10, 64, deleted=deleted)
+    want = g.search_batch(qp, 10, 64, deleted=pack_bitmap(deleted))
     got = hg.search(queries, 10, 64, entry, lvl, point_deleted=deleted)
     for a, b in zip(got, want):
         assert_topk_equal(a, b, what="filtered")

@@ -1,0 +1,70 @@
+"""Sharded search through the C ABI (qb_comm_* / qb_multi_search_batch): W shards, one host thread per shard (the reference's
+one-blocking-task-per-segment model, segments_searcher.rs:255), lists exchanged through peer-mapped buffers and merged on the
+device.  Shards are spread over the visible GPUs; on a single-GPU box they share device 0, which exercises the same exchange
+protocol (flags, parity slots, merge) through same-device pointers — so the sharded == single gate runs everywhere."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qb():
+    from qdrant_b200 import scorer
+
+    return scorer
+
+
+@pytest.mark.parametrize("world,nq,top,n,dim", [(2, 1, 10, 150_003, 64), (3, 5, 10, 90_001, 96), (4, 40, 7, 70_000, 32), (8, 1, 10, 80_000, 128)])
+def test_sharded_equals_single_through_the_c_abi(qb, oracle, world, nq, top, n, dim):
+    import torch
+
+    from qdrant_b200._capi import ScoredPoint, check, f32p, lib, u32p, vp
+    from qdrant_b200.sharded import shard_ranges
+
+    n_dev = torch.cuda.device_count()
+    rng = np.random.default_rng(world)
+    base = oracle.preprocess_rows_f32(oracle.COSINE, rng.standard_normal((n, dim)).astype(np.float32))
+    queries = rng.standard_normal((6, nq, dim)).astype(np.float32)          # six consecutive collective calls (parity slots, seq)
+    single = qb.DenseVectorStorage(base, qb.Distance.Cosine)
+    shards, comms = [], (vp * world)()
+    for r, (b, e) in enumerate(shard_ranges(n, world)):
+        st = qb.DenseVectorStorage(base[b:e], qb.Distance.Cosine, device=r % n_dev)
+        check(lib().qb_storage_set_id_base(st._h, b))
+        shards.append(st)
+        h = vp()
+        check(lib().qb_comm_create(r % n_dev, r, world, 64, 16, C.byref(h)))
+        comms[r] = h
+    check(lib().qb_comm_connect_local(comms, world))
+    results = [[None] * 6 for _ in range(world)]
+    errors = []
+
+    def task(r):
+        try:
+            for it in range(6):
+                q = np.ascontiguousarray(queries[it])
+                out = np.zeros((nq, top), dtype=qb.SCORED_POINT_OFFSET); cnt = np.zeros(nq, np.uint32)
+                check(lib().qb_multi_search_batch(comms[r], shards[r]._h, q.ctypes.data_as(f32p), nq, top, None, None,
+                                                  out.ctypes.data_as(C.POINTER(ScoredPoint)), cnt.ctypes.data_as(u32p), None))
+                results[r][it] = [out[i, : cnt[i]].copy() for i in range(nq)]
+        except Exception as ex:   # noqa: BLE001
+            errors.append((r, ex))
+
+    th = [threading.Thread(target=task, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errors, errors
+    for it in range(6):
+        want = single.search_batch(queries[it], top)
+        for r in range(world):
+            for i in range(nq):
+                np.testing.assert_array_equal(results[r][it][i], want[i], err_msg=f"world {world} rank {r} call {it} query {i}")
+    for r in range(world):
+        lib().qb_comm_destroy(comms[r])
+        shards[r].close()
+    single.close()

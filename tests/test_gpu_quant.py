@@ -144,6 +144,36 @@ def test_pq_search_batch(qb, oracle):
     st.close()
 
 
+@pytest.mark.parametrize("dist,n,dim,chunk,nq", [("Dot", 70_000, 128, 4, 5), ("Euclid", 66_000, 128, 2, 8), ("Cosine", 70_001, 1536, 16, 7), ("Manhattan", 131_000, 64, 2, 3)])
+def test_pq_batched_four_query_cluster_kernel(qb, oracle, dist, n, dim, chunk, nq):
+    """pq_scan4_kernel (m % 32 == 0: CTA pair, float4-interleaved LUT halves, partial sums handed over through distributed shared
+    memory) == oracle score_point_sse order, bit-exact, for every queries-per-pass variant, with deletions and several row blocks."""
+    d = getattr(qb.Distance, dist)
+    dt, inv = qparams(qb, d)
+    rng = np.random.default_rng(dim + nq)
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    if d == qb.Distance.Cosine:
+        base = oracle.preprocess_rows_f32(oracle.COSINE, base)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    cents = (rng.standard_normal((256, dim)) * 0.3).astype(np.float32)
+    codes = rng.integers(0, 256, (n, dim // chunk), dtype=np.uint8)          # scoring parity does not depend on how codes were chosen
+    pq = oracle.PQ(dim, chunk, cents, codes, dt, inv)
+    st = qb.ProductQuantizedVectors(codes, cents, chunk, dim, d)
+    luts = np.stack([pq.encode_query(oracle.preprocess_f32(int(d), q)) for q in queries])
+    deleted = rng.random(n) < 0.02
+    want = pq.scan(luts, 10, deleted=pack_bitmap(deleted))
+    for qpp in (0, 4, 2, 1):
+        qb.set_option("pq_queries_per_pass", qpp)
+        try:
+            got = st.search_batch(queries, 10, point_deleted=deleted)
+        finally:
+            qb.set_option("pq_queries_per_pass", 0)
+        for i in range(nq):
+            assert_topk_equal(got[i], want[i], None, f"pq4 {dist} qpp={qpp} q={i}")
+    assert st.search_stats()[1] == 0
+    st.close()
+
+
 # ------------------------------------------------------------------------------------------------ BQ
 @pytest.mark.parametrize("dist", ["Cosine", "Dot", "Euclid", "Manhattan"])
 @pytest.mark.parametrize("enc", ["OneBit", "TwoBits", "OneAndHalfBits"])
