@@ -11,7 +11,7 @@ use crate::common::operation_error::{OperationError, OperationResult};
 use crate::vector_storage::raw_scorer::RawScorer;
 use crate::vector_storage::query_scorer::QueryScorerBytes;
 
-fn last_error() -> String {
+pub(crate) fn last_error() -> String {
     unsafe { CStr::from_ptr(qb_last_error()).to_string_lossy().into_owned() }
 }
 
@@ -46,6 +46,7 @@ impl B200Storage {
 }
 
 impl B200RawScorer<'_> {
+    pub(crate) fn raw(&self) -> *mut qb_scorer { self.raw }
     fn sync_counters(&self) {
         let mut c = qb_hw_counters::default();
         unsafe { qb_scorer_take_counters(self.raw, &mut c) };

@@ -113,6 +113,18 @@ QB_API qb_status qb_storage_create_pq(int32_t device, uint32_t dim, uint32_t m, 
 QB_API qb_status qb_storage_create_bq(int32_t device, uint32_t dim, qb_bq_encoding enc, qb_bq_query_encoding qenc,
                                const uint8_t* rows, uint32_t row_bytes, uint64_t count, qb_qdistance dt, int32_t invert,
                                const float* mean_std, qb_distance metric, qb_storage** out);
+/* The same storages from a segment directory's files AS THEY LIE ON DISK: the caller hands over the (mmapped) bytes.
+ *   matrix.dat           b"data" + count x dim x size_of::<T>() row-major (dense/dense_vector_storage.rs:31, immutable_dense_vectors.rs:100-113);
+ *                        every complete row after the header is loaded
+ *   quantized.meta.json  serde_json of MetadataInt8 / PQ Metadata / BQ Metadata (encoded_vectors_u8.rs:84-91, encoded_vectors_pq.rs:46-51,
+ *                        encoded_vectors_binary.rs:112-125) — the kind is recognised from its fields
+ *   quantized.data       headerless rows of quantized_vector_size bytes (quantized/quantized_storage.rs:63-69); count = 0 means
+ *                        "as many rows as the bytes hold" (mmap files are page-padded: pass the real count when known)
+ * `metric` is the segment's Distance (decides Metric::preprocess of incoming queries), as in qb_storage_create_*. */
+QB_API qb_status qb_storage_load_dense_file(int32_t device, qb_dtype dt, qb_distance distance, uint32_t dim, const uint8_t* file_bytes, uint64_t n_bytes,
+                                            qb_storage** out);
+QB_API qb_status qb_storage_load_quantized(int32_t device, qb_distance metric, const char* meta_json, uint64_t json_len, const uint8_t* data, uint64_t n_bytes,
+                                           uint64_t count, qb_storage** out);
 QB_API void qb_storage_destroy(qb_storage* s);
 
 QB_API qb_status qb_storage_info(const qb_storage* s, uint32_t* dim, uint64_t* count, uint64_t* hbm_bytes);
@@ -235,6 +247,28 @@ QB_API qb_status qb_bq_encode_rows_device(int32_t device, uint32_t dim, uint64_t
 /* EncodedVectorsPQ::encode_vector (encoded_vectors_pq.rs:301-329); centroids = n_centroids x dim on the HOST; dev_codes = count x ceil(dim / chunk) */
 QB_API qb_status qb_pq_encode_rows_device(int32_t device, uint32_t dim, uint32_t chunk, uint32_t n_centroids, const float* centroids, uint64_t count,
                                           const float* dev_rows, uint64_t row_stride_bytes, uint8_t* dev_codes, void* stream);
+
+/* ---------------------------------------------------------------- quantizer TRAINING on the device -- */
+/* The steps before encode.  What the reference computes deterministically is reproduced operation for operation; what it draws from an
+ * unseeded RNG is an input: the caller passes the sampled vectors (the reference samples rows with a randomly keyed Permutor,
+ * quantile.rs:286-314, encoded_vectors_pq.rs:365-372) and a seed for re-seeding empty k-means clusters (kmeans.rs:113-121).
+ * row_stride_bytes = 0 means dim * 4; all row pointers are DEVICE memory, outputs are host memory. */
+/* VectorStats::build (vector_stats.rs:48-117): per-coordinate f64 Welford over ALL `count` rows in order -> mean_std_out = dim x
+ * {mean, stddev} (what qb_storage_create_bq / qb_bq_encode_rows_device take), min_max_out = dim x {min, max} or NULL */
+QB_API qb_status qb_bq_vector_stats_device(int32_t device, uint32_t dim, uint64_t count, const float* dev_rows, uint64_t row_stride_bytes, float* mean_std_out,
+                                           float* min_max_out);
+/* find_quantile_interval (quantile.rs:35-88) on the n_sample sampled vectors + alpha_offset_from_min_max (encoded_vectors_u8.rs:523-527).
+ * *found = 0 when the reference would return None (keep the min/max alpha / offset of qb_sq8_find_alpha_offset_device). */
+QB_API qb_status qb_sq8_quantile_interval_device(int32_t device, uint32_t dim, uint64_t n_sample, const float* dev_sample_rows, uint64_t row_stride_bytes,
+                                                 float quantile, float* alpha, float* offset, int32_t* found);
+/* EncodedVectorsPQ::find_centroids -> kmeans (encoded_vectors_pq.rs:342-407, kmeans.rs:9-167) on the sampled vectors, all chunks at once:
+ * first-minimum assignment on sequential f32 squared distances, means as f64 partial sums over `max_threads` contiguous sample ranges
+ * merged in range order (update_centroids' per-thread counters), stop when the L1 shift of a chunk's centroids < accuracy or after
+ * max_iterations (reference: 100, 1e-5, KMEANS_SAMPLE_SIZE = 10 000 vectors).  centroids_out = n_centroids x dim (Metadata.centroids).
+ * iterations_out (optional) = Lloyd iterations launched (a multiple-of-4 upper bound of the slowest chunk's count). */
+QB_API qb_status qb_pq_train_device(int32_t device, uint32_t dim, uint32_t chunk, uint32_t n_centroids, uint64_t n_sample, const float* dev_sample_rows,
+                                    uint64_t row_stride_bytes, uint32_t max_iterations, float accuracy, uint32_t max_threads, uint64_t seed, float* centroids_out,
+                                    uint32_t* iterations_out);
 
 /* Oversampling + rescoring contract (index/vector_index_search_common.rs:27-91): rescore `n` candidate ids of
  * one query with the ORIGINAL-vector scorer `orig`, sort descending, truncate to `top`. */

@@ -30,7 +30,7 @@ SCORED = np.dtype([("idx", np.uint32), ("score", np.float32)])  # #[repr(C)] Sco
 
 def ensure_built() -> None:
     so = os.path.join(_HERE, "liboracle.so")
-    need = not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "hnsw.c", "mt.c"))
+    need = not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "hnsw.c", "mt.c", "train.c"))
     need_ref = not os.path.exists(os.path.join(_HERE, "_ref", "libsimd_utils.so")) and os.path.isdir(
         "/root/reference/lib/quantization/cpp"
     )
@@ -131,6 +131,10 @@ def lib() -> C.CDLL:
         L.qo_hnsw_search_batch.argtypes = [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_uint32, C.c_void_p, u32p]
         L.qo_hnsw_entry.restype, L.qo_hnsw_entry.argtypes = None, [C.c_void_p, u32p, u32p, u32p, u32p]
         L.qo_hnsw_export_plain.restype, L.qo_hnsw_export_plain.argtypes = C.c_uint64, [C.c_void_p, C.c_void_p]
+        L.qo_bq_vector_stats.restype, L.qo_bq_vector_stats.argtypes = None, [f32p, C.c_uint64, C.c_uint32, f32p, f32p]
+        L.qo_sq8_quantile_interval.restype, L.qo_sq8_quantile_interval.argtypes = C.c_int, [f32p, C.c_uint64, C.c_uint32, C.c_float, f32p, f32p]
+        L.qo_kmeans_pq.restype = C.c_uint32
+        L.qo_kmeans_pq.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, C.c_uint64, f32p]
         L.qo_pool_create.restype, L.qo_pool_create.argtypes = C.c_void_p, [C.c_uint32]
         L.qo_pool_destroy.restype, L.qo_pool_destroy.argtypes = None, [C.c_void_p]
         L.qo_pool_threads.restype, L.qo_pool_threads.argtypes = C.c_uint32, [C.c_void_p]
@@ -660,3 +664,28 @@ class CpuPool:
         if self._p:
             lib().qo_pool_destroy(self._p)
             self._p = None
+
+
+# ------------------------------------------------------------------------------------------------ quantizer training (oracle/train.c)
+def bq_vector_stats(data):
+    """VectorStats::build (vector_stats.rs:48-117): (mean_std [dim, 2], min_max [dim, 2]) from sequential f64 Welford updates."""
+    data = np.ascontiguousarray(_f32(data))
+    ms, mm = np.zeros((data.shape[1], 2), np.float32), np.zeros((data.shape[1], 2), np.float32)
+    lib().qo_bq_vector_stats(_p(data, C.c_float), data.shape[0], data.shape[1], _p(ms, C.c_float), _p(mm, C.c_float))
+    return ms, mm
+
+
+def sq8_quantile_interval(sample, quantile: float):
+    """find_quantile_interval on the sampled vectors (quantile.rs:35-88) -> (alpha, offset) or None."""
+    sample = np.ascontiguousarray(_f32(sample))
+    a, o = C.c_float(), C.c_float()
+    ok = lib().qo_sq8_quantile_interval(_p(sample, C.c_float), sample.shape[0], sample.shape[1], np.float32(quantile), C.byref(a), C.byref(o))
+    return (np.float32(a.value), np.float32(o.value)) if ok else None
+
+
+def kmeans_pq(sample, chunk: int, n_centroids: int = 256, max_iter: int = 100, accuracy: float = 1e-5, groups: int = 1, seed: int = 0):
+    """find_centroids / kmeans (encoded_vectors_pq.rs:342-407, kmeans.rs:9-167) on the sampled vectors -> (centroids [K, dim], iterations)."""
+    sample = np.ascontiguousarray(_f32(sample))
+    out = np.zeros((n_centroids, sample.shape[1]), np.float32)
+    it = lib().qo_kmeans_pq(_p(sample, C.c_float), sample.shape[0], sample.shape[1], chunk, n_centroids, max_iter, np.float32(accuracy), groups, seed, _p(out, C.c_float))
+    return out, int(it)

@@ -40,6 +40,8 @@ SIGNATURES = {
     "qb_storage_create_sq8": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, u8p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int32, C.c_int, C.POINTER(vp)]),
     "qb_storage_create_pq": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, u32p, f32p, C.c_uint32, u8p, C.c_uint64, C.c_int, C.c_int32, C.c_int, C.POINTER(vp)]),
     "qb_storage_create_bq": (C.c_int32, [C.c_int32, C.c_uint32, C.c_int, C.c_int, u8p, C.c_uint32, C.c_uint64, C.c_int, C.c_int32, f32p, C.c_int, C.POINTER(vp)]),
+    "qb_storage_load_dense_file": (C.c_int32, [C.c_int32, C.c_int, C.c_int, C.c_uint32, u8p, C.c_uint64, C.POINTER(vp)]),
+    "qb_storage_load_quantized": (C.c_int32, [C.c_int32, C.c_int, C.c_char_p, C.c_uint64, u8p, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "qb_storage_destroy": (None, [vp]),
     "qb_storage_info": (C.c_int32, [vp, u32p, u64p, u64p]),
     "qb_storage_set_deleted": (C.c_int32, [vp, u64p, C.c_uint64]),
@@ -67,6 +69,9 @@ SIGNATURES = {
     "qb_pq_encode_rows_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint64, vp, C.c_uint64, vp, vp]),
     "qb_search_maxsim": (C.c_int32, [vp, u32p, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
     "qb_score_maxsim": (C.c_int32, [vp, u32p, C.c_uint32, f32p, C.c_uint32, u32p, C.c_size_t, f32p]),
+    "qb_bq_vector_stats_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, f32p, f32p]),
+    "qb_sq8_quantile_interval_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_float, f32p, f32p, i32p]),
+    "qb_pq_train_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_float, C.c_uint32, C.c_uint64, f32p, u32p]),
     "qb_rescore": (C.c_int32, [vp, u32p, C.c_size_t, C.c_uint32, C.POINTER(ScoredPoint), u32p]),
     "qb_storage_set_id_base": (C.c_int32, [vp, C.c_uint32]),
     "qb_topk_merge_device": (C.c_int32, [C.c_int32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]),

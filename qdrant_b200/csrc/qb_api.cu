@@ -14,6 +14,7 @@
 qb_status qb_dense_f32_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_dense_f32_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
 qb_status qb_dense_f32_scan_localk(const qb_storage* s, const QbScanArgs& a, uint32_t top, uint64_t* n_slots, cudaStream_t stream);
+qb_status qb_dense_f32_scan_fold(const qb_storage* s, const QbScanArgs& a, int kind, uint32_t n_a, uint32_t n_b, const float* d_coef, bool* done, cudaStream_t stream);
 qb_status qb_dense_x_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_dense_x_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
 qb_status qb_dense_x_convert_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, void* d_out, cudaStream_t stream);
@@ -975,8 +976,10 @@ static qb_status search_custom_impl(qb_storage* s, qb_query_kind kind, const flo
     const uint64_t n = id_list ? n_ids : s->count;
     *out_count = 0;
     if (n == 0) return QB_OK;
-    // every candidate needs its similarity to every example before the fold: E x n floats + n keys of scratch
-    QB_CHECK(n * (12ull + 4ull * ne) <= (16ull << 30), QB_ERR_UNSUPPORTED, "search_custom: %llu candidates x %u examples exceed the 16 GB scratch budget",
+    // dense f32 scans with up to 16 example vectors fold inside the streaming kernel (rows read once, no similarity matrix);
+    // otherwise every candidate needs its similarity to every example before the fold: E x n floats + n keys of scratch
+    const bool try_fold = !id_list && s->kind == QB_KIND_DENSE && s->dtype == QB_DT_F32 && s->dim >= 32 && ne <= 16 && n >= 1024;
+    QB_CHECK(try_fold || n * (12ull + 4ull * ne) <= (16ull << 30), QB_ERR_UNSUPPORTED, "search_custom: %llu candidates x %u examples exceed the 16 GB scratch budget",
              (unsigned long long)n, ne);
     if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
     QB_TRY(use_device(s->device));
@@ -995,9 +998,8 @@ static qb_status search_custom_impl(qb_storage* s, qb_query_kind kind, const flo
     QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)ne));
     QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)top));
     QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)8));
-    QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)n));
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)n));
-    QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, (size_t)ne * n * 4 + (size_t)n_coef * 4 + 256));
+    QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)n_coef + 64));
     QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
     QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), ne,
                            reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + round_up_u64(raw_bytes, 16)), c->d_queries_enc, c->d_q_off, stream));
@@ -1008,22 +1010,33 @@ static qb_status search_custom_impl(qb_storage* s, qb_query_kind kind, const flo
         QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_bitmap, words64 * 8, cudaMemcpyHostToDevice, stream));
         d_del2 = c->d_deleted2;
     }
-    if (id_list) QB_CUDA(cudaMemcpyAsync(c->d_ids, hs + ids_off, n * 4, cudaMemcpyHostToDevice, stream));
-    else QB_TRY(qb_launch_iota(c->d_ids, n, stream));
-    float* d_sims = reinterpret_cast<float*>(c->d_mma);
-    for (uint32_t e = 0; e < ne; ++e) {
-        if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
-        QB_TRY(launch_example(s, c->d_queries_enc, c->d_q_off, e, false, c->d_ids, n, d_sims + (size_t)e * n, stream));
-    }
     QbEmit emit{};
     emit.cand = c->d_cand; emit.cap = n; emit.dense = 1; emit.dense_base = 0; emit.deleted = s->d_deleted; emit.deleted2 = d_del2; emit.id_base = s->id_base;
     const float* d_coef = nullptr;
-    if (n_coef) {   // coefficients ride behind the similarity matrix
-        float* dc = d_sims + (size_t)ne * n;
-        QB_CUDA(cudaMemcpyAsync(dc, coef, (size_t)n_coef * 4, cudaMemcpyHostToDevice, stream));
-        d_coef = dc;
+    if (n_coef) {
+        QB_CUDA(cudaMemcpyAsync(c->d_thr, coef, (size_t)n_coef * 4, cudaMemcpyHostToDevice, stream));
+        d_coef = c->d_thr;
     }
-    QB_TRY(qb_launch_custom_combine((int)kind, n_a, n_b, d_coef, d_sims, n, n, nullptr, c->d_ids, &emit, stream));
+    bool folded = false;
+    if (try_fold) {
+        QbScanArgs a{};
+        a.d_q_enc = c->d_queries_enc; a.nq = ne; a.row_begin = 0; a.row_end = n; a.emit = emit;
+        QB_TRY(qb_dense_f32_scan_fold(s, a, (int)kind, n_a, n_b, d_coef, &folded, stream));
+    }
+    if (!folded) {
+        QB_CHECK(n * (12ull + 4ull * ne) <= (16ull << 30), QB_ERR_UNSUPPORTED, "search_custom: %llu candidates x %u examples exceed the 16 GB scratch budget",
+                 (unsigned long long)n, ne);
+        QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)n));
+        QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, (size_t)ne * n * 4 + 256));
+        if (id_list) QB_CUDA(cudaMemcpyAsync(c->d_ids, hs + ids_off, n * 4, cudaMemcpyHostToDevice, stream));
+        else QB_TRY(qb_launch_iota(c->d_ids, n, stream));
+        float* d_sims = reinterpret_cast<float*>(c->d_mma);
+        for (uint32_t e = 0; e < ne; ++e) {
+            if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
+            QB_TRY(launch_example(s, c->d_queries_enc, c->d_q_off, e, false, c->d_ids, n, d_sims + (size_t)e * n, stream));
+        }
+        QB_TRY(qb_launch_custom_combine((int)kind, n_a, n_b, d_coef, d_sims, n, n, nullptr, c->d_ids, &emit, stream));
+    }
     QB_TRY(qb_launch_select(c->d_cand, nullptr, n, n, 1, top, 0, c->d_out, c->d_out_counts, nullptr, nullptr, stream));
     QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
     QB_CUDA(cudaMemcpyAsync(hs + raw_bytes + res_bytes, c->d_out_counts, 4, cudaMemcpyDeviceToHost, stream));

@@ -13,61 +13,14 @@
 //   MaxSim         query_scorer/mod.rs:77-98     multivectors: sum over query tokens of the best similarity to a point's tokens
 // fast_sigmoid = x / (1 + |x|), scaled_fast_sigmoid = 0.5 * (fast_sigmoid(x) + 1)   (lib/common/common/src/math.rs:7-18)
 #include "qb_internal.h"
+#include "qb_fold.cuh"
 
 namespace {
-
-__device__ __forceinline__ int total_cmp(float a, float b) {  // f32::total_cmp as -1 / 0 / 1
-    int x = __float_as_int(a), y = __float_as_int(b);
-    x ^= (int)((unsigned int)(x >> 31) >> 1);
-    y ^= (int)((unsigned int)(y >> 31) >> 1);
-    return (x > y) - (x < y);
-}
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, fabsf(x))); }
-__device__ __forceinline__ float scaled_fast_sigmoid(float x) { return __fmul_rn(0.5f, __fadd_rn(fast_sigmoid(x), 1.0f)); }
-
-// sims: [n_examples][stride] similarities, example-major
-__device__ __forceinline__ float combine(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ coef, const float* __restrict__ sims, uint64_t stride, uint64_t i) {
-    switch (kind) {
-        case QB_QUERY_FEEDBACK_NAIVE: {  // coef = [a, partial_computation of pair 0, 1, ...]; `score += partial * delta` is a multiply then an add in Rust
-            float score = __fmul_rn(coef[0], sims[i]);
-            for (uint32_t e = 0; e < n_a; ++e) {
-                const float delta = __fsub_rn(sims[(1 + 2 * e) * stride + i], sims[(2 + 2 * e) * stride + i]);
-                score = __fadd_rn(score, __fmul_rn(coef[1 + e], delta));
-            }
-            return score;
-        }
-        case QB_QUERY_RECO_BEST_SCORE: {
-            float max_p = __int_as_float(0xff800000), max_n = __int_as_float(0xff800000);
-            for (uint32_t e = 0; e < n_a; ++e) { const float s = sims[e * stride + i]; if (total_cmp(s, max_p) > 0) max_p = s; }
-            for (uint32_t e = 0; e < n_b; ++e) { const float s = sims[(n_a + e) * stride + i]; if (total_cmp(s, max_n) > 0) max_n = s; }
-            return (max_p > max_n) ? scaled_fast_sigmoid(max_p) : -scaled_fast_sigmoid(max_n);
-        }
-        case QB_QUERY_RECO_SUM_SCORES: {
-            float p = 0.0f, n = 0.0f;
-            for (uint32_t e = 0; e < n_a; ++e) p = __fadd_rn(p, sims[e * stride + i]);
-            for (uint32_t e = 0; e < n_b; ++e) n = __fadd_rn(n, sims[(n_a + e) * stride + i]);
-            return __fsub_rn(p, n);
-        }
-        case QB_QUERY_DISCOVER: {
-            int rank = 0;
-            for (uint32_t e = 0; e < n_a; ++e) rank += total_cmp(sims[(1 + 2 * e) * stride + i], sims[(2 + 2 * e) * stride + i]);
-            return __fadd_rn((float)rank, scaled_fast_sigmoid(sims[i]));
-        }
-        default: {  // QB_QUERY_CONTEXT
-            float sum = 0.0f;
-            for (uint32_t e = 0; e < n_a; ++e) {
-                const float d = __fsub_rn(__fsub_rn(sims[(2 * e) * stride + i], sims[(2 * e + 1) * stride + i]), 1.1920929e-7f);
-                sum = __fadd_rn(sum, fast_sigmoid(fminf(d, 0.0f)));
-            }
-            return sum;
-        }
-    }
-}
 
 __global__ void custom_combine_kernel(int kind, uint32_t n_a, uint32_t n_b, const float* __restrict__ coef, const float* __restrict__ sims, uint64_t stride, uint64_t n, float* __restrict__ scores,
                                       const uint32_t* __restrict__ ids, QbEmit emit, int to_keys) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float sc = combine(kind, n_a, n_b, coef, sims, stride, i);
+        const float sc = qbf::fold(kind, n_a, n_b, coef, [&](uint32_t e) { return sims[(uint64_t)e * stride + i]; });
         if (to_keys) qb_emit(emit, 0, i, ids ? ids[i] : (uint32_t)i, sc);
         else scores[i] = sc;
     }

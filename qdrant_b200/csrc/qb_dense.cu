@@ -19,6 +19,7 @@
 // map is needed), completion on mbarriers; 8 consumer warps each own every 8th slot, read rows and the query from
 // shared memory with conflict-free 128-bit loads and emit candidates that pass the per-query threshold.
 #include "qb_internal.h"
+#include "qb_fold.cuh"
 #include "qb_score.cuh"
 
 namespace {
@@ -43,7 +44,30 @@ struct StreamParams {
     uint32_t slot_bytes;        // rows_per_slot * stride
     uint32_t q_smem_bytes;      // nq * stride rounded up to 128
     int l2_keep;                // 1: data set fits L2 -> keep it resident (evict_last); 0: stream (evict_first)
+    // custom queries: the nq "queries" are the example vectors of ONE query and a row's nq similarities are folded (Query::score_by,
+    // qb_fold.cuh) into the single score that is emitted for query slot 0; fold_kind = 0: plain batch, every query emits its own score
+    int fold_kind;
+    uint32_t fold_na, fold_nb;
+    const float* fold_coef;
 };
+
+// one row against the p.nq queries staged in shared memory, row read once (score_avx_group8_multi); emits per query, or the fold
+template <int METRIC, int NQ>
+__device__ __forceinline__ void stream_score_multi(const StreamParams& p, const QbEmit& emit, const float* rp, const float* q_s, uint32_t stride_f, int t, bool valid,
+                                                   uint64_t slot) {
+    float sc[NQ];
+    // queries past p.nq alias query 0 (computed, never emitted)
+    score_avx_group8_multi<METRIC, NQ>(rp, q_s, (NQ == 1) ? 0u : stride_f, p.dim, t, sc);
+    if (!(valid && t == 0)) return;
+    if (p.fold_kind) {
+        const float f = qbf::fold(p.fold_kind, p.fold_na, p.fold_nb, p.fold_coef, [&](uint32_t e) { return sc[e < (uint32_t)NQ ? e : 0]; });
+        qb_emit(emit, 0, slot, (uint32_t)slot, f);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            if ((uint32_t)q < p.nq) qb_emit(emit, q, slot, (uint32_t)slot, sc[q]);
+    }
+}
 
 // LOCALK (single query, top <= 16): instead of a threshold pass + filtered emission, every consumer warp keeps its own k best keys
 // in registers (lane i < 16 holds entry i; an insertion is two warp-wide min reductions and happens ~k ln(rows/k) times per warp),
@@ -105,12 +129,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(con
     }
     if (LOCALK && threadIdx.x < STREAM_CONSUMER_WARPS)
         reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned long long*>(empty + p.n_slots) + STREAM_CONSUMER_WARPS * (QB_LOCALK_SLOTS + 4))[threadIdx.x] = 0u;
-    // stage the queries (small, L2-resident) into shared memory
+    // stage the queries (small, L2-resident) into shared memory; slots up to the next power of two repeat query 0 (the multi-query
+    // scorer is instantiated for 2 / 4 / 8 / 16 queries and never emits the padding)
     {
-        const uint32_t n4 = (p.nq * p.stride) >> 4;
+        uint32_t nq_pad = 1;
+        while (nq_pad < p.nq) nq_pad <<= 1;
+        const uint32_t per = p.stride >> 4, n4 = nq_pad * per;
         const float4* src = reinterpret_cast<const float4*>(p.q);
         float4* dst = reinterpret_cast<float4*>(q_s);
-        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = (i / per < p.nq) ? src[i] : src[i % per];
     }
     __syncthreads();
 
@@ -168,12 +195,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(con
                         const LkState st = lk_drain(LkState{my_key, wmin, wthr}, lk_queue + cw * 4, &lk_count[cw], lane, n_queued);
                         my_key = st.my_key; wmin = st.wmin; wthr = st.wthr;
                     }
-                } else {
-                    for (uint32_t q = 0; q < p.nq; ++q) {
-                        float sc = score_avx_group8<METRIC>(rp, q_s + (size_t)q * stride_f, p.dim, t);
-                        if (valid && t == 0) qb_emit(emit, q, r0 + rin, (uint32_t)(r0 + rin), sc);
-                    }
-                }
+                } else if (p.nq == 1) {
+                    const float sc = score_avx_group8<METRIC>(rp, q_s, p.dim, t);
+                    if (valid && t == 0) qb_emit(emit, 0, r0 + rin, (uint32_t)(r0 + rin), sc);
+                } else if (p.nq <= 2) stream_score_multi<METRIC, 2>(p, emit, rp, q_s, stride_f, t, valid, r0 + rin);
+                else if (p.nq <= 4) stream_score_multi<METRIC, 4>(p, emit, rp, q_s, stride_f, t, valid, r0 + rin);
+                else if (p.nq <= 8) stream_score_multi<METRIC, 8>(p, emit, rp, q_s, stride_f, t, valid, r0 + rin);
+                else stream_score_multi<METRIC, 16>(p, emit, rp, q_s, stride_f, t, valid, r0 + rin);
             }
             if (!LOCALK) {
                 __syncwarp();
@@ -342,7 +370,9 @@ qb_status launch_stream(const StreamParams& sp_in, const QbEmit& emit, int sm_co
     StreamParams sp = sp_in;
     *done = false;
     const uint32_t kMaxSmem = 227 * 1024;
-    sp.q_smem_bytes = (uint32_t)round_up_u64((uint64_t)sp.nq * sp.stride, 128);
+    uint32_t nq_pad = 1;
+    while (nq_pad < sp.nq) nq_pad <<= 1;
+    sp.q_smem_bytes = (uint32_t)round_up_u64((uint64_t)nq_pad * sp.stride, 128);
     uint32_t rps = (16384 / sp.stride) & ~3u;
     if (rps < 4) rps = 4;
     sp.rows_per_slot = rps;
@@ -385,7 +415,7 @@ qb_status qb_dense_f32_scan(const qb_storage* s, const QbScanArgs& a, cudaStream
     if (n == 0 || a.nq == 0) return QB_OK;
     // streaming ring for contiguous ranges of wide-enough rows; queries are processed in chunks that fit smem
     if (!a.d_ids && s->dim >= 32 && n >= 1024) {
-        const uint32_t q_chunk_max = 8;
+        const uint32_t q_chunk_max = 16;
         bool all_done = true;
         for (uint32_t q0 = 0; q0 < a.nq && all_done; q0 += q_chunk_max) {
             const uint32_t qn = (a.nq - q0 < q_chunk_max) ? a.nq - q0 : q_chunk_max;
@@ -422,6 +452,27 @@ qb_status qb_dense_f32_scan(const qb_storage* s, const QbScanArgs& a, cudaStream
         case M_EUCLID: return launch_group<M_EUCLID>(gp, a.emit, s->sm_count, stream);
         case M_MANHATTAN: return launch_group<M_MANHATTAN>(gp, a.emit, s->sm_count, stream);
         default: return launch_group<M_DOT>(gp, a.emit, s->sm_count, stream);
+    }
+}
+
+// Custom query over a contiguous row range in ONE pass: the a.nq encoded "queries" are the example vectors, every row's similarities are
+// folded in the kernel (no [examples][rows] matrix, rows read once).  *done = false when the shape does not suit the streaming kernel.
+qb_status qb_dense_f32_scan_fold(const qb_storage* s, const QbScanArgs& a, int kind, uint32_t n_a, uint32_t n_b, const float* d_coef, bool* done, cudaStream_t stream) {
+    *done = false;
+    const uint64_t n = a.row_end - a.row_begin;
+    if (a.d_ids || s->dim < 32 || n < 1024 || a.nq < 1 || a.nq > 16) return QB_OK;
+    StreamParams sp{};
+    sp.rows = reinterpret_cast<const uint8_t*>(s->d_rows);
+    sp.stride = s->row_stride; sp.dim = s->dim;
+    sp.row_begin = a.row_begin; sp.row_end = a.row_end;
+    sp.q = reinterpret_cast<const float*>(a.d_q_enc);
+    sp.nq = a.nq;
+    sp.l2_keep = (s->hbm_bytes <= (64ull << 20)) ? 1 : 0;
+    sp.fold_kind = kind; sp.fold_na = n_a; sp.fold_nb = n_b; sp.fold_coef = d_coef;
+    switch (metric_of(s->distance)) {
+        case M_EUCLID: return launch_stream<M_EUCLID>(sp, a.emit, s->sm_count, stream, done);
+        case M_MANHATTAN: return launch_stream<M_MANHATTAN>(sp, a.emit, s->sm_count, stream, done);
+        default: return launch_stream<M_DOT>(sp, a.emit, s->sm_count, stream, done);
     }
 }
 

@@ -106,6 +106,17 @@ __device__ __forceinline__ void score_list(const HnswParams& p, const HnswSmem& 
     }
 }
 
+// one TMA-engine instruction pulls a whole vector (dim * 4 bytes) from HBM into L2, so that the group's demand loads — which the
+// compiler keeps only 3-4 deep — are L2 hits instead of HBM round trips
+__device__ __forceinline__ void prefetch_row_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void prefetch_point(const HnswParams& p, uint32_t id) {
+    if (KIND == HK_DENSE_AVX || KIND == HK_DENSE_SMALL) prefetch_row_l2(p.rows + (size_t)id * p.stride, p.stride);
+    else prefetch_row_l2(p.codes + (size_t)id * p.ad, p.ad);
+}
+
 __device__ __forceinline__ bool hnsw_filtered_out(const HnswParams& p, uint32_t id) {
     bool d = false;
     if (p.deleted) d = (p.deleted[id >> 5] >> (id & 31)) & 1u;
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
                         const bool keep = l != HNSW_EMPTY && l < p.n_points && !hnsw_filtered_out(p, l);
                         const unsigned int bal = __ballot_sync(0xFFFFFFFFu, keep);
                         const uint32_t pos = cnt + __popc(bal & ((1u << tid) - 1u));
-                        if (keep && pos < p.m && pos < HNSW_MAX_LINKS) sm.ids[pos] = l;
+                        if (keep && pos < p.m && pos < HNSW_MAX_LINKS) { sm.ids[pos] = l; prefetch_point<KIND>(p, l); }
                         cnt += __popc(bal);
                     }
                     if (tid == 0) s_n = min(min(cnt, p.m), HNSW_MAX_LINKS);
@@ -230,6 +241,7 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
                 asm volatile("bar.sync 1, 64;" ::: "memory");
                 const uint32_t pos = ((tid >> 5) ? s_warp_cnt[0] : 0u) + __popc(bal & ((1u << (tid & 31)) - 1u));
                 if (keep) {
+                    prefetch_point<KIND>(p, l);          // HBM -> L2 for the whole vector, in flight while the list is published
                     sm.ids[pos] = l;
                     const uint32_t lp = s_nlog + pos;
                     if (lp < p.vlog_cap) vlog[lp] = l;

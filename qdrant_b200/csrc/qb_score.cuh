@@ -58,6 +58,43 @@ __device__ __forceinline__ float score_avx_group8(const float* __restrict__ row,
     return (METRIC == M_DOT) ? r : -r;
 }
 
+// NQ queries against ONE row: the row's float4 of every 32-block is loaded once and FMA-ed into NQ independent accumulator sets, so a
+// batch (or the examples of a custom query) costs one pass over the rows and one row read from shared memory instead of NQ.  Each
+// (query, lane) chain is the very chain score_avx_group8 runs, so every result is bit-identical to the single-query function.
+// qry + q * q_stride_f = query q (16-B aligned).
+template <int METRIC, int NQ>
+__device__ __forceinline__ void score_avx_group8_multi(const float* __restrict__ row, const float* __restrict__ qry, uint32_t q_stride_f, uint32_t dim, int t,
+                                                       float (&out)[NQ]) {
+    const uint32_t nblk = dim >> 5;
+    const float4* r4 = reinterpret_cast<const float4*>(row) + t;
+    float4 acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (uint32_t b = 0; b < nblk; ++b) {
+        const float4 v = r4[b * 8];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float4 w = (reinterpret_cast<const float4*>(qry + (size_t)q * q_stride_f) + t)[b * 8];
+            acc[q].x = elem_step<METRIC>(w.x, v.x, acc[q].x);
+            acc[q].y = elem_step<METRIC>(w.y, v.y, acc[q].y);
+            acc[q].z = elem_step<METRIC>(w.z, v.z, acc[q].z);
+            acc[q].w = elem_step<METRIC>(w.w, v.w, acc[q].w);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        float4 a = acc[q];
+        a = add4(a, shfl_xor4(a, 2));
+        a = add4(a, shfl_xor4(a, 4));
+        a = add4(a, shfl_xor4(a, 1));
+        float r = __fadd_rn(__fadd_rn(a.x, a.y), __fadd_rn(a.z, a.w));
+        const float* qq = qry + (size_t)q * q_stride_f;
+        for (uint32_t i = nblk << 5; i < dim; ++i) r = tail_step<METRIC>(qq[i], row[i], r);
+        out[q] = (METRIC == M_DOT) ? r : -r;
+    }
+}
+
 // SSE tier (16 <= dim < 32, one 16-block, unfused mul+add) and scalar tier (dim < 16); one thread per pair.
 template <int METRIC>
 __device__ __forceinline__ float score_small(const float* __restrict__ row, const float* __restrict__ qry, uint32_t dim) {

@@ -640,6 +640,38 @@ def pq_encode_rows(rows_ptr: int, count: int, dim: int, chunk: int, centroids, o
     check(lib().qb_pq_encode_rows_device(device, dim, chunk, c.shape[0], c.ctypes.data_as(f32p), count, vp(rows_ptr), row_stride_bytes, vp(out_ptr), vp(stream)))
 
 
+class _LoadedStorage(_Storage):
+    def __init__(self, handle, device: int, distance: Distance):
+        super().__init__()
+        self._h, self.device, self.distance = handle, device, Distance(distance)
+        d, n = C.c_uint32(), C.c_uint64()
+        check(lib().qb_storage_info(self._h, C.byref(d), C.byref(n), None))
+        self.dim, self.count = int(d.value), int(n.value)
+
+    def raw_scorer(self, query) -> RawScorer:
+        return self._raw_scorer(query)
+
+    def raw_internal_scorer(self, point_id: int) -> RawScorer:
+        return self._raw_internal_scorer(point_id)
+
+
+def load_dense_file(file_bytes, distance: Distance, dim: int, datatype: VectorStorageDatatype = VectorStorageDatatype.Float32, device: int = 0) -> _Storage:
+    """A segment's `matrix.dat` (b"data" header + rows, dense/immutable_dense_vectors.rs:100-113) as it lies on disk."""
+    blob = np.frombuffer(bytes(file_bytes), dtype=np.uint8) if not isinstance(file_bytes, np.ndarray) else np.ascontiguousarray(file_bytes, dtype=np.uint8)
+    h = vp()
+    check(lib().qb_storage_load_dense_file(device, int(datatype), int(distance), int(dim), blob.ctypes.data_as(u8p), blob.size, C.byref(h)))
+    return _LoadedStorage(h, device, distance)
+
+
+def load_quantized(meta_json, data, metric: Distance, count: int = 0, device: int = 0) -> _Storage:
+    """`quantized.meta.json` + `quantized.data` of a segment, unchanged (quantized/quantized_storage.rs:63-69)."""
+    meta = meta_json.encode() if isinstance(meta_json, str) else bytes(meta_json)
+    blob = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+    h = vp()
+    check(lib().qb_storage_load_quantized(device, int(metric), meta, len(meta), blob.ctypes.data_as(u8p), blob.size, int(count), C.byref(h)))
+    return _LoadedStorage(h, device, metric)
+
+
 def set_option(name: str, value: int) -> None:
     """Debugging / experiment switches of the library (qb_set_option)."""
     check(lib().qb_set_option(name.encode(), int(value)))

@@ -87,3 +87,21 @@ def test_custom_query_flat_layouts():
     vecs, n_a, n_b = qb.ContextQuery([qb.ContextPair(v[4], v[5])]).flat()
     assert (n_a, n_b) == (1, 0) and [int(x[0]) for x in vecs] == [4, 5]
     assert int(qb.RecoBestScoreQuery.kind) == 1 and int(qb.RecoSumScoresQuery.kind) == 2 and int(qb.DiscoverQuery.kind) == 3 and int(qb.ContextQuery.kind) == 4
+
+
+def test_rust_ffi_declares_every_exported_function():
+    """bindings/rust/src/ffi.rs is generated from the header (tools/gen_rust_ffi.py): it must cover the whole C ABI, with matching arity."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    fns, status, abi = gen.parse()
+    assert sorted(f[0] for f in fns) == header_functions()
+    rs = open(os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")).read()
+    assert f"QB200_ABI_VERSION: i32 = {abi}" in rs
+    for name, params, ret in fns:
+        m = re.search(r"pub fn " + name + r"\(([^)]*)\)", rs)
+        assert m, f"{name} missing from ffi.rs (run tools/gen_rust_ffi.py)"
+        got = [a for a in m.group(1).split(",") if a.strip()]
+        assert len(got) == len(params), f"{name}: {len(got)} parameters in ffi.rs, {len(params)} in the header"

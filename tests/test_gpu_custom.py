@@ -30,6 +30,7 @@ def make_queries(qb, rng, dim):
         qb.DiscoverQuery(v(), [qb.ContextPair(v(), v()), qb.ContextPair(v(), v()), qb.ContextPair(v(), v())]),
         qb.DiscoverQuery(v(), []),
         qb.ContextQuery([qb.ContextPair(v(), v()), qb.ContextPair(v(), v())]),
+        qb.RecoSumScoresQuery(qb.RecoQuery([v() for _ in range(12)], [v() for _ in range(9)])),   # 21 examples: beyond the fused-fold scan's 16
         feedback_query(qb, rng, dim, 4),
         feedback_query(qb, rng, dim, 1),     # fewer than two feedback items: no pairs, score = a * sim(target)
     ]
