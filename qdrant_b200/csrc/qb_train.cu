@@ -10,7 +10,7 @@
 // per-thread-range f64 partial sums of update_centroids merged in thread order, the sequential f32 distance sums).  What the reference
 // draws from an unseeded RNG is an INPUT here: the caller passes the sampled vectors (Permutor-sampled rows in the reference,
 // quantile.rs:286-314, encoded_vectors_pq.rs:365-372) and a seed for the re-seeding of empty k-means clusters (kmeans.rs:115 uses
-// rand::rng()); the oracle follows the same rule, so training parity is pinned given (sample, seed, thread count).
+// rand::rng()); the CPU restatement used by the tests follows the same rule, so training parity is pinned given (sample, seed, thread count).
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) km_update_kernel(const KmParams p) {
     float out;
     if (cnt == 0) {
         // empty cluster: the reference re-seeds it with a random sampled vector (rand::rng(), kmeans.rs:113-121); here the index is a
-        // function of (seed, iteration, chunk, centroid) so that the oracle can follow
+        // function of (seed, iteration, chunk, centroid) so that a CPU restatement can follow
         const uint32_t di = (uint32_t)(km_mix(p.seed ^ km_mix(((unsigned long long)p.iter << 40) ^ ((unsigned long long)j << 20) ^ c)) % p.n);
         out = (float)(double)p.sample[(uint64_t)di * p.stride_f + s + k];
     } else {
