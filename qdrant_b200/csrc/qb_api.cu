@@ -32,6 +32,10 @@ size_t qb_sq8_mma_scratch_bytes(const qb_storage* s, uint32_t nq_pad);
 qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_t nq_pad, const float* d_q_off, uint32_t nq, uint32_t n_blk,
                           uint64_t row_begin, uint64_t row_end, const QbEmit& emit, unsigned int* d_flags, unsigned long long* seg_len,
                           void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
+uint32_t qb_f32_mma_block(qb_storage* s, uint32_t nq, cudaStream_t stream);
+size_t qb_f32_mma_scratch_bytes(const qb_storage* s, uint32_t nq_pad);
+qb_status qb_f32_mma_scan(qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, uint32_t nq_pad, uint32_t n_blk_flag, uint64_t row_end, const QbEmit& emit,
+                          unsigned int* d_flags, void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
 qb_status qb_bq_encode_queries(const qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, int force_binary, void* d_out, cudaStream_t stream);
 qb_status qb_bq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 qb_status qb_bq_score_points(const qb_storage* s, const void* d_q_enc, int bits, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream);
@@ -249,6 +253,7 @@ extern "C" qb_status qb_storage_write_rows(qb_storage* s, uint64_t first_row, ui
     QB_TRY(use_device(s->device));
     QB_CUDA(cudaMemcpy2D(reinterpret_cast<uint8_t*>(s->d_rows) + first_row * s->row_stride, s->row_stride, host_rows, row_stride_bytes, rb, n_rows,
                          cudaMemcpyHostToDevice));
+    s->bf16_ready = false;   // the bf16 shadow (if any) no longer mirrors the rows
     return QB_OK;
 }
 
@@ -261,6 +266,7 @@ extern "C" qb_status qb_storage_write_rows_device(qb_storage* s, uint64_t first_
     QB_TRY(use_device(s->device));
     QB_CUDA(cudaMemcpy2D(reinterpret_cast<uint8_t*>(s->d_rows) + first_row * s->row_stride, s->row_stride, dev_rows, row_stride_bytes, rb, n_rows,
                          cudaMemcpyDeviceToDevice));
+    s->bf16_ready = false;
     return QB_OK;
 }
 
@@ -404,7 +410,7 @@ extern "C" void qb_storage_destroy(qb_storage* s) {
     ctx_destroy(s->dev_ctx);
     for (auto& pr : s->prof_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : s->prof_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    cudaFree(s->d_rows); cudaFree(s->d_codes); cudaFree(s->d_voff); cudaFree(s->d_pq_div); cudaFree(s->d_centroids); cudaFree(s->d_pq_codes);
+    cudaFree(s->d_rows); cudaFree(s->d_bf16); cudaFree(s->d_bf16_meta); cudaFree(s->d_codes); cudaFree(s->d_voff); cudaFree(s->d_pq_div); cudaFree(s->d_centroids); cudaFree(s->d_pq_codes);
     cudaFree(s->d_bq_rows); cudaFree(s->d_mean_std); cudaFree(s->d_deleted);
     cudaGetLastError();
     delete s;
@@ -617,7 +623,9 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         QB_CHECK(n_slots == 0, QB_ERR_CUDA, "local top-k scan wrote %llu slots", (unsigned long long)n_slots);
     }
     const bool mma_ok = !d_ids && !(rs_flags & RS_NO_MMA) && !qb_opt().disable_mma;
-    const SearchPlan plan = make_plan(n_cand, nq, top, force_direct, mma_ok && qb_sq8_mma_block(s, nq) != 0 && !(rs_flags & RS_NO_REFINE));
+    // dense f32 (dot / cosine) batches: bf16 tensor-core prefilter + exact rescoring of the survivors (qb_sq8_mma.cu, F16)
+    const bool f32_mma = mma_ok && s->kind == QB_KIND_DENSE && n_cand >= (1ull << 17) && qb_f32_mma_block(s, nq, stream) != 0;
+    const SearchPlan plan = make_plan(n_cand, nq, top, force_direct, mma_ok && (f32_mma || qb_sq8_mma_block(s, nq) != 0) && !(rs_flags & RS_NO_REFINE));
     if (can_flag && plan.direct) *can_flag = false;  // full materialisation: no threshold, no counters, nothing to overflow
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)plan.q_chunk * plan.cap));
     QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)nq));
@@ -649,23 +657,28 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             // pass 1: sample prefix, materialised densely -> per-query threshold = k-th best of the sample
             a.row_begin = 0; a.row_end = plan.sample;
             a.emit.dense = 1; a.emit.dense_base = 0;
-            const uint32_t mma_blk = mma_ok ? qb_sq8_mma_block(s, qn) : 0;
+            const bool f32b = f32_mma && qb_f32_mma_block(s, qn, stream) != 0;   // this chunk of the batch is wide enough for the tensor-core prefilter
+            const uint32_t mma_blk = mma_ok ? (f32b ? qb_f32_mma_block(s, qn, stream) : qb_sq8_mma_block(s, qn)) : 0;
             const uint32_t nq_pad = mma_blk ? (uint32_t)round_up_u64(qn, mma_blk & 0x7FFFFFFFu) : 0;
-            if (mma_blk) {
+            const uint32_t q_stride_f = s->row_stride / 4;              // dense f32: encoded queries = preprocessed f32 rows
+            if (mma_blk && !f32b) {
                 QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, plan.sample, a.emit, d_overflow, nullptr,
                                        nullptr, 0, stream));
             } else {
-                QB_TRY(qb_launch_scan(s, a, stream));
+                QB_TRY(qb_launch_scan(s, a, stream));                   // the sample is always scored exactly for f32 storages
             }
             QB_TRY(qb_launch_select(c->d_cand, nullptr, plan.cap, plan.sample, qn, top, 1, nullptr, nullptr, c->d_thr + q0, nullptr, stream));
-            if (mma_blk) QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, qb_sq8_mma_scratch_bytes(s, nq_pad)));
+            if (mma_blk) QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, f32b ? qb_f32_mma_scratch_bytes(s, nq_pad) : qb_sq8_mma_scratch_bytes(s, nq_pad)));
             if (plan.sample2) {
                 // level 2: a longer prefix filtered by the level-1 threshold; its k-th best survivor is the threshold of the full pass
                 QB_CUDA(cudaMemsetAsync(c->d_cnt + q0, 0, (size_t)qn * 4, stream));
                 a.row_end = plan.sample2;
                 a.emit.dense = 0; a.emit.thr = c->d_thr + q0; a.emit.cnt = c->d_cnt + q0;
                 unsigned long long seg2 = 0;
-                if (mma_blk) {
+                if (f32b) {
+                    QB_TRY(qb_f32_mma_scan(s, reinterpret_cast<const float*>(a.d_q_enc), q_stride_f, qn, nq_pad, mma_blk, plan.sample2, a.emit, d_overflow, c->d_mma,
+                                           c->mma_bytes, stream));
+                } else if (mma_blk) {
                     QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, plan.sample2, a.emit, d_overflow,
                                            (rs_flags & RS_NO_SEGMENTS) ? nullptr : &seg2, c->d_mma, c->mma_bytes, stream));
                 } else {
@@ -680,7 +693,11 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
             if (is_stopped && *is_stopped) { qb_set_error("search cancelled"); return QB_ERR_CANCELLED; }
             profile_begin(s, c, stream, &e0, &e1);
             unsigned long long seg_len = 0;
-            if (mma_blk) {
+            if (f32b) {
+                // batched dense f32: bf16 tensor-core prefilter, survivors re-scored exactly (qb_sq8_mma.cu, F16)
+                QB_TRY(qb_f32_mma_scan(s, reinterpret_cast<const float*>(a.d_q_enc), q_stride_f, qn, nq_pad, mma_blk, n_cand, a.emit, d_overflow, c->d_mma, c->mma_bytes,
+                                       stream));
+            } else if (mma_blk) {
                 // batched SQ8: tensor-core GEMM with the fused epilogue/filter (qb_sq8_mma.cu)
                 QB_TRY(qb_sq8_mma_scan(s, reinterpret_cast<const uint8_t*>(a.d_q_enc), nq_pad, a.d_q_off, qn, mma_blk, 0, n_cand, a.emit, d_overflow,
                                        (rs_flags & RS_NO_SEGMENTS) ? nullptr : &seg_len, c->d_mma, c->mma_bytes, stream));

@@ -42,6 +42,9 @@ struct qb_storage {
     qb_dtype dtype = QB_DT_F32;
     qb_distance distance = QB_DIST_DOT;
     void* d_rows = nullptr;          // row-major, stride padded to 16 B
+    // bf16 shadow of the f32 rows for the tensor-core prefilter of batched searches (qb_sq8_mma.cu, F16): built on first use
+    uint16_t* d_bf16 = nullptr;  uint32_t bf16_row_h = 0;  unsigned int* d_bf16_meta = nullptr;   // meta: [0] max |row| (float bits), [1] non-finite flag
+    bool bf16_ready = false, bf16_usable = false;
     uint32_t row_stride = 0;         // bytes
     uint32_t elem_size = 4;
 

@@ -34,10 +34,19 @@
 // Exactness: codes are <= 127, so dot <= 127^2 * K.  While dot < 2^24 the CPU's lane-wise f32 tree equals f32(dot)
 // exactly (all partial sums are non-negative integers <= dot).  If any dot >= 2^24 (possible only for K > 1040) the
 // kernel raises a flag and the host reruns the batch on the lane-exact CUDA-core kernel.
+//
+// F16 = true: the same pipeline for DENSE f32 storages (dot / cosine) — "batched multi-query x segment scoring on tensor cores" for
+// full-precision vectors.  bf16 inputs cannot reproduce the reference's f32 FMA chains, so the tensor cores only PREFILTER:
+//      approx = bf16(row) . bf16(query)   (tcgen05.mma kind::f16, f32 accumulators; a bf16 shadow plane of the rows lives beside the f32 plane)
+//      |approx - exact| <= eps_q = (2^-8 + 2^-18 + K 2^-22) |q| max|row|  (RN-even input rounding of both operands + f32 accumulation) + slack
+// a row survives when approx >= thr_q - eps_q, and every survivor is re-scored by the bit-exact AVX-order kernel before the
+// selection sees it (f32_rescore_kernel).  thr_q comes from exactly scored samples, so it never exceeds the final k-th score:
+// nothing that belongs to the top-k can be filtered out, and the reported scores are the exact ones.
 #include <cuda.h>
 #include <stdlib.h>
 
 #include "qb_internal.h"
+#include "qb_score.cuh"
 
 namespace {
 
@@ -166,6 +175,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
     return d;
 }
 template <bool TWO>
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (TWO)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a_desc),
+            "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(a_desc),
+            "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+template <bool TWO>
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     if (TWO)
         asm volatile(
@@ -224,6 +246,48 @@ __device__ __forceinline__ void epilogue_exact(EpiShared* es, uint32_t acc, uint
     }
 }
 
+// F16 prefilter survivors: (query, row) pairs whose bf16 approximation reached the batch threshold; the key carries the approximate
+// score and the LOCAL row — f32_rescore_kernel replaces it with the exact score (or drops it) before any selection.
+__device__ __forceinline__ void epilogue_approx(EpiShared* es, float val, uint32_t n, uint64_t row, bool valid_row, bool dead) {
+    const uint32_t q = es->q_base + n;
+    if (q >= es->nq || !valid_row || dead) return;
+    const float approx = __fsub_rn(val, __int_as_float(es->bias[n]));
+    const uint32_t seg_cap = es->seg_cap;
+    if (seg_cap) {
+        const unsigned int pos = atomicAdd(&es->cnt[n], 1u);
+        if (pos < seg_cap) es->cand[(unsigned long long)q * es->cap + (unsigned long long)es->seg_index * seg_cap + pos] = qb_pack_key(approx, (uint32_t)row);
+        else atomicOr(es->flags, 8u);
+    } else {
+        const unsigned int pos = atomicAdd(&es->gcnt[q], 1u);
+        if (pos < es->cap) es->cand[(unsigned long long)q * es->cap + pos] = qb_pack_key(approx, (uint32_t)row);
+    }
+}
+__device__ __noinline__ void epilogue_hits_f16(EpiShared* es, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
+                                               uint32_t r8, uint32_t r9, uint32_t r10, uint32_t r11, uint32_t r12, uint32_t r13, uint32_t r14, uint32_t r15, uint32_t c,
+                                               float t_row, uint64_t row, uint32_t row_flags) {
+    uint32_t mask = 0;
+#define QB_HIT(j) mask |= (__uint_as_float(r##j) >= t_row) ? (1u << j) : 0u;
+    QB_HIT(0) QB_HIT(1) QB_HIT(2) QB_HIT(3) QB_HIT(4) QB_HIT(5) QB_HIT(6) QB_HIT(7) QB_HIT(8) QB_HIT(9) QB_HIT(10) QB_HIT(11) QB_HIT(12) QB_HIT(13) QB_HIT(14) QB_HIT(15)
+#undef QB_HIT
+    while (mask) {
+        const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
+        mask &= mask - 1u;
+        const bool b0 = j & 1u, b1 = j & 2u, b2 = j & 4u, b3 = j & 8u;
+        const uint32_t s0 = b0 ? r1 : r0, s1 = b0 ? r3 : r2, s2 = b0 ? r5 : r4, s3 = b0 ? r7 : r6, s4 = b0 ? r9 : r8, s5 = b0 ? r11 : r10, s6 = b0 ? r13 : r12,
+                       s7 = b0 ? r15 : r14;
+        const uint32_t u0 = b1 ? s1 : s0, u1 = b1 ? s3 : s2, u2 = b1 ? s5 : s4, u3 = b1 ? s7 : s6;
+        const uint32_t w0 = b2 ? u1 : u0, w1 = b2 ? u3 : u2;
+        epilogue_approx(es, __uint_as_float(b3 ? w1 : w0), c * 16 + j, row, (row_flags & 1u) != 0, (row_flags & 2u) != 0);
+    }
+}
+__device__ __forceinline__ void epilogue_chunk_f16(EpiShared* es, uint32_t (&r)[16], uint32_t c, float t_row, uint64_t row, uint32_t row_flags) {
+    float mx = __uint_as_float(r[0]);
+#pragma unroll
+    for (int j = 1; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+    if (__any_sync(0xFFFFFFFFu, mx >= t_row))
+        epilogue_hits_f16(es, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], c, t_row, row, row_flags);
+}
+
 // Slow path of a chunk: at least one lane of the warp has a column at or above the threshold.  ONE out-of-line copy for the
 // whole kernel (the 16 accumulator values travel in registers): the hot loop stays a few hundred bytes of straight-line code.
 __device__ __noinline__ void epilogue_hits(EpiShared* es, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
@@ -256,7 +320,7 @@ __device__ __forceinline__ void epilogue_chunk(EpiShared* es, uint32_t (&r)[16],
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <bool TWO>
+template <bool TWO, bool F16 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const MmaParams p, const QbEmit emit) {
     constexpr int STAGES = TWO ? STAGES_2 : STAGES_1;
@@ -301,13 +365,14 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t q = q_base + i;
         const bool real = i < p.n_blk && q < p.nq;
         es->thr[i] = real ? (emit.dense ? __int_as_float(0xff800000) : emit.thr[q]) : __int_as_float(0x7f800000);  // +inf: padding never emits
-        es->qoff[i] = real ? p.q_off[q] : 0.0f;
+        es->qoff[i] = (real && !F16) ? p.q_off[q] : 0.0f;
         es->bias[i] = (real && use_bias) ? p.bias_i[q] : 0;
         es->cnt[i] = 0u;
     }
     // bias MMA operands, written with ordinary stores (both 16-B halves of a row are identical: swizzle-agnostic)
     for (uint32_t i = threadIdx.x; i < MMA_M * BIAS_KB / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(a_const)[i] = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x017F7F7Fu);  // bytes 0-14 = 127, byte 15 = 1
+        reinterpret_cast<uint4*>(a_const)[i] = F16 ? make_uint4(0x3F803F80u, 0u, 0u, 0u)                          // bf16 (1, 1, 0, 0, 0, 0, 0, 0)
+                                                   : make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x017F7F7Fu);  // bytes 0-14 = 127, byte 15 = 1
     if (use_bias)
         for (uint32_t i = threadIdx.x; i < n_mine * BIAS_KB / 16; i += blockDim.x)
             reinterpret_cast<uint4*>(b_bias)[i] = reinterpret_cast<const uint4*>(p.bias_rows + (size_t)(q_base + rank * n_mine) * BIAS_KB)[i];
@@ -367,7 +432,9 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ------------------------------------------------------------ MMA issuer (leader CTA of a pair; warp-uniform loop, one elected lane issues)
         if (rank == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A/B = u8, both K-major, M = 128 / 256, N = n_blk
-            const uint32_t idesc = (2u << 4) | (0u << 7) | (0u << 10) | ((p.n_blk >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            // (F16: D = f32, A/B = bf16)
+            const uint32_t idesc = (F16 ? ((1u << 4) | (1u << 7) | (1u << 10)) : ((2u << 4) | (0u << 7) | (0u << 10))) | ((p.n_blk >> 3) << 17) |
+                                   ((uint32_t)(TILE_M >> 4) << 24);
             // one lane issues every MMA and an int8 MMA lasts ~100 cycles: descriptors differ only in their 14-bit start-address
             // field (low word), everything else is hoisted out of the loop
             const uint64_t a_desc0 = make_smem_desc(qb_smem_u32(a_s)), b_desc0 = make_smem_desc(qb_smem_u32(b_s));
@@ -392,11 +459,16 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (elect_one()) {
 #pragma unroll
                         for (uint32_t j = 0; j < KB / 32; ++j)
-                            if (k32 + j < n_k32)  // +32 B inside the swizzled row per K-step
-                                mma_i8<TWO>(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * j), ((uint64_t)b_hi << 32) | (b_lo + 2 * j), idesc, (k32 + j) != 0 ? 1u : 0u);
+                            if (k32 + j < n_k32) {  // +32 B inside the swizzled row per K-step (32 u8 codes, or 16 bf16 values)
+                                if (F16) mma_f16<TWO>(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * j), ((uint64_t)b_hi << 32) | (b_lo + 2 * j), idesc, (k32 + j) != 0 ? 1u : 0u);
+                                else mma_i8<TWO>(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * j), ((uint64_t)b_hi << 32) | (b_lo + 2 * j), idesc, (k32 + j) != 0 ? 1u : 0u);
+                            }
                         tc_commit<TWO>(&empty_a[s]);                      // frees the smem stage once the MMAs above have read it
                         if (ka + 1 == n_kb) {
-                            if (use_bias) mma_i8<TWO>(d_tmem, bias_a_desc, bias_b_desc, idesc, 1u);  // D += bias_q in every row
+                            if (use_bias) {                                                          // D += bias_q in every row
+                                if (F16) mma_f16<TWO>(d_tmem, bias_a_desc, bias_b_desc, idesc, 1u);
+                                else mma_i8<TWO>(d_tmem, bias_a_desc, bias_b_desc, idesc, 1u);
+                            }
                             tc_commit<TWO>(&tm_full[acc]);                                        // accumulator complete -> epilogue
                         }
                     }
@@ -409,12 +481,13 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t quarter = (uint32_t)(warp & 3);  // TMEM lanes this warp may read: [32*quarter, 32*quarter+32)
         const uint32_t part = (uint32_t)(warp >> 2);    // which of every EPI_PARTS 16-column chunks
         const uint32_t n_chunks = p.n_blk >> 4;
-        const bool pre = use_bias && p.multiplier > 0.0f;
+        const bool pre = use_bias && (F16 || p.multiplier > 0.0f);
         const int t_int = pre ? ((p.debug & 4) ? 0x7fffffff - T_CLAMP : *p.t_int) : -T_CLAMP;  // one threshold for the whole batch, in a register
+        const float t_f16 = (F16 && pre) ? __int_as_float(*p.t_int) : __int_as_float(0xff800000);  // F16: the same word holds the f32 threshold
         // the per-row offset (and delete bit) of the NEXT tile is fetched one tile ahead, off the critical path
         uint64_t row_n = (uint64_t)worker * TILE_M + row_in_tile0 + quarter * 32 + lane;
         bool valid_n = my_tiles > 0 && row_n < p.n_rows;
-        float voff_n = valid_n ? p.voff[row_n] : 0.0f;
+        float voff_n = (valid_n && !F16) ? p.voff[row_n] : 0.0f;
         bool dead_n = !valid_n || qb_is_deleted(emit, (uint32_t)(valid_n ? row_n : 0));
         for (uint64_t ti = 0; ti < my_tiles; ++ti) {
             const uint32_t acc = (uint32_t)(ti & 1), acc_ph = (uint32_t)((ti >> 1) & 1);
@@ -424,12 +497,12 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (ti + 1 < my_tiles) {
                 row_n = (worker + (ti + 1) * p.n_workers) * TILE_M + row_in_tile0 + quarter * 32 + lane;
                 valid_n = row_n < p.n_rows;
-                voff_n = valid_n ? p.voff[row_n] : 0.0f;
+                voff_n = (valid_n && !F16) ? p.voff[row_n] : 0.0f;
                 dead_n = !valid_n || qb_is_deleted(emit, (uint32_t)(valid_n ? row_n : 0));
             }
             // row term of the prefilter: score >= thr  <=>  dot >= t_query - v_off/mult; everything is rounded towards "pass"
             int vi = 0;
-            if (pre) {
+            if (pre && !F16) {
                 const float vm = v_off / p.multiplier;
                 const float up = ceilf(vm + 1.0e-5f * fabsf(vm)) + 2.0f;
                 vi = (int)fminf(fmaxf(up, (float)-T_CLAMP), (float)T_CLAMP);
@@ -452,11 +525,13 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (i & 1) {
                     tmem_ld_wait(rb);
                     if (c + EPI_PARTS < n_chunks) tmem_ld16_issue(t_addr + (c + EPI_PARTS) * 16, ra);
-                    epilogue_chunk(es, rb, c, t_row, row, row_flags, v_off);
+                    if (F16) epilogue_chunk_f16(es, rb, c, t_f16, row, row_flags);
+                    else epilogue_chunk(es, rb, c, t_row, row, row_flags, v_off);
                 } else {
                     tmem_ld_wait(ra);
                     if (c + EPI_PARTS < n_chunks) tmem_ld16_issue(t_addr + (c + EPI_PARTS) * 16, rb);
-                    epilogue_chunk(es, ra, c, t_row, row, row_flags, v_off);
+                    if (F16) epilogue_chunk_f16(es, ra, c, t_f16, row, row_flags);
+                    else epilogue_chunk(es, ra, c, t_row, row, row_flags, v_off);
                 }
             }
             tc_fence_before();
@@ -530,6 +605,130 @@ __global__ void __launch_bounds__(1024) qb_mma_bias_kernel(const float* __restri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- F16 (dense f32 storages): helpers
+__device__ __forceinline__ uint16_t bf16_rne(float f) {       // round to nearest even (finite inputs)
+    uint32_t u = __float_as_uint(f);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+__device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
+
+// f32 rows -> bf16 shadow rows (zero padded to the shadow stride); also max |row| (as float bits, rows are finite or the flag is raised)
+__global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __restrict__ rows, uint64_t stride_f, uint32_t dim, uint64_t n, uint16_t* __restrict__ out,
+                                                                uint32_t out_stride_h, unsigned int* __restrict__ max_norm_bits, unsigned int* __restrict__ nonfinite) {
+    const int t = threadIdx.x & 7;
+    const uint64_t groups = (uint64_t)gridDim.x * (blockDim.x >> 3), g0 = (uint64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    const uint64_t n_iter = (n + groups - 1) / groups;
+    for (uint64_t it = 0; it < n_iter; ++it) {
+        const uint64_t r = g0 + it * groups;
+        const bool valid = r < n;
+        const float* src = rows + (valid ? r : 0) * stride_f;
+        uint16_t* dst = out + (valid ? r : 0) * out_stride_h;
+        float ss = 0.f;
+        bool bad = false;
+        for (uint32_t i = t; i < out_stride_h; i += 8) {
+            const float v = (i < dim) ? src[i] : 0.f;
+            bad |= !(fabsf(v) <= 3.0e38f);
+            ss = fmaf(v, v, ss);
+            if (valid) dst[i] = bf16_rne(v);
+        }
+        ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 1); ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 2); ss += __shfl_xor_sync(0xFFFFFFFFu, ss, 4);
+        if (valid && t == 0) {
+            if (bad || !(ss <= 3.0e38f)) atomicOr(nonfinite, 1u);
+            else atomicMax(max_norm_bits, __float_as_uint(sqrtf(ss) * 1.000001f));   // non-negative floats order like their bit patterns
+        }
+    }
+}
+
+// queries: bf16 B rows [nq_pad][row_h] + eps_q; thresholds -> bias rows (two bf16 halves, hi + lo, duplicated in both 16-B halves of the
+// 32-B row so that the 32-B swizzle is immaterial), the f32 bias each query adds and the batch threshold T.  One CTA.
+__global__ void __launch_bounds__(1024) f16_prepare_kernel(const float* __restrict__ q, uint32_t q_stride_f, uint32_t dim, uint32_t row_h, uint32_t nq, uint32_t n_pad,
+                                                           const float* __restrict__ thr, const unsigned int* __restrict__ max_norm_bits, uint16_t* __restrict__ qb,
+                                                           uint8_t* __restrict__ bias_rows, int* __restrict__ bias_f, int* __restrict__ t_out, unsigned int* __restrict__ flags) {
+    __shared__ float s_t[1024];
+    __shared__ float s_T;
+    const float R = __uint_as_float(*max_norm_bits);
+    // eps_q and t_q = thr_q - eps_q (thread per query, strided)
+    float tmax = __int_as_float(0xff800000);
+    for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const float* src = q + (size_t)(i < nq ? i : 0) * q_stride_f;
+        uint16_t* dst = qb + (size_t)i * row_h;
+        double ss = 0.0;
+        for (uint32_t k = 0; k < row_h; ++k) {
+            const float v = (i < nq && k < dim) ? src[k] : 0.f;
+            ss += (double)v * (double)v;
+            dst[k] = bf16_rne(v);
+        }
+        if (i < nq) {
+            const float qn = (float)sqrt(ss) * 1.000001f;
+            if (!(qn <= 3.0e38f)) atomicOr(flags, 1u);      // NaN / inf in a query: OrderedFloat semantics need the exact path
+            // |approx - exact| <= (2^-8 + 2^-18 + K 2^-22) |q| |x|  (+ the rounding of adding the bias in the accumulator, + slack)
+            const float eps = (0.00390625f + 3.9e-6f + (float)row_h * 2.4e-7f) * qn * R * 1.01f + 1.0e-6f * (1.0f + fabsf(thr[i]));
+            const float t = thr[i] - eps;                  // -inf stays -inf: no threshold yet, everything must pass
+            reinterpret_cast<float*>(bias_f)[i] = t;         // parked; turned into the bias below
+            if (t > -3.0e38f && t > tmax) tmax = t;
+        }
+    }
+    s_t[threadIdx.x] = tmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float T = __int_as_float(0xff800000);
+        for (uint32_t i = 0; i < blockDim.x; ++i) T = fmaxf(T, s_t[i]);
+        if (!(T > -3.0e38f)) T = 0.0f;                       // no query has a threshold: T is arbitrary, every bias is "pass everything"
+        s_T = T;
+        *reinterpret_cast<float*>(t_out) = T;
+    }
+    __syncthreads();
+    const float T = s_T;
+    for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        float b = 0.0f;
+        if (i < nq) {
+            const float t = reinterpret_cast<float*>(bias_f)[i];
+            b = (t > -3.0e38f) ? (T - t) * 1.0000002f + 1.0e-30f : 1.0e30f;     // rounded towards "pass"
+            if (!(b >= 0.0f)) b = 0.0f;
+        }
+        // b / 2 = x + y with x = bf16 truncation, y = the remainder rounded UP to bf16: 2 (x + y) >= b, exactly representable in f32
+        const float h = 0.5f * b;
+        const uint16_t x = (uint16_t)(__float_as_uint(h) >> 16);
+        const float rem = h - bf16_to_f32(x);
+        uint32_t yu = __float_as_uint(rem);
+        uint16_t y = (uint16_t)(yu >> 16);
+        if ((yu & 0xFFFFu) != 0u) y += 1;                    // round the non-negative remainder up
+        const float applied = 2.0f * (bf16_to_f32(x) + bf16_to_f32(y));
+        bias_f[i] = __float_as_int(i < nq ? applied : 0.0f);
+        uint32_t w0 = (uint32_t)x | ((uint32_t)y << 16);
+        if (i >= nq) w0 = 0u;
+        const uint4 v = make_uint4(w0, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(bias_rows + (size_t)i * BIAS_KB)[0] = v;
+        reinterpret_cast<uint4*>(bias_rows + (size_t)i * BIAS_KB)[1] = v;
+    }
+}
+
+// Replace every surviving (approx score, local row) key by the exact AVX-order f32 score, or by "empty" when the exact score misses the
+// query's threshold: 8 lanes per candidate, the same chains as every other f32 path.  Lists are counted (cnt[q], capped at cap).
+__global__ void __launch_bounds__(256) f32_rescore_kernel(const uint8_t* __restrict__ rows, uint32_t stride, uint32_t dim, const float* __restrict__ q, uint32_t q_stride_f,
+                                                          uint32_t nq, unsigned long long* __restrict__ cand, const unsigned int* __restrict__ cnt, unsigned long long cap,
+                                                          const float* __restrict__ thr, uint32_t id_base) {
+    const int t = threadIdx.x & 7;
+    const uint32_t g = (blockIdx.x * (blockDim.x >> 3)) + (threadIdx.x >> 3), n_groups = gridDim.x * (blockDim.x >> 3);
+    for (uint32_t qi = blockIdx.y; qi < nq; qi += gridDim.y) {
+        const unsigned int c = min((unsigned long long)cnt[qi], cap);
+        const float* qv = q + (size_t)qi * q_stride_f;
+        const float th = thr[qi];
+        unsigned long long* list = cand + (unsigned long long)qi * cap;
+        const uint32_t n_iter = (c + n_groups - 1) / n_groups;
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const uint32_t i = g + it * n_groups;
+            const bool valid = i < c;
+            const unsigned long long key = valid ? list[i] : 0ull;
+            const uint32_t row = valid ? qb_key_id(key) : 0u;
+            const float sc = qbs::score_avx_group8<qbs::M_DOT>(reinterpret_cast<const float*>(rows + (size_t)row * stride), qv, dim, t);
+            if (valid && t == 0) list[i] = (key != 0ull && !(sc < th)) ? qb_pack_key(sc, row + id_base) : 0ull;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -558,8 +757,10 @@ qb_status make_map_u8(CUtensorMap* m, const void* base, uint64_t inner_bytes, ui
 }
 
 // query block width for a variant: resident B + A ring + small arrays must fit 227 KB; equal-width blocks
-uint32_t block_for(const qb_storage* s, uint32_t nq, bool two) {
-    const uint32_t n_kb = (s->actual_dim + KB - 1) / KB;
+uint32_t block_for_bytes(uint32_t k_bytes, uint32_t nq, bool two);
+uint32_t block_for(const qb_storage* s, uint32_t nq, bool two) { return block_for_bytes(s->actual_dim, nq, two); }
+uint32_t block_for_bytes(uint32_t k_bytes, uint32_t nq, bool two) {
+    const uint32_t n_kb = (k_bytes + KB - 1) / KB;
     const size_t budget = 227 * 1024 - (size_t)(two ? STAGES_2 : STAGES_1) * A_STAGE_BYTES - MMA_M * BIAS_KB - SMALL_SMEM;
     uint32_t n_blk = (uint32_t)(budget / ((size_t)n_kb * KB + BIAS_KB)) * (two ? 2u : 1u);
     const uint32_t gran = two ? 32u : 16u;
@@ -650,6 +851,111 @@ qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_
         QB_CUDA(cudaFuncSetAttribute(sq8_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sq8_mma_kernel<false><<<workers * n_qblocks, THREADS, smem, stream>>>(map_a, map_b, p, emit);
     }
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- dense f32 batches (F16 prefilter + exact rescoring)
+// bf16 shadow plane of a dense f32 storage, built on first use (and rebuilt after rows were rewritten): +50 % HBM for the storage, the
+// price of reading 2 bytes per element instead of 4 on every batched pass and of feeding the tensor cores.
+static qb_status f32_shadow_ensure(qb_storage* s, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(s->mu);          // concurrent first batches build it once
+    if (s->bf16_ready) return QB_OK;
+    const uint32_t row_h = (uint32_t)round_up_u64(s->dim, 8);
+    if (!s->d_bf16) {
+        QB_CUDA(cudaMalloc(&s->d_bf16, std::max<size_t>((size_t)s->count * row_h * 2, 256)));
+        QB_CUDA(cudaMalloc(&s->d_bf16_meta, 256));
+        s->hbm_bytes += (uint64_t)s->count * row_h * 2;
+    }
+    s->bf16_row_h = row_h;
+    QB_CUDA(cudaMemsetAsync(s->d_bf16_meta, 0, 256, stream));
+    const uint64_t blocks = std::min<uint64_t>(ceil_div_u64(std::max<uint64_t>(s->count, 1), 32), (uint64_t)s->sm_count * 16);
+    f32_to_bf16_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(s->d_rows), s->row_stride / 4, s->dim, s->count, s->d_bf16, row_h,
+                                                                  s->d_bf16_meta, s->d_bf16_meta + 1);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    unsigned int meta[2] = {0, 0};
+    QB_CUDA(cudaMemcpyAsync(meta, s->d_bf16_meta, 8, cudaMemcpyDeviceToHost, stream));
+    QB_CUDA(cudaStreamSynchronize(stream));
+    s->bf16_ready = true;
+    s->bf16_usable = meta[1] == 0;      // NaN / inf rows: OrderedFloat ranks NaN scores highest, only the exact kernels honour that
+    return QB_OK;
+}
+
+// Query block width of the tensor-core prefilter for a dense f32 storage (0 = not applicable); bit 31 = cta_group::2.
+uint32_t qb_f32_mma_block(qb_storage* s, uint32_t nq, cudaStream_t stream) {
+    if (s->kind != QB_KIND_DENSE || s->dtype != QB_DT_F32) return 0;
+    if (s->distance != QB_DIST_DOT && s->distance != QB_DIST_COSINE) return 0;   // the approximation bounds a dot product
+    if (nq < 32 || s->count < 65536 || s->dim < 32 || qb_opt().disable_mma) return 0;
+    if (f32_shadow_ensure(s, stream) != QB_OK) { cudaGetLastError(); return 0; }  // e.g. no room for the shadow plane: stay on the exact kernels
+    if (!s->bf16_usable) return 0;                                                // NaN / inf rows: only the exact kernels honour OrderedFloat
+    const uint32_t k_bytes = (uint32_t)round_up_u64(s->dim, 8) * 2;
+    if (!qb_opt().mma_1cta && !(s->sm_count & 1))
+        if (const uint32_t b2 = block_for_bytes(k_bytes, nq, true)) return b2 | 0x80000000u;
+    return block_for_bytes(k_bytes, nq, false);
+}
+size_t qb_f32_mma_scratch_bytes(const qb_storage* s, uint32_t nq_pad) { return (size_t)nq_pad * ((size_t)round_up_u64(s->dim, 8) * 2 + BIAS_KB + 4) + 512; }
+
+// Filter pass over rows [0, row_end): survivors of the bf16 prefilter are re-scored exactly and land, with their exact scores, in the
+// counted candidate lists of `emit` (emit.thr = exact per-query thresholds).  d_q_pre = preprocessed f32 queries [nq][q_stride_f].
+// Returns QB_ERR_UNSUPPORTED (nothing launched) when the storage holds non-finite values: the caller takes the exact path.
+qb_status qb_f32_mma_scan(qb_storage* s, const float* d_q_pre, uint32_t q_stride_f, uint32_t nq, uint32_t nq_pad, uint32_t n_blk_flag, uint64_t row_end, const QbEmit& emit,
+                          unsigned int* d_flags, void* d_scratch, size_t scratch_bytes, cudaStream_t stream) {
+    const bool two = (n_blk_flag & 0x80000000u) != 0;
+    const uint32_t n_blk = n_blk_flag & 0x7FFFFFFFu;
+    QB_CHECK(!emit.dense && emit.thr && emit.cnt, QB_ERR_INVALID, "f32_mma_scan: filter mode only");
+    QB_CHECK(s->bf16_ready && s->bf16_usable, QB_ERR_INVALID, "f32_mma_scan: no usable bf16 shadow (qb_f32_mma_block decides)");
+    const uint32_t row_h = s->bf16_row_h, ad = row_h * 2;
+    const uint32_t n_qblocks = (nq + n_blk - 1) / n_blk;
+    QB_CHECK(nq_pad >= n_qblocks * n_blk && nq_pad % 16 == 0, QB_ERR_INVALID, "f32_mma_scan: query block not padded");
+    QB_CHECK(d_scratch && scratch_bytes >= qb_f32_mma_scratch_bytes(s, nq_pad), QB_ERR_INVALID, "f32_mma_scan: scratch too small");
+    uint8_t* sc = reinterpret_cast<uint8_t*>(d_scratch);
+    uint16_t* qb = reinterpret_cast<uint16_t*>(sc);
+    uint8_t* bias_rows = sc + round_up_u64((size_t)nq_pad * ad, 256);
+    int* bias_f = reinterpret_cast<int*>(bias_rows + (size_t)nq_pad * BIAS_KB);
+    int* t_word = bias_f + nq_pad;
+    f16_prepare_kernel<<<1, 1024, 0, stream>>>(d_q_pre, q_stride_f, s->dim, row_h, nq, nq_pad, emit.thr, s->d_bf16_meta, qb, bias_rows, bias_f, t_word, d_flags);
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    MmaParams p{};
+    p.voff = nullptr; p.n_rows = row_end; p.ad = ad; p.n_blk = n_blk; p.n_qblocks = n_qblocks; p.nq = nq;
+    p.multiplier = 1.0f; p.q_off = nullptr; p.flags = d_flags; p.check_exact = 0; p.debug = qb_opt().mma_debug;
+    p.bias_rows = bias_rows; p.bias_i = bias_f; p.t_int = t_word; p.seg_cap = 0;
+    CUtensorMap map_a, map_b;
+    QB_TRY(make_map_u8(&map_a, s->d_bf16, ad, row_end, KB, MMA_M));
+    QB_TRY(make_map_u8(&map_b, qb, ad, nq_pad, KB, two ? n_blk / 2 : n_blk));
+    const uint32_t tile_m = two ? 2 * MMA_M : MMA_M;
+    const uint64_t n_tiles = (row_end + tile_m - 1) / tile_m;
+    uint32_t workers = (two ? (uint32_t)s->sm_count / 2 : (uint32_t)s->sm_count) / n_qblocks;
+    if (workers < 1) workers = 1;
+    if (workers > n_tiles) workers = (uint32_t)n_tiles;
+    p.n_workers = workers;
+    const uint32_t n_kb = (ad + KB - 1) / KB;
+    const size_t smem = (size_t)(two ? n_blk / 2 : n_blk) * ((size_t)n_kb * KB + BIAS_KB) + (size_t)(two ? STAGES_2 : STAGES_1) * A_STAGE_BYTES + MMA_M * BIAS_KB + SMALL_SMEM;
+    QB_CHECK(smem <= 227 * 1024, QB_ERR_INVALID, "f32_mma_scan: shared memory %zu exceeds 227 KB", smem);
+    if (two) {
+        QB_CUDA(cudaFuncSetAttribute(sq8_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * workers * n_qblocks);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        QB_CUDA(cudaLaunchKernelEx(&cfg, sq8_mma_kernel<true, true>, map_a, map_b, p, emit));
+    } else {
+        QB_CUDA(cudaFuncSetAttribute(sq8_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sq8_mma_kernel<false, true><<<workers * n_qblocks, THREADS, smem, stream>>>(map_a, map_b, p, emit);
+    }
+    QB_LAUNCHED();
+    QB_CUDA(cudaGetLastError());
+    // exact scores for the survivors (and only them)
+    const dim3 grid(8, std::min<uint32_t>(nq, (uint32_t)s->sm_count * 4));
+    f32_rescore_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(s->d_rows), s->row_stride, s->dim, d_q_pre, q_stride_f, nq, emit.cand, emit.cnt, emit.cap,
+                                                 emit.thr, emit.id_base);
     QB_LAUNCHED();
     QB_CUDA(cudaGetLastError());
     return QB_OK;

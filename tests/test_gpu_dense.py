@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from tests.util import assert_topk_equal
+from tests.util import assert_topk_equal, pack_bitmap
 
 pytestmark = pytest.mark.gpu
 
@@ -190,4 +190,57 @@ def test_filtered_scorer_like_hnsw_hop(qb, oracle):
     assert len(ids) == 16 and all(not deleted[i] for i in ids)
     qp = oracle.preprocess_f32(int(d), queries[0])
     np.testing.assert_array_equal(res["score"], oracle.score_points_f32(int(d), base, qp, np.array(ids, np.uint32)))
+    st.close()
+
+
+# ------------------------------------------------------------------------------------------------ batched f32 on the tensor cores (J1)
+@pytest.mark.parametrize("dist,n,dim,nq", [("Cosine", 150_000, 768, 200), ("Dot", 140_000, 100, 64), ("Cosine", 200_000, 128, 300), ("Dot", 131_072, 1536, 33)])
+def test_f32_batch_tensor_core_prefilter_is_exact(qb, oracle, dist, n, dim, nq):
+    """Batches of >= 32 f32 queries: bf16 tcgen05 prefilter + exact rescoring of the survivors == oracle peek_top_iter, bit-exact
+    scores, no fallback rerun, and == the CUDA-core path (option disable_mma)."""
+    d = getattr(qb.Distance, dist)
+    rng = np.random.default_rng(dim + nq)
+    base = (rng.standard_normal((n, dim)) * (1.0 if dist == "Cosine" else rng.uniform(0.2, 3.0, (n, 1)))).astype(np.float32)   # Dot: rows of very different norms
+    if d == qb.Distance.Cosine:
+        base = oracle.preprocess_rows_f32(oracle.COSINE, base)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    queries[0] = base[12345] * 3.0                    # a query whose best match is exact: score far above the rest
+    qp = np.stack([oracle.preprocess_f32(int(d), q) for q in queries])
+    deleted = rng.random(n) < 0.03
+    st = qb.DenseVectorStorage(base, d)
+    st.search_stats(reset=True)
+    got = st.search_batch(queries, 10, point_deleted=deleted)
+    searches, reruns = st.search_stats(reset=True)
+    assert (searches, reruns) == (1, 0), (searches, reruns)
+    want = oracle.scan_f32(int(d), base, qp, 10, deleted=pack_bitmap(deleted))
+    for i in range(nq):
+        assert_topk_equal(got[i], want[i], None, f"f32-mma {dist} q={i}")
+    qb.set_option("disable_mma", 1)
+    try:
+        got_cc = st.search_batch(queries[:40], 10, point_deleted=deleted)
+    finally:
+        qb.set_option("disable_mma", 0)
+    for a, b in zip(got[:40], got_cc):
+        np.testing.assert_array_equal(a, b)
+    st.close()
+
+
+def test_f32_batch_with_nan_rows_and_nan_queries_stays_exact(qb, oracle):
+    rng = np.random.default_rng(3)
+    n, dim, nq = 140_000, 64, 40
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    st = qb.DenseVectorStorage(base, qb.Distance.Dot)
+    queries[5, 3] = np.nan                            # every score of query 5 is NaN: the prefilter cannot rank it -> exact rerun
+    got = st.search_batch(queries, 5)
+    want = oracle.scan_f32(oracle.DOT, base, queries, 5)
+    for i in range(nq):
+        if i != 5:
+            assert_topk_equal(got[i], want[i], None, f"nan-query batch q={i}")
+    assert np.isnan(got[5]["score"]).all()
+    st.close()
+    base[777, 1] = np.nan                             # a NaN row ranks first for every query (OrderedFloat): the storage opts out of the prefilter
+    st = qb.DenseVectorStorage(base, qb.Distance.Dot)
+    got = st.search_batch(queries[:4].copy() * 0 + rng.standard_normal((4, dim)).astype(np.float32), 5)
+    assert all(g["idx"][0] == 777 and np.isnan(g["score"][0]) for g in got)
     st.close()

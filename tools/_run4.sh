@@ -3,6 +3,7 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_custom.py tests/test_gpu_hnsw_device.py tests/test_gpu_dense.py tests/test_gpu_formats.py tests/test_gpu_train.py -q -m gpu > gpurun_out/t_r2_d.log 2>&1; echo "rc=$?" >> gpurun_out/t_r2_d.log
 tail -8 gpurun_out/t_r2_d.log
+timeout 900 python tools/f32_batch_probe.py 10000000 1024 > gpurun_out/f32_batch_probe_a.json 2> gpurun_out/f32_batch_probe_a.err; cat gpurun_out/f32_batch_probe_a.json; tail -3 gpurun_out/f32_batch_probe_a.err
 timeout 600 python tools/hnsw_probe.py 200000 768 4096 128 > gpurun_out/hnsw_probe_b.json 2> gpurun_out/hnsw_probe_b.err; cat gpurun_out/hnsw_probe_b.json; tail -3 gpurun_out/hnsw_probe_b.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pq_scan4 --launch-skip 14 --launch-count 1 -o gpurun_out/ncu_pq4_r02 -f python bench.py --config c4 --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_pq4.log 2>&1; tail -3 gpurun_out/ncu_pq4.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:hnsw_search --launch-skip 1 --launch-count 1 -o gpurun_out/ncu_hnsw_r02 -f python tools/hnsw_probe.py 100000 768 2048 128 > gpurun_out/ncu_hnsw.log 2>&1; tail -3 gpurun_out/ncu_hnsw.log
