@@ -76,6 +76,8 @@ extern "C" {
     pub fn qb_search_feedback(s: *mut qb_storage, vectors: *const f32, n_pairs: u32, a: f32, partial: *const f32, top: u32, deleted_bitmap: *const u64, id_list: *const u32, n_ids: u64, is_stopped: *const i32, out: *mut qb_scored_point, out_count: *mut u32, counters: *mut qb_hw_counters) -> qb_status;
     pub fn qb_search_maxsim(s: *mut qb_storage, point_offsets: *const u32, n_points: u32, query_vectors: *const f32, n_query_vectors: u32, top: u32, deleted_points: *const u64, out: *mut qb_scored_point, out_count: *mut u32, counters: *mut qb_hw_counters) -> qb_status;
     pub fn qb_score_maxsim(s: *mut qb_storage, point_offsets: *const u32, n_points: u32, query_vectors: *const f32, n_query_vectors: u32, point_ids: *const u32, n: usize, scores: *mut f32) -> qb_status;
+    pub fn qb_search_maxsim_custom(s: *mut qb_storage, point_offsets: *const u32, n_points: u32, kind: i32, example_vectors: *const f32, example_offsets: *const u32, n_a: u32, n_b: u32, coef: *const f32, top: u32, deleted_points: *const u64, out: *mut qb_scored_point, out_count: *mut u32, counters: *mut qb_hw_counters) -> qb_status;
+    pub fn qb_score_maxsim_custom(s: *mut qb_storage, point_offsets: *const u32, n_points: u32, kind: i32, example_vectors: *const f32, example_offsets: *const u32, n_a: u32, n_b: u32, coef: *const f32, point_ids: *const u32, n: usize, scores: *mut f32) -> qb_status;
     pub fn qb_sq8_find_alpha_offset_device(device: i32, dim: u32, count: u64, dev_rows: *const f32, row_stride_bytes: u64, alpha: *mut f32, offset: *mut f32) -> qb_status;
     pub fn qb_sq8_encode_rows_device(device: i32, dim: u32, count: u64, dev_rows: *const f32, row_stride_bytes: u64, alpha: f32, offset: f32, dt: i32, invert: i32, dev_out: *mut u8, stream: *mut c_void) -> qb_status;
     pub fn qb_bq_row_bytes(dim: u32, encoding: i32) -> u32;

@@ -108,8 +108,9 @@ QB_API qb_status qb_storage_create_sq8(int32_t device, uint32_t dim, uint64_t co
 QB_API qb_status qb_storage_create_pq(int32_t device, uint32_t dim, uint32_t m, const uint32_t* div_start_end,
                                const float* centroids, uint32_t n_centroids, const uint8_t* codes, uint64_t count,
                                qb_qdistance dt, int32_t invert, qb_distance metric, qb_storage** out);
-/* BQ (u128 words): rows of row_bytes = ceil(bits/128)*16 (encoded_vectors_binary.rs:829-839);
- * mean_std = dim x {mean, stddev} for the 2-bit / 1.5-bit encodings (VectorStats), or NULL. */
+/* BQ: rows of row_bytes = ceil(bits/128)*16 (EncodedVectorsBin<u128>, single vectors, encoded_vectors_binary.rs:829-839) or
+ * ceil(bits/8) (EncodedVectorsBin<u8>, the token rows of multivector storages, quantized_vectors.rs:270-282; zero-padded to u128 words
+ * at upload); mean_std = dim x {mean, stddev} for the 2-bit / 1.5-bit encodings (VectorStats), or NULL. */
 QB_API qb_status qb_storage_create_bq(int32_t device, uint32_t dim, qb_bq_encoding enc, qb_bq_query_encoding qenc,
                                const uint8_t* rows, uint32_t row_bytes, uint64_t count, qb_qdistance dt, int32_t invert,
                                const float* mean_std, qb_distance metric, qb_storage** out);
@@ -227,6 +228,18 @@ QB_API qb_status qb_search_maxsim(qb_storage* s, const uint32_t* point_offsets, 
                                   qb_hw_counters* counters /* optional */);
 QB_API qb_status qb_score_maxsim(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, const float* query_vectors,
                                  uint32_t n_query_vectors, const uint32_t* point_ids, size_t n, float* scores);
+
+/* MultiCustomQueryScorer / QuantizedMultiCustomQueryScorer (query_scorer/multi_custom_query_scorer.rs:88-104, quantized/
+ * quantized_multi_custom_query_scorer.rs): a recommend / discover / context / feedback query whose EXAMPLES are multivectors.  A
+ * point's similarity to an example is MaxSim (score_multi), the per-example similarities are folded by Query::score_by like the
+ * single-vector custom queries.  example e = example_vectors rows [example_offsets[e], example_offsets[e + 1]) (raw f32 x dim), the
+ * examples ordered as qb_scorer_create_custom / qb_scorer_create_feedback order their vectors; coef = [a, partial computations...] for
+ * QB_QUERY_FEEDBACK_NAIVE, else NULL. */
+QB_API qb_status qb_search_maxsim_custom(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, qb_query_kind kind, const float* example_vectors,
+                                         const uint32_t* example_offsets, uint32_t n_a, uint32_t n_b, const float* coef, uint32_t top, const uint64_t* deleted_points,
+                                         qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters /* optional */);
+QB_API qb_status qb_score_maxsim_custom(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, qb_query_kind kind, const float* example_vectors,
+                                        const uint32_t* example_offsets, uint32_t n_a, uint32_t n_b, const float* coef, const uint32_t* point_ids, size_t n, float* scores);
 
 /* ---------------------------------------------------------------- quantizer encode on the device -- */
 /* The ENCODE half of the quantizers, on f32 rows already resident in HBM; outputs are the reference's row formats bit

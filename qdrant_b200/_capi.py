@@ -72,6 +72,9 @@ SIGNATURES = {
     "qb_bq_vector_stats_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, f32p, f32p]),
     "qb_sq8_quantile_interval_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_float, f32p, f32p, i32p]),
     "qb_pq_train_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_float, C.c_uint32, C.c_uint64, f32p, u32p]),
+    "qb_search_maxsim_custom": (C.c_int32, [vp, u32p, C.c_uint32, C.c_int, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.c_uint32, u64p, C.POINTER(ScoredPoint), u32p,
+                                            C.POINTER(HwCounters)]),
+    "qb_score_maxsim_custom": (C.c_int32, [vp, u32p, C.c_uint32, C.c_int, f32p, u32p, C.c_uint32, C.c_uint32, f32p, u32p, C.c_size_t, f32p]),
     "qb_rescore": (C.c_int32, [vp, u32p, C.c_size_t, C.c_uint32, C.POINTER(ScoredPoint), u32p]),
     "qb_storage_set_id_base": (C.c_int32, [vp, C.c_uint32]),
     "qb_topk_merge_device": (C.c_int32, [C.c_int32, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64, vp]),

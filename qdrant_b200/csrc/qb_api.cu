@@ -385,7 +385,18 @@ extern "C" qb_status qb_storage_create_bq(int32_t device, uint32_t dim, qb_bq_en
     QB_CHECK(out, QB_ERR_INVALID, "create_bq: null out");
     *out = nullptr;
     QB_CHECK(dim >= 1 && dim <= 65536, QB_ERR_INVALID, "create_bq: dim %u outside [1,65536]", dim);
-    QB_CHECK(row_bytes == bq_row_bytes_for(dim, enc), QB_ERR_INVALID, "create_bq: row_bytes %u != expected %u", row_bytes, bq_row_bytes_for(dim, enc));
+    // EncodedVectorsBin<u128, _> rows (single vectors) are whole u128 words; multivector storages use EncodedVectorsBin<u8, _> whose rows
+    // are ceil(bits / 8) bytes (quantized_vectors.rs:270-282).  Bit i sits in byte i / 8, bit i % 8 for both word types (little-endian
+    // words), so a u8 row is the prefix of the u128 row: it is zero-padded to whole u128 words at upload and scored by the same kernels
+    // (padding bits are zero in rows and queries alike and add nothing to any popcount).
+    const uint32_t rb128 = bq_row_bytes_for(dim, enc);
+    uint64_t ext_bits = dim;
+    if (enc == QB_BQ_TWO_BITS) ext_bits = (uint64_t)dim * 2;
+    else if (enc == QB_BQ_ONE_AND_HALF_BITS) ext_bits = ((uint64_t)dim * 3 + 1) / 2;
+    const uint32_t rb_u8 = (uint32_t)((std::max<uint64_t>(ext_bits, 1) + 7) / 8);
+    QB_CHECK(row_bytes == rb128 || row_bytes == rb_u8, QB_ERR_INVALID, "create_bq: row_bytes %u is neither the u128 row size %u nor the u8 row size %u", row_bytes, rb128, rb_u8);
+    const uint32_t src_row_bytes = row_bytes;
+    row_bytes = rb128;
     QB_CHECK(count == 0 || rows, QB_ERR_INVALID, "create_bq: null rows");
     QB_CHECK(count <= 0xFFFFFFFFull, QB_ERR_INVALID, "create_bq: count exceeds u32");
     QB_TRY(use_device(device));
@@ -396,7 +407,12 @@ extern "C" qb_status qb_storage_create_bq(int32_t device, uint32_t dim, qb_bq_en
     if (ok && mean_std) ok = cudaMalloc(&s->d_mean_std, (size_t)dim * 8) == cudaSuccess;
     if (!ok) { qb_set_error("create_bq: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); qb_storage_destroy(s); return QB_ERR_OOM; }
     s->hbm_bytes = rb;
-    cudaError_t e = count ? cudaMemcpy(s->d_bq_rows, rows, (size_t)count * row_bytes, cudaMemcpyDefault) : cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (count && src_row_bytes == row_bytes) e = cudaMemcpy(s->d_bq_rows, rows, (size_t)count * row_bytes, cudaMemcpyDefault);
+    else if (count) {
+        e = cudaMemset(s->d_bq_rows, 0, rb);
+        if (e == cudaSuccess) e = cudaMemcpy2D(s->d_bq_rows, row_bytes, rows, src_row_bytes, src_row_bytes, count, cudaMemcpyDefault);
+    }
     if (e == cudaSuccess && mean_std) e = cudaMemcpy(s->d_mean_std, mean_std, (size_t)dim * 8, cudaMemcpyDefault);
     if (e != cudaSuccess) { qb_set_error("create_bq: upload: %s", cudaGetErrorString(e)); qb_storage_destroy(s); return QB_ERR_CUDA; }
     *out = s;
@@ -1187,6 +1203,126 @@ extern "C" qb_status qb_score_maxsim(qb_storage* s, const uint32_t* point_offset
     QB_CHECK(n == 0 || (point_ids && scores), QB_ERR_INVALID, "score_maxsim: null argument");
     if (n == 0) return QB_OK;
     return maxsim_run(s, point_offsets, n_points, query_vectors, n_query_vectors, point_ids, n, nullptr, 0, nullptr, nullptr, scores, nullptr);
+}
+
+// MultiCustomQueryScorer (query_scorer/multi_custom_query_scorer.rs:88-104) / QuantizedMultiCustomQueryScorer: a custom query whose
+// examples are MULTIVECTORS; a point's similarity to an example is MaxSim (score_multi -> score_max_similarity), the per-example
+// similarities are folded by Query::score_by exactly like the single-vector custom queries.
+static qb_status maxsim_custom_run(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, qb_query_kind kind, const float* example_vectors,
+                                   const uint32_t* example_offsets, uint32_t n_a, uint32_t n_b, const float* coef, const uint32_t* point_ids, uint64_t n_sel,
+                                   const uint64_t* deleted_points, uint32_t top, qb_scored_point* out, uint32_t* out_count, float* scores, qb_hw_counters* counters) {
+    QB_CHECK(s && point_offsets && example_vectors && example_offsets, QB_ERR_INVALID, "maxsim_custom: null argument");
+    uint32_t ne = 0;
+    QB_TRY(check_custom(kind, n_a, n_b, &ne));
+    QB_CHECK(kind != QB_QUERY_FEEDBACK_NAIVE || coef, QB_ERR_INVALID, "maxsim_custom: feedback queries need [a, partial computations]");
+    for (uint32_t e = 0; e < ne; ++e) QB_CHECK(example_offsets[e] < example_offsets[e + 1], QB_ERR_INVALID, "maxsim_custom: example %u has no vectors", e);
+    for (uint32_t p = 0; p < n_points; ++p) QB_CHECK(point_offsets[p] <= point_offsets[p + 1], QB_ERR_INVALID, "maxsim_custom: point_offsets not ascending at %u", p);
+    QB_CHECK(n_points == 0 || point_offsets[n_points] <= s->count, QB_ERR_INVALID, "maxsim_custom: point_offsets end beyond the stored vectors");
+    const uint64_t n_pts = point_ids ? n_sel : n_points;
+    if (n_pts == 0) return QB_OK;
+    std::vector<uint32_t> h_off(n_pts + 1), h_rows;
+    uint64_t n_rows;
+    if (point_ids) {
+        uint64_t acc = 0;
+        for (uint64_t i = 0; i < n_pts; ++i) {
+            QB_CHECK(point_ids[i] < n_points, QB_ERR_INVALID, "maxsim_custom: point id %u out of range", point_ids[i]);
+            h_off[i] = (uint32_t)acc;
+            for (uint32_t r = point_offsets[point_ids[i]]; r < point_offsets[point_ids[i] + 1]; ++r) h_rows.push_back(r);
+            acc = h_rows.size();
+        }
+        h_off[n_pts] = (uint32_t)acc;
+        n_rows = acc;
+    } else {
+        for (uint64_t i = 0; i <= n_pts; ++i) h_off[i] = point_offsets[i];
+        n_rows = point_offsets[n_points];
+    }
+    uint32_t max_tok = 0;
+    const uint32_t total_tok = example_offsets[ne];
+    for (uint32_t e = 0; e < ne; ++e) max_tok = std::max(max_tok, example_offsets[e + 1] - example_offsets[e]);
+    QB_CHECK(max_tok <= 4096, QB_ERR_INVALID, "maxsim_custom: %u vectors in one example (max 4096)", max_tok);
+    QB_CHECK(n_rows * (4ull * max_tok + 4) + n_pts * (4ull * ne + 20) <= (16ull << 30), QB_ERR_UNSUPPORTED, "maxsim_custom: scratch budget exceeded");
+    QB_TRY(use_device(s->device));
+    QbSearchCtx* c = nullptr;
+    QB_TRY(qb_ctx_acquire(s, &c));
+    struct Rel { qb_storage* s; QbSearchCtx* c; ~Rel() { qb_ctx_release(s, c); } } rel{s, c};
+    cudaStream_t stream = c->stream;
+    const uint32_t n_coef = (kind == QB_QUERY_FEEDBACK_NAIVE) ? 1 + n_a : 0;
+    const size_t raw_bytes = (size_t)total_tok * s->dim * 4;
+    const size_t res_bytes = scores ? (size_t)n_pts * 4 : (size_t)top * sizeof(qb_scored_point);
+    QB_TRY(qb_ensure_pinned(&c->h_stage, &c->h_stage_bytes, raw_bytes + res_bytes + (size_t)n_coef * 4 + 16));
+    uint8_t* hs = reinterpret_cast<uint8_t*>(c->h_stage);
+    memcpy(hs, example_vectors, raw_bytes);
+    if (n_coef) memcpy(hs + raw_bytes + res_bytes, coef, (size_t)n_coef * 4);
+    QB_TRY(qb_ensure_device(&c->d_queries_raw, &c->queries_raw_bytes, round_up_u64(raw_bytes, 16) + (size_t)total_tok * pre_stride_f(s) * 4));
+    QB_TRY(qb_ensure_device(&c->d_queries_enc, &c->queries_enc_bytes, ((size_t)total_tok + 256) * qb_encoded_query_bytes(s)));
+    QB_TRY(ensure_dev_elems(&c->d_q_off, &c->q_off_elems, (size_t)total_tok));
+    QB_TRY(ensure_dev_elems(&c->d_ids, &c->ids_elems, (size_t)std::max<uint64_t>(n_rows, 1)));
+    QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)n_coef + 64));
+    // scratch: [token similarities max_tok x n_rows][per-example MaxSim ne x n_pts][column offsets n_pts + 1][final scores n_pts]
+    const size_t sims_bytes = round_up_u64((size_t)max_tok * n_rows * 4, 256), ex_bytes = round_up_u64((size_t)ne * n_pts * 4, 256), off_bytes = round_up_u64((n_pts + 1) * 4, 256);
+    QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, sims_bytes + ex_bytes + off_bytes + n_pts * 4 + 256));
+    uint8_t* sc = reinterpret_cast<uint8_t*>(c->d_mma);
+    float* d_sims = reinterpret_cast<float*>(sc);
+    float* d_ex = reinterpret_cast<float*>(sc + sims_bytes);
+    uint32_t* d_off = reinterpret_cast<uint32_t*>(sc + sims_bytes + ex_bytes);
+    float* d_scores = reinterpret_cast<float*>(sc + sims_bytes + ex_bytes + off_bytes);
+    QB_CUDA(cudaMemcpyAsync(c->d_queries_raw, hs, raw_bytes, cudaMemcpyHostToDevice, stream));
+    QB_TRY(prepare_queries(s, reinterpret_cast<const float*>(c->d_queries_raw), total_tok,
+                           reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->d_queries_raw) + round_up_u64(raw_bytes, 16)), c->d_queries_enc, c->d_q_off, stream));
+    QB_CUDA(cudaMemcpyAsync(d_off, h_off.data(), (n_pts + 1) * 4, cudaMemcpyHostToDevice, stream));
+    if (point_ids) { if (n_rows) QB_CUDA(cudaMemcpyAsync(c->d_ids, h_rows.data(), n_rows * 4, cudaMemcpyHostToDevice, stream)); }
+    else QB_TRY(qb_launch_iota(c->d_ids, n_rows, stream));
+    const float* d_coef = nullptr;
+    if (n_coef) { QB_CUDA(cudaMemcpyAsync(c->d_thr, hs + raw_bytes + res_bytes, (size_t)n_coef * 4, cudaMemcpyHostToDevice, stream)); d_coef = c->d_thr; }
+    for (uint32_t e = 0; e < ne; ++e) {
+        const uint32_t t0 = example_offsets[e], nt = example_offsets[e + 1] - t0;
+        for (uint32_t t = 0; t < nt && n_rows; ++t) QB_TRY(launch_example(s, c->d_queries_enc, c->d_q_off, t0 + t, false, c->d_ids, n_rows, d_sims + (size_t)t * n_rows, stream));
+        QB_TRY(qb_launch_maxsim_fold(d_sims, n_rows, nt, d_off, nullptr, n_pts, d_ex + (size_t)e * n_pts, nullptr, stream));
+    }
+    if (scores) {
+        QB_TRY(qb_launch_custom_combine((int)kind, n_a, n_b, d_coef, d_ex, n_pts, n_pts, d_scores, nullptr, nullptr, stream));
+        QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, d_scores, n_pts * 4, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaStreamSynchronize(stream));
+        memcpy(scores, hs + raw_bytes, n_pts * 4);
+    } else {
+        const uint32_t* d_del2 = nullptr;
+        if (deleted_points) {
+            const size_t words64 = (size_t)ceil_div_u64(n_points, 64);
+            QB_TRY(ensure_dev_elems(&c->d_deleted2, &c->deleted2_words, words64 * 2));
+            QB_CUDA(cudaMemcpyAsync(c->d_deleted2, deleted_points, words64 * 8, cudaMemcpyHostToDevice, stream));
+            d_del2 = c->d_deleted2;
+        }
+        QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)n_pts));
+        QB_TRY(ensure_dev_elems(&c->d_out, &c->out_elems, (size_t)top));
+        QB_TRY(ensure_dev_elems(&c->d_out_counts, &c->out_counts_elems, (size_t)8));
+        QbEmit emit{};
+        emit.cand = c->d_cand; emit.cap = n_pts; emit.dense = 1; emit.dense_base = 0; emit.deleted = nullptr; emit.deleted2 = d_del2; emit.id_base = 0;
+        QB_TRY(qb_launch_custom_combine((int)kind, n_a, n_b, d_coef, d_ex, n_pts, n_pts, nullptr, nullptr, &emit, stream));
+        QB_TRY(qb_launch_select(c->d_cand, nullptr, n_pts, n_pts, 1, top, 0, c->d_out, c->d_out_counts, nullptr, nullptr, stream));
+        QB_CUDA(cudaMemcpyAsync(hs + raw_bytes, c->d_out, res_bytes, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaMemcpyAsync(hs + raw_bytes + res_bytes + (size_t)n_coef * 4, c->d_out_counts, 4, cudaMemcpyDeviceToHost, stream));
+        QB_CUDA(cudaStreamSynchronize(stream));
+        memcpy(out, hs + raw_bytes, res_bytes);
+        memcpy(out_count, hs + raw_bytes + res_bytes + (size_t)n_coef * 4, 4);
+    }
+    if (counters) { counters->cpu += n_rows * (uint64_t)total_tok * cpu_units_per_point(s); counters->vector_io_read += n_rows * (uint64_t)ne * (s->on_disk ? 1 : 0); }
+    return QB_OK;
+}
+
+extern "C" qb_status qb_search_maxsim_custom(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, qb_query_kind kind, const float* example_vectors,
+                                             const uint32_t* example_offsets, uint32_t n_a, uint32_t n_b, const float* coef, uint32_t top, const uint64_t* deleted_points,
+                                             qb_scored_point* out, uint32_t* out_count, qb_hw_counters* counters) {
+    QB_CHECK(out && out_count, QB_ERR_INVALID, "search_maxsim_custom: null output");
+    QB_CHECK(top >= 1 && top <= QB_MAX_TOP, QB_ERR_INVALID, "search_maxsim_custom: top %u outside [1,%u]", top, QB_MAX_TOP);
+    *out_count = 0;
+    return maxsim_custom_run(s, point_offsets, n_points, kind, example_vectors, example_offsets, n_a, n_b, coef, nullptr, 0, deleted_points, top, out, out_count, nullptr, counters);
+}
+
+extern "C" qb_status qb_score_maxsim_custom(qb_storage* s, const uint32_t* point_offsets, uint32_t n_points, qb_query_kind kind, const float* example_vectors,
+                                            const uint32_t* example_offsets, uint32_t n_a, uint32_t n_b, const float* coef, const uint32_t* point_ids, size_t n, float* scores) {
+    QB_CHECK(n == 0 || (point_ids && scores), QB_ERR_INVALID, "score_maxsim_custom: null argument");
+    if (n == 0) return QB_OK;
+    return maxsim_custom_run(s, point_offsets, n_points, kind, example_vectors, example_offsets, n_a, n_b, coef, point_ids, n, nullptr, 0, nullptr, nullptr, scores, nullptr);
 }
 
 extern "C" void qb_scorer_destroy(qb_scorer* sc) {

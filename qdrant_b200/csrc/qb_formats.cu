@@ -201,7 +201,13 @@ extern "C" qb_status qb_storage_load_quantized(int32_t device, qb_distance metri
         }
     }
     QB_CHECK(enc == QB_BQ_ONE_BIT || !ms.empty(), QB_ERR_INVALID, "load_quantized: two-bit / one-and-a-half-bit encodings need vector_stats");
-    const uint32_t rb = qb_bq_row_bytes(dim, (qb_bq_encoding)enc);
+    uint32_t rb = qb_bq_row_bytes(dim, (qb_bq_encoding)enc);
+    {   // multivector storages hold u8-word rows: ceil(bits / 8) bytes (quantized_vectors.rs:270-282); recognised when the byte count says so
+        uint64_t ext = dim;
+        if (enc == QB_BQ_TWO_BITS) ext = (uint64_t)dim * 2; else if (enc == QB_BQ_ONE_AND_HALF_BITS) ext = ((uint64_t)dim * 3 + 1) / 2;
+        const uint32_t rb8 = (uint32_t)((ext + 7) / 8);
+        if (count && rb8 != rb && n_bytes < count * (uint64_t)rb && n_bytes >= count * (uint64_t)rb8) rb = rb8;
+    }
     if (!count) count = n_bytes / rb;
     QB_CHECK(count * rb <= n_bytes, QB_ERR_INVALID, "load_quantized: %llu rows of %u bytes exceed quantized.data", (unsigned long long)count, rb);
     return qb_storage_create_bq(device, dim, (qb_bq_encoding)enc, (qb_bq_query_encoding)qenc, data, rb, count, (qb_qdistance)vp.dt, vp.invert, ms.empty() ? nullptr : ms.data(),

@@ -598,6 +598,36 @@ class MultiVectorView:
                                     ids.ctypes.data_as(u32p), ids.size, scores.ctypes.data_as(f32p)))
         return scores
 
+    # ---- custom queries whose examples are multivectors (MultiCustomQueryScorer, multi_custom_query_scorer.rs:88-104).  `query` is one of the
+    # query classes above with 2-D arrays (vectors x dim) in place of vectors.
+    def _flat_multi(self, query):
+        examples, n_a, n_b = query.flat()
+        mats = [self._query(e) for e in examples]
+        off = np.concatenate([[0], np.cumsum([m.shape[0] for m in mats])]).astype(np.uint32)
+        coef = None
+        if query.kind == QueryKind.FeedbackNaive:
+            coef = np.concatenate([[np.float32(query.a)], query.partial]).astype(np.float32)
+        return np.ascontiguousarray(np.concatenate(mats)), off, n_a, n_b, coef
+
+    def search_custom(self, query, top: int, point_deleted=None) -> np.ndarray:
+        vecs, off, n_a, n_b, coef = self._flat_multi(query)
+        out = np.zeros(max(top, 1), dtype=SCORED_POINT_OFFSET)
+        count = C.c_uint32()
+        bm = _bitmap(point_deleted, self.n_points)
+        check(lib().qb_search_maxsim_custom(self.storage._h, self.offsets.ctypes.data_as(u32p), self.n_points, int(query.kind), vecs.ctypes.data_as(f32p),
+                                            off.ctypes.data_as(u32p), n_a, n_b, None if coef is None else coef.ctypes.data_as(f32p), int(top),
+                                            None if bm is None else bm.ctypes.data_as(u64p), out.ctypes.data_as(C.POINTER(ScoredPoint)), C.byref(count), None))
+        return out[: count.value].copy()
+
+    def score_points_custom(self, query, points: Sequence[int]) -> np.ndarray:
+        vecs, off, n_a, n_b, coef = self._flat_multi(query)
+        ids = _ids(points)
+        scores = np.empty(ids.size, dtype=np.float32)
+        check(lib().qb_score_maxsim_custom(self.storage._h, self.offsets.ctypes.data_as(u32p), self.n_points, int(query.kind), vecs.ctypes.data_as(f32p),
+                                           off.ctypes.data_as(u32p), n_a, n_b, None if coef is None else coef.ctypes.data_as(f32p), ids.ctypes.data_as(u32p), ids.size,
+                                           scores.ctypes.data_as(f32p)))
+        return scores
+
 
 # ------------------------------------------------------------------------------------------------ quantizer encode on the device
 # Thin wrappers over the C ABI (include/qb200.h, "quantizer encode on the device"): every pointer is a raw device address.

@@ -171,3 +171,23 @@ def test_short_bitmap_is_rejected_and_io_counter_follows_on_disk(qb, oracle):
     sc.score_points(np.arange(7, dtype=np.uint32))
     assert sc.take_hardware_counters() == (7 * 32 * 4, 7 * 32 * 4)
     sc.close(); st.close()
+
+
+@pytest.mark.parametrize("enc", ["OneBit", "TwoBits", "OneAndHalfBits"])
+def test_bq_u8_word_rows_of_multivector_storages(qb, oracle, enc):
+    """EncodedVectorsBin<u8> rows (ceil(bits / 8) bytes, quantized_vectors.rs:270-282) score exactly like the u128 rows they are a prefix of."""
+    rng = np.random.default_rng(7)
+    n, dim = 2000, 100                                   # 100 bits: 13 bytes as u8 words, 16 bytes as one u128 word
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    e = int(getattr(qb.BQEncoding, enc))
+    ms = oracle.bq_mean_std(base) if e != oracle.BQ_ONE else None
+    bq = oracle.BQ.encode(base, e, oracle.BQQ_SCALAR8, oracle.QD_DOT, False, ms)
+    ext = {0: dim, 1: 2 * dim, 2: (3 * dim + 1) // 2}[e]
+    rows8 = np.ascontiguousarray(bq.rows[:, : (ext + 7) // 8])
+    assert not bq.rows[:, (ext + 7) // 8 :].any()
+    a = qb.BinaryQuantizedVectors(bq.rows, dim, qb.Distance.Dot, qb.BQEncoding(e), qb.BQQueryEncoding.Scalar8bits, ms)
+    b = qb.BinaryQuantizedVectors(rows8, dim, qb.Distance.Dot, qb.BQEncoding(e), qb.BQQueryEncoding.Scalar8bits, ms)
+    q = rng.standard_normal((3, dim)).astype(np.float32)
+    for x, y in zip(a.search_batch(q, 10), b.search_batch(q, 10)):
+        np.testing.assert_array_equal(x, y)
+    a.close(); b.close()

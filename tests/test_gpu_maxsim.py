@@ -100,3 +100,40 @@ def test_maxsim_rejects_bad_offsets(qb):
     with pytest.raises(QbError):
         qb.MultiVectorView(st, [0, 5, 10]).score_points(np.ones((1, 8), np.float32), [2])
     st.close()
+
+
+@pytest.mark.parametrize("dist", ["Cosine", "Euclid"])
+def test_custom_queries_over_multivectors(qb, oracle, dist):
+    """MultiCustomQueryScorer (multi_custom_query_scorer.rs:88-104): the examples of a recommend / discover / context / feedback query are
+    multivectors; similarity(example, point) = MaxSim; Query::score_by folds them."""
+    d = getattr(qb.Distance, dist)
+    rng = np.random.default_rng(33)
+    n_points, dim = 400, 48
+    off = make_points(rng, n_points, 6)
+    rows = oracle.preprocess_rows_f32(int(d), rng.standard_normal((int(off[-1]), dim)).astype(np.float32))
+    st = qb.DenseVectorStorage(rows, d)
+    mv = qb.MultiVectorView(st, off)
+    mvec = lambda: rng.standard_normal((int(rng.integers(1, 5)), dim)).astype(np.float32)  # noqa: E731
+    pos, neg, part = oracle.feedback_pairs(np.array([0.9, 0.2, 0.5], np.float32), 1.2, 0.7)
+    items = [mvec() for _ in range(3)]
+    queries = [
+        qb.RecoBestScoreQuery(qb.RecoQuery([mvec(), mvec()], [mvec()])),
+        qb.RecoSumScoresQuery(qb.RecoQuery([mvec()], [mvec(), mvec()])),
+        qb.DiscoverQuery(mvec(), [qb.ContextPair(mvec(), mvec()), qb.ContextPair(mvec(), mvec())]),
+        qb.ContextQuery([qb.ContextPair(mvec(), mvec())]),
+        qb.FeedbackQuery(mvec(), [qb.ContextPair(items[i], items[j]) for i, j in zip(pos, neg)], part, 0.8),
+    ]
+    # the query classes hold 1-D vectors by default: store the matrices as given
+    for q in queries:
+        ex, n_a, n_b = q.flat()
+        sims = np.stack([np.array([oracle.maxsim_f32(int(d), np.stack([oracle.preprocess_f32(int(d), t) for t in np.atleast_2d(e)]), rows[off[p] : off[p + 1]])
+                                   for p in range(n_points)], np.float32) for e in ex])
+        want = oracle.feedback_score(q.a, q.partial, sims) if int(q.kind) == 5 else oracle.custom_combine(int(q.kind), n_a, n_b, sims)
+        ids = np.arange(n_points, dtype=np.uint32)
+        np.testing.assert_array_equal(mv.score_points_custom(q, ids), want)
+        got = mv.search_custom(q, 10)
+        order = np.argsort(-want, kind="stable")[:10]
+        ref = np.zeros(order.size, dtype=got.dtype)
+        ref["idx"], ref["score"] = order, want[order]
+        assert_topk_equal(got, ref, want, f"multi custom {dist} kind {int(q.kind)}")
+    st.close()
