@@ -373,6 +373,7 @@ def main_ours(args):
                 parity["sharded_equals_merge_of_shards"] = True
     searches, reruns = st.search_stats()
     assert reruns == 0, f"{reruns} fallback reruns in the C2 path"
+    exchange = {"peer": "peer-mapped buffers over NVLink, fused into the merge kernel", "nccl": "NCCL all-gather", "none": "single GPU"}[searcher.exchange]
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         qp = np.stack([o.preprocess_f32(o.COSINE, x) for x in queries])
@@ -391,7 +392,7 @@ def main_ours(args):
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(c2_config(args.rows, args.dim), rows_per_gpu=n_local, parallelism=f"row-sharded x{world}, top-k exchange over NVLink + device merge",
+            "config": dict(c2_config(args.rows, args.dim), rows_per_gpu=n_local, parallelism=f"row-sharded x{world}, top-k exchange ({exchange}) + device merge",
                            l2="inputs larger than L2 (shard = %.1f GB >> 126 MB), no flush needed" % (algo_bytes / 1e9)),
             "gb_per_s_scanned": qps * args.rows * args.dim * 4 / 1e9,
             "e2e": {"value": K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": args.dim * 4, "d2h_bytes_per_step": TOP * 8 + 4,

@@ -266,15 +266,42 @@ __global__ void __launch_bounds__(1024, 1) pq_scan2_kernel(const PqParams p, con
 
 // Four queries per pass on a CTA PAIR (thread-block cluster of 2): the four LUTs are interleaved as float4, so ONE 16-byte shared
 // load serves four queries and — more to the point on random codes — a quarter-warp's 8 gathers spread over 8 sixteen-byte bank
-// groups collide far less than 32 four-byte gathers over 32 banks (expected serialisation ~2.4x instead of ~3.5x).  Four
-// interleaved LUTs are 4 x m x 256 x 4 B = 384 KB at m = 96: CTA 0 holds chunks [0, m/2), CTA 1 chunks [m/2, m).  CTA 0 runs the
-// first half of every row's four-lane accumulation, hands the 16 partial sums (4 lanes x 4 queries) to CTA 1 through DISTRIBUTED
-// SHARED MEMORY (double-buffered, one cluster barrier per 256-row tile), CTA 1 continues the very same f32 chains — lane k keeps
-// adding chunks j = k (mod 4) in ascending j — and finishes with (s0+s2)+(s1+s3): score_point_sse's order exactly
-// (encoded_vectors_pq.rs:411-443).  Requires m % 32 == 0 (16-byte code loads per half), m <= 96 (LUT half <= 192 KB).
-// The launcher walks the code plane in L2-sized row blocks and runs ALL query quads over a block before moving on, so HBM
-// sees every code byte once per batch instead of once per query group.
-constexpr int PQ4_THREADS = 256;
+// groups collide less than 32 four-byte gathers over 32 banks.  Four interleaved LUTs are 4 x m x 256 x 4 B = 384 KB at m = 96:
+// CTA 0 holds chunks [0, m/2), CTA 1 chunks [m/2, m).  CTA 0 runs the first half of every row's four-lane accumulation and hands the
+// 16 partial sums (4 lanes x 4 queries) to CTA 1 through DISTRIBUTED SHARED MEMORY; CTA 1 continues the very same f32 chains — lane
+// k keeps adding chunks j = k (mod 4) in ascending j — and finishes with (s0+s2)+(s1+s3): score_point_sse's order exactly
+// (encoded_vectors_pq.rs:411-443).  The hand-off is per WARP: thread t of warp w in CTA 0 feeds thread t of warp w in CTA 1 through one
+// 64-byte slot, guarded by a full / empty mbarrier pair per warp (remote arrives), so the sixteen warp pairs drift freely — no CTA-wide
+// or cluster-wide barrier inside the row loop — and the consumer frees the slot as soon as it has the partial sums in registers.
+// Requires m % 32 == 0 (16-byte code loads per half), m <= 96 (LUT half <= 192 KB).  The launcher walks the code plane in L2-sized
+// row blocks and runs ALL query quads over a block before moving on, so HBM sees every code byte once per batch.
+constexpr int PQ4_THREADS = 512;
+constexpr int PQ4_WARPS = PQ4_THREADS / 32;
+
+__device__ __forceinline__ uint32_t pq4_map_to_cta(const void* smem_ptr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(qb_smem_u32(smem_ptr)), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void pq4_remote_arrive(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void pq4_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope: the data came from the peer CTA
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(qb_smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 8000000000ll) __trap();   // a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void pq4_st_remote_f4(uint32_t cluster_addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_scan4_kernel(const PqParams p, const QbEmit emit) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(16) float lut_s[];
@@ -282,42 +309,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_s
     const uint32_t rank = cluster.block_rank();
     const uint32_t K = p.n_centroids, mh = p.m >> 1, j0 = rank * mh;
     float4* lut4 = reinterpret_cast<float4*>(lut_s);                 // [mh][K]
-    float4* hand = lut4 + (size_t)mh * K;                            // [2 stages][4][PQ4_THREADS]   (CTA 1's copy is the one in use)
-    float4* hand_remote = cluster.map_shared_rank(hand, 1);          // CTA 0 writes into CTA 1's buffer
-    const int tid = threadIdx.x;
+    float4* hand = lut4 + (size_t)mh * K;                            // [4][PQ4_THREADS]   (CTA 1's copy is the one in use)
+    uint64_t* full = reinterpret_cast<uint64_t*>(hand + 4 * PQ4_THREADS);   // [PQ4_WARPS] in CTA 1: "warp w's partial sums have landed"
+    uint64_t* empty = full + PQ4_WARPS;                                     // [PQ4_WARPS] in CTA 0: "warp w's slot may be overwritten"
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < PQ4_WARPS) { qb_mbar_init(&full[tid], 1); qb_mbar_init(&empty[tid], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cluster.sync();                                                  // both CTAs' barriers exist before any remote arrive
+    const uint32_t hand_remote = pq4_map_to_cta(hand, 1);            // CTA 0 writes into CTA 1's slot
+    const uint32_t full_remote = pq4_map_to_cta(&full[warp], 1);
+    const uint32_t empty_remote = pq4_map_to_cta(&empty[warp], 0);
     const uint64_t n = p.end - p.begin;
     const uint64_t n_tiles = (n + PQ4_THREADS - 1) / PQ4_THREADS;
     const uint32_t cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const size_t lut_elems = (size_t)p.m * K;
+    uint32_t it = 0;                                                 // hand-offs done by this warp so far (both CTAs count alike)
     for (uint32_t q0 = 0; q0 < p.nq; q0 += 4) {
         // ---- interleaved LUT half of this CTA: lut4[jl][c] = (lut_q0, lut_q0+1, lut_q0+2, lut_q0+3)[j0 + jl][c]
         const float* l0 = p.luts + (size_t)q0 * lut_elems + (size_t)j0 * K;
         const float* l1 = (q0 + 1 < p.nq) ? l0 + lut_elems : l0;
         const float* l2 = (q0 + 2 < p.nq) ? l0 + 2 * lut_elems : l0;
         const float* l3 = (q0 + 3 < p.nq) ? l0 + 3 * lut_elems : l0;
+        __syncthreads();                                             // every warp of this CTA is done with the previous quad's LUT
         for (uint32_t i = tid; i < mh * K; i += PQ4_THREADS) lut4[i] = make_float4(l0[i], l1[i], l2[i], l3[i]);
         __syncthreads();
-        uint32_t it = 0;
         for (uint64_t t = cid; t < n_tiles; t += n_clusters, ++it) {
             const uint64_t ci = t * PQ4_THREADS + tid;
             const bool valid = ci < n;
             const uint64_t cand = p.begin + (valid ? ci : 0);
             const uint8_t* code = p.codes + (size_t)cand * p.stride + j0;
+            uint4 cw[3];                                             // m <= 96: at most 48 code bytes per half, fetched before any waiting
+#pragma unroll
+            for (int w = 0; w < 3; ++w) cw[w] = (w * 16u < mh) ? *reinterpret_cast<const uint4*>(code + w * 16) : make_uint4(0, 0, 0, 0);
             float4 s0, s1, s2, s3;
-            float4* hb = (rank == 0 ? hand_remote : hand) + (size_t)(it & 1u) * 4 * PQ4_THREADS;
             if (rank == 0) {
                 s0 = s1 = s2 = s3 = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
-                cluster.sync();                                       // tile `it` of CTA 0 has landed in hand[it & 1]
-                s0 = hb[0 * PQ4_THREADS + tid]; s1 = hb[1 * PQ4_THREADS + tid]; s2 = hb[2 * PQ4_THREADS + tid]; s3 = hb[3 * PQ4_THREADS + tid];
+                pq4_wait_cluster(&full[warp], it & 1u);             // this warp's partial sums of tile `it` have landed
+                s0 = hand[0 * PQ4_THREADS + tid]; s1 = hand[1 * PQ4_THREADS + tid]; s2 = hand[2 * PQ4_THREADS + tid]; s3 = hand[3 * PQ4_THREADS + tid];
+                __syncwarp();
+                if (lane == 0) pq4_remote_arrive(empty_remote);      // slot free again: the producer warp may run ahead into the next tile
             }
-            for (uint32_t j = 0; j < mh; j += 16) {
-                const uint4 cw = *reinterpret_cast<const uint4*>(code + j);
-                const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                if (w * 16u >= mh) break;
+                const uint32_t wd[4] = {cw[w].x, cw[w].y, cw[w].z, cw[w].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float4* l = lut4 + (size_t)(j + 4 * k) * K;
-                    const float4 a = l[w[k] & 255u], b = l[K + ((w[k] >> 8) & 255u)], c = l[2 * K + ((w[k] >> 16) & 255u)], d = l[3 * K + (w[k] >> 24)];
+                    const float4* l = lut4 + (size_t)(w * 16 + 4 * k) * K;
+                    const float4 a = l[wd[k] & 255u], b = l[K + ((wd[k] >> 8) & 255u)], c = l[2 * K + ((wd[k] >> 16) & 255u)], d = l[3 * K + (wd[k] >> 24)];
                     s0.x = __fadd_rn(s0.x, a.x); s0.y = __fadd_rn(s0.y, a.y); s0.z = __fadd_rn(s0.z, a.z); s0.w = __fadd_rn(s0.w, a.w);
                     s1.x = __fadd_rn(s1.x, b.x); s1.y = __fadd_rn(s1.y, b.y); s1.z = __fadd_rn(s1.z, b.z); s1.w = __fadd_rn(s1.w, b.w);
                     s2.x = __fadd_rn(s2.x, c.x); s2.y = __fadd_rn(s2.y, c.y); s2.z = __fadd_rn(s2.z, c.z); s2.w = __fadd_rn(s2.w, c.w);
@@ -325,8 +365,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_s
                 }
             }
             if (rank == 0) {
-                hb[0 * PQ4_THREADS + tid] = s0; hb[1 * PQ4_THREADS + tid] = s1; hb[2 * PQ4_THREADS + tid] = s2; hb[3 * PQ4_THREADS + tid] = s3;
-                cluster.sync();                                       // release tile `it` to CTA 1 (and: CTA 1 is done with hand[(it + 1) & 1])
+                if (it > 0) pq4_wait_cluster(&empty[warp], (it - 1) & 1u);   // the consumer has taken tile it - 1 out of the slot
+                pq4_st_remote_f4(hand_remote + (0 * PQ4_THREADS + tid) * 16u, s0);
+                pq4_st_remote_f4(hand_remote + (1 * PQ4_THREADS + tid) * 16u, s1);
+                pq4_st_remote_f4(hand_remote + (2 * PQ4_THREADS + tid) * 16u, s2);
+                pq4_st_remote_f4(hand_remote + (3 * PQ4_THREADS + tid) * 16u, s3);
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");   // every lane's remote stores are ordered before the warp's arrive
+                __syncwarp();
+                if (lane == 0) pq4_remote_arrive(full_remote);       // release: the warp's stores are visible to the consumer warp before the flip
             } else if (valid) {
                 const uint32_t row = (uint32_t)cand;
                 const float r0 = __fadd_rn(__fadd_rn(s0.x, s2.x), __fadd_rn(s1.x, s3.x));
@@ -339,10 +385,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_s
                 if (q0 + 3 < p.nq) qb_emit(emit, q0 + 3, cand, row, r3);
             }
         }
-        // both CTAs meet before the LUTs / hand-off buffers are reused by the next quad (and before either may exit: a CTA's shared
-        // memory must outlive its peer's last remote access)
-        cluster.sync();
     }
+    cluster.sync();   // a CTA's shared memory (slot, barriers) must outlive its peer's last remote access
 }
 
 // score_internal (encoded_vectors_pq.rs:574-618): decode both codes through the centroids; single pair
@@ -602,7 +646,7 @@ static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cu
     p.codes = s->d_pq_codes; p.stride = s->pq_stride; p.m = s->pq_m; p.n_centroids = s->n_centroids;
     const size_t lut_bytes = (size_t)s->pq_m * s->n_centroids * sizeof(float);
     const int qpp = qb_opt().pq_queries_per_pass;   // 0 = automatic; 1 / 2 / 4 force a kernel (experiments)
-    const size_t smem4 = 2 * lut_bytes + (size_t)2 * 4 * PQ4_THREADS * 16;   // interleaved LUT half (4 queries x m/2 chunks) + hand-off stages
+    const size_t smem4 = 2 * lut_bytes + (size_t)4 * PQ4_THREADS * 16 + (size_t)2 * PQ4_WARPS * 8;   // interleaved LUT half (4 queries x m/2 chunks) + hand-off slot + barriers
     if (p.emit_mode && !p.ids && (qpp == 0 || qpp == 4) && p.nq >= 3 && s->pq_m % 32 == 0 && smem4 <= 227 * 1024 && n >= 65536 && s->sm_count >= 2) {
         // batched scans: four queries per pass on CTA pairs; row blocks sized to stay in L2 while every query quad visits them
         QB_CUDA(cudaFuncSetAttribute(pq_scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));

@@ -51,15 +51,32 @@ class ShardedSegmentSearcher:
         self.comm = vp()
         self.exchange = exchange if self.world > 1 else "none"
         if self.exchange == "peer":
+            # every step is agreed on by all ranks: if CUDA IPC is not available on this box (container policy), ALL ranks take the NCCL exchange
+            ok, why = 1, ""
             h = vp()
-            check(lib().qb_comm_create(device.index, self.rank, self.world, self.max_queries, self.top, C.byref(h)))
-            self.comm = h
+            if lib().qb_comm_create(device.index, self.rank, self.world, self.max_queries, self.top, C.byref(h)) != 0:
+                ok, why = 0, lib().qb_last_error().decode("utf-8", "replace")
             mine = (C.c_uint8 * 64)()
-            check(lib().qb_comm_local_handle(self.comm, mine))
+            if ok and lib().qb_comm_local_handle(h, mine) != 0:
+                ok, why = 0, lib().qb_last_error().decode("utf-8", "replace")
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(mine))      # 64 bytes per rank, once
-            blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
-            check(lib().qb_comm_connect(self.comm, blob))
+            dist.all_gather_object(handles, (ok, bytes(mine)))      # 64 bytes per rank, once
+            ok = int(all(x[0] for x in handles))
+            if ok:
+                blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(x[1] for x in handles))
+                if lib().qb_comm_connect(h, blob) != 0:
+                    ok, why = 0, lib().qb_last_error().decode("utf-8", "replace")
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok)
+            if all(flags):
+                self.comm = h
+            else:
+                if h:
+                    lib().qb_comm_destroy(h)
+                self.exchange = "nccl"
+                if self.rank == 0:
+                    import sys
+                    print(f"[qdrant_b200] peer-memory exchange unavailable ({why or 'a peer rank failed'}): using the NCCL all-gather exchange", file=sys.stderr)
             dist.barrier()
         self.stream = torch.cuda.ExternalStream(storage.stream_ptr(), device=device)
         nq, k, w = self.max_queries, self.top, self.world

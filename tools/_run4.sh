@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_custom.py tests/test_gpu_hnsw_device.py tests/test_gpu_dense.py tests/test_gpu_formats.py tests/test_gpu_train.py -q -m gpu > gpurun_out/t_r2_d.log 2>&1; echo "rc=$?" >> gpurun_out/t_r2_d.log
+timeout 900 python -m pytest tests/test_gpu_custom.py tests/test_gpu_hnsw_device.py tests/test_gpu_dense.py tests/test_gpu_formats.py tests/test_gpu_train.py tests/test_gpu_maxsim.py tests/test_gpu_edges.py tests/test_gpu_quant.py tests/test_gpu_multi_local.py -q -m gpu > gpurun_out/t_r2_d.log 2>&1; echo "rc=$?" >> gpurun_out/t_r2_d.log
 tail -8 gpurun_out/t_r2_d.log
 timeout 900 python tools/f32_batch_probe.py 10000000 1024 > gpurun_out/f32_batch_probe_a.json 2> gpurun_out/f32_batch_probe_a.err; cat gpurun_out/f32_batch_probe_a.json; tail -3 gpurun_out/f32_batch_probe_a.err
 timeout 600 python tools/hnsw_probe.py 200000 768 4096 128 > gpurun_out/hnsw_probe_b.json 2> gpurun_out/hnsw_probe_b.err; cat gpurun_out/hnsw_probe_b.json; tail -3 gpurun_out/hnsw_probe_b.err
