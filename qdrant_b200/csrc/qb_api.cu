@@ -82,6 +82,8 @@ extern "C" qb_status qb_set_option(const char* name, int64_t value) {
     else if (n == "sample_rows") o.sample_rows = (uint64_t)value;
     else if (n == "verbose") o.verbose = value != 0;
     else if (n == "pq_queries_per_pass") o.pq_queries_per_pass = (int)value;
+    else if (n == "hnsw_threads") o.hnsw_threads = (int)value;
+    else if (n == "hnsw_no_prefetch") o.hnsw_no_prefetch = value != 0;
     else { qb_set_error("set_option: unknown option '%s'", name); return QB_ERR_INVALID; }
     return QB_OK;
 }

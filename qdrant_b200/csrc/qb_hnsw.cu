@@ -35,8 +35,6 @@ using namespace qbs;
 
 namespace {
 
-constexpr int HNSW_THREADS = 256;
-constexpr int HNSW_GROUPS = HNSW_THREADS / 8;
 constexpr uint32_t HNSW_MAX_LINKS = 64;      // links scored per hop (m0 <= 64)
 constexpr uint32_t HNSW_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t HNSW_MAX_EF = 4096;
@@ -66,6 +64,7 @@ struct HnswParams {
     // results
     qb_scored_point* out; uint32_t* out_counts; uint32_t id_base;
     unsigned long long* stats;                   // [0] hops (scorer calls), [1] scored points
+    int prefetch;                                // 1: bulk-prefetch the surviving neighbours' vectors into L2 before scoring
 };
 
 struct HnswSmem {
@@ -91,8 +90,9 @@ __device__ __forceinline__ float score_one(const HnswParams& p, const uint8_t* q
 }
 
 // scores ids[0..n) into sc[0..n): one 8-lane group per id (dense small dims: one thread per id)
-template <int KIND, int METRIC>
+template <int KIND, int METRIC, int NT>
 __device__ __forceinline__ void score_list(const HnswParams& p, const HnswSmem& sm, float q_off, uint32_t n) {
+    constexpr int HNSW_GROUPS = NT / 8;
     const int tid = threadIdx.x;
     if (KIND == HK_DENSE_SMALL) {
         if ((uint32_t)tid < n) sm.sc[tid] = score_one<KIND, METRIC>(p, sm.q, q_off, sm.ids[tid], 0);
@@ -124,8 +124,9 @@ __device__ __forceinline__ bool hnsw_filtered_out(const HnswParams& p, uint32_t 
     return d;
 }
 
-template <int KIND, int METRIC>
-__global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswParams p) {
+template <int KIND, int METRIC, int NT>
+__global__ void __launch_bounds__(NT) hnsw_search_kernel(const HnswParams p) {
+    constexpr int HNSW_THREADS = NT;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ unsigned int s_q, s_best, s_n, s_nvalid, s_len, s_nlog, s_cur, s_changed, s_warp_cnt[2];
     __shared__ float s_cur_score;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
         __syncthreads();
 
         // ---- search_entry: greedy descent from the entry point's level to level 1 (graph_layers.rs:247-316)
-        score_list<KIND, METRIC>(p, sm, q_off, 1);      // score_point(entry)
+        score_list<KIND, METRIC, NT>(p, sm, q_off, 1);      // score_point(entry)
         __syncthreads();
         if (tid == 0) { s_cur = p.entry; s_cur_score = sm.sc[0]; ++hops; ++evals; }
         __syncthreads();
@@ -185,14 +186,14 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
                         const bool keep = l != HNSW_EMPTY && l < p.n_points && !hnsw_filtered_out(p, l);
                         const unsigned int bal = __ballot_sync(0xFFFFFFFFu, keep);
                         const uint32_t pos = cnt + __popc(bal & ((1u << tid) - 1u));
-                        if (keep && pos < p.m && pos < HNSW_MAX_LINKS) { sm.ids[pos] = l; prefetch_point<KIND>(p, l); }
+                        if (keep && pos < p.m && pos < HNSW_MAX_LINKS) { sm.ids[pos] = l; if (p.prefetch) prefetch_point<KIND>(p, l); }
                         cnt += __popc(bal);
                     }
                     if (tid == 0) s_n = min(min(cnt, p.m), HNSW_MAX_LINKS);
                 }
                 __syncthreads();
                 const uint32_t n = s_n;
-                score_list<KIND, METRIC>(p, sm, q_off, n);
+                score_list<KIND, METRIC, NT>(p, sm, q_off, n);
                 __syncthreads();
                 if (tid == 0) {
                     bool changed = false;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
                 asm volatile("bar.sync 1, 64;" ::: "memory");
                 const uint32_t pos = ((tid >> 5) ? s_warp_cnt[0] : 0u) + __popc(bal & ((1u << (tid & 31)) - 1u));
                 if (keep) {
-                    prefetch_point<KIND>(p, l);          // HBM -> L2 for the whole vector, in flight while the list is published
+                    if (p.prefetch) prefetch_point<KIND>(p, l);          // HBM -> L2 for the whole vector, in flight while the list is published
                     sm.ids[pos] = l;
                     const uint32_t lp = s_nlog + pos;
                     if (lp < p.vlog_cap) vlog[lp] = l;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
             if (tid == 0) { s_nlog += n; if (n) { ++hops; evals += n; } s_nvalid = 0; }
             if (n == 0) { __syncthreads(); continue; }
             // 3. score
-            score_list<KIND, METRIC>(p, sm, q_off, n);
+            score_list<KIND, METRIC, NT>(p, sm, q_off, n);
             __syncthreads();
             // 4. keys of the new points; the ones that cannot enter a full list are dropped here (key 0 = empty)
             const unsigned long long lower = (len == ef) ? keys[ef - 1] : 0ull;
@@ -318,12 +319,12 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswPar
     if (tid == 0 && p.stats) { atomicAdd(&p.stats[0], hops); atomicAdd(&p.stats[1], evals); }
 }
 
-template <int KIND>
+template <int KIND, int NT>
 qb_status launch_kind(int metric, const HnswParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
 #define QB_HNSW_LAUNCH(M)                                                                                              \
     do {                                                                                                               \
-        QB_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<KIND, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        hnsw_search_kernel<KIND, M><<<grid, HNSW_THREADS, smem, stream>>>(p);                                          \
+        QB_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<KIND, M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        hnsw_search_kernel<KIND, M, NT><<<grid, NT, smem, stream>>>(p);                                                \
     } while (0)
     if (KIND == HK_SQ8 || KIND == HK_SQ8_LANEX) QB_HNSW_LAUNCH(M_DOT);
     else if (metric == M_EUCLID) QB_HNSW_LAUNCH(M_EUCLID);
@@ -335,12 +336,30 @@ qb_status launch_kind(int metric, const HnswParams& p, unsigned grid, size_t sme
     return QB_OK;
 }
 
-template <int KIND, int METRIC>
+template <int KIND, int METRIC, int NT>
 int occupancy_of(size_t smem) {
     int nb = 0;
-    cudaFuncSetAttribute(hnsw_search_kernel<KIND, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hnsw_search_kernel<KIND, METRIC>, HNSW_THREADS, smem) != cudaSuccess) nb = 1;
+    cudaFuncSetAttribute(hnsw_search_kernel<KIND, METRIC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hnsw_search_kernel<KIND, METRIC, NT>, NT, smem) != cudaSuccess) nb = 1;
     return nb < 1 ? 1 : nb;
+}
+template <int NT>
+int occupancy_dispatch(int kind, int metric, size_t smem) {
+    switch (kind) {
+        case HK_DENSE_AVX: return metric == M_EUCLID ? occupancy_of<HK_DENSE_AVX, M_EUCLID, NT>(smem) : metric == M_MANHATTAN ? occupancy_of<HK_DENSE_AVX, M_MANHATTAN, NT>(smem) : occupancy_of<HK_DENSE_AVX, M_DOT, NT>(smem);
+        case HK_DENSE_SMALL: return metric == M_EUCLID ? occupancy_of<HK_DENSE_SMALL, M_EUCLID, NT>(smem) : metric == M_MANHATTAN ? occupancy_of<HK_DENSE_SMALL, M_MANHATTAN, NT>(smem) : occupancy_of<HK_DENSE_SMALL, M_DOT, NT>(smem);
+        case HK_SQ8: return occupancy_of<HK_SQ8, M_DOT, NT>(smem);
+        default: return occupancy_of<HK_SQ8_LANEX, M_DOT, NT>(smem);
+    }
+}
+template <int NT>
+qb_status launch_dispatch(int kind, int metric, const HnswParams& p, unsigned grid, size_t smem, cudaStream_t stream) {
+    switch (kind) {
+        case HK_DENSE_AVX: return launch_kind<HK_DENSE_AVX, NT>(metric, p, grid, smem, stream);
+        case HK_DENSE_SMALL: return launch_kind<HK_DENSE_SMALL, NT>(metric, p, grid, smem, stream);
+        case HK_SQ8: return launch_kind<HK_SQ8, NT>(metric, p, grid, smem, stream);
+        default: return launch_kind<HK_SQ8_LANEX, NT>(metric, p, grid, smem, stream);
+    }
 }
 
 }  // namespace
@@ -450,13 +469,11 @@ qb_status qb_hnsw_launch(qb_hnsw* g, const void* d_q_enc, const float* d_q_off, 
     p.out = d_out; p.out_counts = d_counts; p.id_base = s->id_base; p.stats = g->d_stats;
     const size_t smem = hnsw_smem_bytes(p.q_bytes, ef);
     QB_CHECK(smem <= 200 * 1024, QB_ERR_UNSUPPORTED, "hnsw_search: query (%u B) + ef %u need %zu B of shared memory", p.q_bytes, ef, smem);
-    int per_sm;
-    switch (kind) {
-        case HK_DENSE_AVX: per_sm = metric == M_EUCLID ? occupancy_of<HK_DENSE_AVX, M_EUCLID>(smem) : metric == M_MANHATTAN ? occupancy_of<HK_DENSE_AVX, M_MANHATTAN>(smem) : occupancy_of<HK_DENSE_AVX, M_DOT>(smem); break;
-        case HK_DENSE_SMALL: per_sm = metric == M_EUCLID ? occupancy_of<HK_DENSE_SMALL, M_EUCLID>(smem) : metric == M_MANHATTAN ? occupancy_of<HK_DENSE_SMALL, M_MANHATTAN>(smem) : occupancy_of<HK_DENSE_SMALL, M_DOT>(smem); break;
-        case HK_SQ8: per_sm = occupancy_of<HK_SQ8, M_DOT>(smem); break;
-        default: per_sm = occupancy_of<HK_SQ8_LANEX, M_DOT>(smem); break;
-    }
+    // threads per CTA: 256 = one 8-lane group per level-0 link (m0 = 32), fewer queries in flight per SM; 128 = two scoring rounds per hop,
+    // twice the resident queries.  The traversal is a chain of dependent memory round trips, so queries in flight is what hides them.
+    const int nt = qb_opt().hnsw_threads == 128 ? 128 : 256;
+    const int per_sm = nt == 128 ? occupancy_dispatch<128>(kind, metric, smem) : occupancy_dispatch<256>(kind, metric, smem);
+    p.prefetch = qb_opt().hnsw_no_prefetch ? 0 : 1;
     const unsigned max_grid = (unsigned)s->sm_count * (unsigned)per_sm;
     const unsigned grid = std::min<unsigned>(max_grid, nq);
     // per-CTA visited bitmaps + logs (grown on demand, zeroed once: the kernel leaves them clean)
@@ -471,12 +488,7 @@ qb_status qb_hnsw_launch(qb_hnsw* g, const void* d_q_enc, const float* d_q_off, 
     }
     p.visited = g->d_visited; p.visited_words = words; p.vlog = g->d_vlog; p.vlog_cap = g->vlog_cap; p.work = g->d_work;
     QB_CUDA(cudaMemsetAsync(g->d_work, 0, 4, stream));
-    switch (kind) {
-        case HK_DENSE_AVX: return launch_kind<HK_DENSE_AVX>(metric, p, grid, smem, stream);
-        case HK_DENSE_SMALL: return launch_kind<HK_DENSE_SMALL>(metric, p, grid, smem, stream);
-        case HK_SQ8: return launch_kind<HK_SQ8>(metric, p, grid, smem, stream);
-        default: return launch_kind<HK_SQ8_LANEX>(metric, p, grid, smem, stream);
-    }
+    return nt == 128 ? launch_dispatch<128>(kind, metric, p, grid, smem, stream) : launch_dispatch<256>(kind, metric, p, grid, smem, stream);
 }
 
 qb_status qb_hnsw_read_stats(qb_hnsw* g, cudaStream_t stream) {

@@ -26,6 +26,14 @@ entry, lvl, m, m0 = g.entry()
 blob = g.export_plain()
 st = qb.DenseVectorStorage(base, qb.Distance.Cosine)
 hg = qb.HnswGraph(st, blob, m, m0)
+variants = {}
+for nt in (256, 128):
+    for nopf in (0, 1):
+        qb.set_option("hnsw_threads", nt); qb.set_option("hnsw_no_prefetch", nopf)
+        hg.search(queries[:256], 10, ef, entry, lvl)
+        t0 = time.perf_counter(); hg.search(queries, 10, ef, entry, lvl); dt = time.perf_counter() - t0
+        variants[f"threads{nt}_{'noprefetch' if nopf else 'prefetch'}"] = nq / dt
+qb.set_option("hnsw_threads", 0); qb.set_option("hnsw_no_prefetch", 0)
 hg.search(queries[:256], 10, ef, entry, lvl)
 hg.stats(reset=True)
 t0 = time.perf_counter(); got = hg.search(queries, 10, ef, entry, lvl); gpu_s = time.perf_counter() - t0
@@ -37,4 +45,4 @@ exact = st.search_batch(queries[:200], 10)
 rec = float(np.mean([np.mean(r["score"] >= e["score"][-1]) for r, e in zip(got[:200], exact)]))
 print(json.dumps({"rows": n, "dim": dim, "queries": nq, "ef": ef, "build_s": build_s, "threads": threads, "gpu_qps_e2e": nq / gpu_s, "cpu_qps_all_threads": nq / cpu_s,
                   "cpu_qps_1_thread": nq / cpu1_s, "identical_lists": same, "recall_at_10": rec, "hops_per_query": hops / nq, "evals_per_query": evals / nq,
-                  "gpu_ms_per_query_serial_equiv": gpu_s / nq * 1e3}))
+                  "gpu_ms_per_query_serial_equiv": gpu_s / nq * 1e3, "variants_qps_e2e": variants}))
