@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(con
                         const LkState st = lk_drain(LkState{my_key, wmin, wthr}, lk_queue + cw * 4, &lk_count[cw], lane, n_queued);
                         my_key = st.my_key; wmin = st.wmin; wthr = st.wthr;
                     }
-                } else if (p.nq == 1) {
+                } else if (p.nq == 1 && !p.fold_kind) {
                     const float sc = score_avx_group8<METRIC>(rp, q_s, p.dim, t);
                     if (valid && t == 0) qb_emit(emit, 0, r0 + rin, (uint32_t)(r0 + rin), sc);
                 } else if (p.nq <= 2) stream_score_multi<METRIC, 2>(p, emit, rp, q_s, stride_f, t, valid, r0 + rin);

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(1024, 1) pq_scan2_kernel(const PqParams p, con
 // 16 partial sums (4 lanes x 4 queries) to CTA 1 through DISTRIBUTED SHARED MEMORY; CTA 1 continues the very same f32 chains — lane
 // k keeps adding chunks j = k (mod 4) in ascending j — and finishes with (s0+s2)+(s1+s3): score_point_sse's order exactly
 // (encoded_vectors_pq.rs:411-443).  The hand-off is per WARP: thread t of warp w in CTA 0 feeds thread t of warp w in CTA 1 through one
-// 64-byte slot, guarded by a full / empty mbarrier pair per warp (remote arrives), so the sixteen warp pairs drift freely — no CTA-wide
+// 64-byte slot: the producer's st.async stores complete transaction bytes on the consumer warp's `full` mbarrier, the consumer's remote
+// arrive on the producer warp's `empty` mbarrier frees the slot, so the sixteen warp pairs drift freely — no fence, no CTA-wide
 // or cluster-wide barrier inside the row loop — and the consumer frees the slot as soon as it has the partial sums in registers.
 // Requires m % 32 == 0 (16-byte code loads per half), m <= 96 (LUT half <= 192 KB).  The launcher walks the code plane in L2-sized
 // row blocks and runs ALL query quads over a block before moving on, so HBM sees every code byte once per batch.
@@ -298,8 +299,12 @@ __device__ __forceinline__ void pq4_wait_cluster(uint64_t* bar, uint32_t parity)
         else if (clock64() - t0 > 8000000000ll) __trap();   // a protocol bug must not hang the GPU
     }
 }
-__device__ __forceinline__ void pq4_st_remote_f4(uint32_t cluster_addr, float4 v) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+// asynchronous remote store that credits its 16 bytes to the CONSUMER's mbarrier (st.async ... complete_tx): the producer needs neither
+// a fence nor an arrive — the consumer arms the barrier with the 2048 bytes a warp hands over and waits for them
+__device__ __forceinline__ void pq4_st_async_f4(uint32_t cluster_addr, float4 v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "r"(cluster_bar)
+                 : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_scan4_kernel(const PqParams p, const QbEmit emit) {
@@ -345,6 +350,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_s
             if (rank == 0) {
                 s0 = s1 = s2 = s3 = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
+                if (lane == 0) qb_mbar_arrive_expect_tx(&full[warp], 32u * 64u);   // arm: 32 lanes x 4 float4 arrive through st.async
                 pq4_wait_cluster(&full[warp], it & 1u);             // this warp's partial sums of tile `it` have landed
                 s0 = hand[0 * PQ4_THREADS + tid]; s1 = hand[1 * PQ4_THREADS + tid]; s2 = hand[2 * PQ4_THREADS + tid]; s3 = hand[3 * PQ4_THREADS + tid];
                 __syncwarp();
@@ -366,13 +372,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_s
             }
             if (rank == 0) {
                 if (it > 0) pq4_wait_cluster(&empty[warp], (it - 1) & 1u);   // the consumer has taken tile it - 1 out of the slot
-                pq4_st_remote_f4(hand_remote + (0 * PQ4_THREADS + tid) * 16u, s0);
-                pq4_st_remote_f4(hand_remote + (1 * PQ4_THREADS + tid) * 16u, s1);
-                pq4_st_remote_f4(hand_remote + (2 * PQ4_THREADS + tid) * 16u, s2);
-                pq4_st_remote_f4(hand_remote + (3 * PQ4_THREADS + tid) * 16u, s3);
-                asm volatile("fence.acq_rel.cluster;" ::: "memory");   // every lane's remote stores are ordered before the warp's arrive
-                __syncwarp();
-                if (lane == 0) pq4_remote_arrive(full_remote);       // release: the warp's stores are visible to the consumer warp before the flip
+                pq4_st_async_f4(hand_remote + (0 * PQ4_THREADS + tid) * 16u, s0, full_remote);
+                pq4_st_async_f4(hand_remote + (1 * PQ4_THREADS + tid) * 16u, s1, full_remote);
+                pq4_st_async_f4(hand_remote + (2 * PQ4_THREADS + tid) * 16u, s2, full_remote);
+                pq4_st_async_f4(hand_remote + (3 * PQ4_THREADS + tid) * 16u, s3, full_remote);
             } else if (valid) {
                 const uint32_t row = (uint32_t)cand;
                 const float r0 = __fadd_rn(__fadd_rn(s0.x, s2.x), __fadd_rn(s1.x, s3.x));
