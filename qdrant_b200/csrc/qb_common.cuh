@@ -45,7 +45,7 @@ struct QbOptions {
     bool disable_localk = false, disable_mma = false, mma_1cta = false, mma_no_segments = false, verbose = false;
     int mma_debug = 0;
     int pq_queries_per_pass = 0;   // 0 = automatic
-    int hnsw_threads = 0;          // 0 / 256 (default) or 128 threads per traversal CTA
+    int hnsw_threads = 0;          // 0 / 128 (default) or 256 threads per traversal CTA
     bool hnsw_no_prefetch = false;
     uint64_t sample_rows = 0;
 };

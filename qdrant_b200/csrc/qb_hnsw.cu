@@ -8,7 +8,7 @@
 //   FilteredScorer::score_points   point_scorer.rs:265-295   (filter, truncate to level_m, score)
 // which calls the scorer once per hop with <= m0 ids.  Through a per-call GPU boundary that loop is launch/latency bound
 // (round 1: 10x slower than the CPU scorer); here the loop itself runs on the device: one persistent CTA per in-flight
-// query, graph links resident in HBM, the query in shared memory, the hop's neighbours scored by the CTA's 8-lane groups
+// query (128 threads), graph links resident in HBM, the query in shared memory, the hop's neighbours scored by the CTA's 8-lane groups
 // with the SAME bit-exact per-pair arithmetic as the scan kernels (qb_score.cuh), so a hop costs three dependent memory
 // round trips (links, visited flags, vectors) and no host interaction.  Throughput comes from many queries in flight
 // (SMs x resident CTAs), not from one fast query.
@@ -469,9 +469,10 @@ qb_status qb_hnsw_launch(qb_hnsw* g, const void* d_q_enc, const float* d_q_off, 
     p.out = d_out; p.out_counts = d_counts; p.id_base = s->id_base; p.stats = g->d_stats;
     const size_t smem = hnsw_smem_bytes(p.q_bytes, ef);
     QB_CHECK(smem <= 200 * 1024, QB_ERR_UNSUPPORTED, "hnsw_search: query (%u B) + ef %u need %zu B of shared memory", p.q_bytes, ef, smem);
-    // threads per CTA: 256 = one 8-lane group per level-0 link (m0 = 32), fewer queries in flight per SM; 128 = two scoring rounds per hop,
-    // twice the resident queries.  The traversal is a chain of dependent memory round trips, so queries in flight is what hides them.
-    const int nt = qb_opt().hnsw_threads == 128 ? 128 : 256;
+    // threads per CTA: 256 = one 8-lane group per level-0 link (m0 = 32), fewer queries in flight per SM; 128 (default) = two scoring rounds
+    // per hop, twice the resident queries.  The traversal is a chain of dependent memory round trips, so queries in flight is what hides
+    // them: measured 519 K vs 276-423 K q/s (500K x 768, ef 128, 8192-query batch, through the host API).
+    const int nt = qb_opt().hnsw_threads == 256 ? 256 : 128;
     const int per_sm = nt == 128 ? occupancy_dispatch<128>(kind, metric, smem) : occupancy_dispatch<256>(kind, metric, smem);
     p.prefetch = qb_opt().hnsw_no_prefetch ? 0 : 1;
     const unsigned max_grid = (unsigned)s->sm_count * (unsigned)per_sm;
