@@ -200,7 +200,7 @@ void qb_ctx_release(qb_storage* s, QbSearchCtx* c) {
 static void ctx_destroy(QbSearchCtx* c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_queries_raw); cudaFree(c->d_queries_enc); cudaFree(c->d_q_off); cudaFree(c->d_thr); cudaFree(c->d_cnt);
+    cudaFree(c->d_queries_raw); cudaFree(c->d_queries_enc); cudaFree(c->d_q_off); cudaFree(c->d_thr); cudaFree(c->d_cnt); cudaFree(c->d_done);
     cudaFree(c->d_cand); cudaFree(c->d_out); cudaFree(c->d_out_counts); cudaFree(c->d_deleted2); cudaFree(c->d_ids); cudaFree(c->d_mma);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -628,6 +628,9 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         QbScanArgs a{};
         a.d_q_enc = c->d_queries_enc; a.nq = 1; a.row_begin = 0; a.row_end = n_cand;
         a.emit.deleted = s->d_deleted; a.emit.deleted2 = d_deleted2; a.emit.id_base = s->id_base; a.emit.cand = c->d_cand; a.emit.cap = 4096;
+        // the last CTA of the scan merges the per-CTA lists into d_out itself (d_done = its arrival counter: zeroed once, reset by the kernel)
+        if (!c->d_done) { QB_CUDA(cudaMalloc(&c->d_done, 256)); QB_CUDA(cudaMemsetAsync(c->d_done, 0, 256, stream)); }
+        a.emit.final_out = d_out; a.emit.final_count = d_counts; a.emit.done_counter = c->d_done;
         uint64_t n_slots = 0;
         cudaEvent_t e0, e1;
         profile_begin(s, c, stream, &e0, &e1);
@@ -635,7 +638,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         if (n_slots != 0 && n_slots <= 4096) {
             profile_end(s, stream, e0, e1);
             if (can_flag) *can_flag = false;
-            return qb_launch_select(c->d_cand, nullptr, 4096, n_slots, 1, top, 0, d_out, d_counts, nullptr, nullptr, stream);
+            return QB_OK;
         }
         if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
         QB_CHECK(n_slots == 0, QB_ERR_CUDA, "local top-k scan wrote %llu slots", (unsigned long long)n_slots);

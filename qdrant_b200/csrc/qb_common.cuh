@@ -106,6 +106,8 @@ struct QbEmit {
     int dense;                      // 1 = dense mode
     uint32_t id_base;               // added to reported ids (row offset of this shard inside the sharded segment set)
     uint32_t local_k;               // per-CTA top-k mode of the dense streaming kernel: entries kept per warp / written per CTA
+    // per-CTA top-k mode: the LAST CTA to finish merges the per-CTA lists and writes the query's final top-k here (no select launch)
+    qb_scored_point* final_out; uint32_t* final_count; unsigned int* done_counter;
 };
 
 #ifdef __CUDACC__

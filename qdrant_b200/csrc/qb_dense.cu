@@ -230,6 +230,53 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(con
                         __syncwarp();
                     }
                 if (lane < QB_LOCALK_SLOTS) emit.cand[(unsigned long long)blockIdx.x * QB_LOCALK_SLOTS + lane] = (lane < (int)emit.local_k) ? lists[lane] : 0ull;
+                if (emit.done_counter) {
+                    // Last CTA standing merges the per-CTA lists: each is sorted descending, so the global top-k is a gridDim-way merge of
+                    // list heads — k rounds of (best head per lane, warp arg-max, the winner advances) instead of a separate select launch.
+                    __threadfence();
+                    __syncwarp();
+                    unsigned int ticket = 0;
+                    if (lane == 0) ticket = atomicAdd(emit.done_counter, 1u);
+                    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+                    if (ticket == gridDim.x - 1) {
+                        __threadfence();
+                        const unsigned long long* all = emit.cand;
+                        constexpr int PER = 8;                           // lists per lane: up to 256 CTAs
+                        unsigned int pos[PER];
+                        unsigned long long head[PER];
+#pragma unroll
+                        for (int i = 0; i < PER; ++i) {
+                            const unsigned int l = lane + 32u * i;
+                            pos[i] = 0;
+                            head[i] = (l < gridDim.x) ? __ldcg(all + (unsigned long long)l * QB_LOCALK_SLOTS) : 0ull;
+                        }
+                        unsigned int n_out = 0;
+                        for (unsigned int r = 0; r < emit.local_k; ++r) {
+                            unsigned long long best = 0ull;
+                            int bi = 0;
+#pragma unroll
+                            for (int i = 0; i < PER; ++i) if (head[i] > best) { best = head[i]; bi = i; }
+                            unsigned long long wbest = best;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xFFFFFFFFu, wbest, o); wbest = w > wbest ? w : wbest; }
+                            if (wbest == 0ull) break;                    // fewer than k candidates in the whole scan
+                            if (best == wbest) {                         // keys are unique: exactly one lane owns the winner
+#pragma unroll
+                                for (int i = 0; i < PER; ++i)
+                                    if (i == bi) {
+                                        pos[i] += 1;
+                                        const unsigned int l = lane + 32u * i;
+                                        head[i] = (pos[i] < (unsigned int)QB_LOCALK_SLOTS) ? __ldcg(all + (unsigned long long)l * QB_LOCALK_SLOTS + pos[i]) : 0ull;
+                                    }
+                                qb_scored_point sp;
+                                sp.idx = qb_key_id(wbest); sp.score = qb_key_score(wbest);
+                                emit.final_out[r] = sp;
+                            }
+                            n_out = r + 1;
+                        }
+                        if (lane == 0) { *emit.final_count = n_out; *emit.done_counter = 0u; }
+                    }
+                }
             }
         }
     }

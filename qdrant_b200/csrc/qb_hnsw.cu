@@ -472,8 +472,8 @@ qb_status qb_hnsw_launch(qb_hnsw* g, const void* d_q_enc, const float* d_q_off, 
     // threads per CTA: 256 = one 8-lane group per level-0 link (m0 = 32), fewer queries in flight per SM; 128 (default) = two scoring rounds
     // per hop, twice the resident queries.  The traversal is a chain of dependent memory round trips, so queries in flight is what hides
     // them: measured 519 K vs 276-423 K q/s (500K x 768, ef 128, 8192-query batch, through the host API).
-    const int nt = qb_opt().hnsw_threads == 256 ? 256 : 128;
-    const int per_sm = nt == 128 ? occupancy_dispatch<128>(kind, metric, smem) : occupancy_dispatch<256>(kind, metric, smem);
+    const int nt = qb_opt().hnsw_threads == 256 ? 256 : (qb_opt().hnsw_threads == 64 ? 64 : 128);
+    const int per_sm = nt == 128 ? occupancy_dispatch<128>(kind, metric, smem) : (nt == 64 ? occupancy_dispatch<64>(kind, metric, smem) : occupancy_dispatch<256>(kind, metric, smem));
     p.prefetch = qb_opt().hnsw_no_prefetch ? 0 : 1;
     const unsigned max_grid = (unsigned)s->sm_count * (unsigned)per_sm;
     const unsigned grid = std::min<unsigned>(max_grid, nq);
@@ -489,7 +489,8 @@ qb_status qb_hnsw_launch(qb_hnsw* g, const void* d_q_enc, const float* d_q_off, 
     }
     p.visited = g->d_visited; p.visited_words = words; p.vlog = g->d_vlog; p.vlog_cap = g->vlog_cap; p.work = g->d_work;
     QB_CUDA(cudaMemsetAsync(g->d_work, 0, 4, stream));
-    return nt == 128 ? launch_dispatch<128>(kind, metric, p, grid, smem, stream) : launch_dispatch<256>(kind, metric, p, grid, smem, stream);
+    return nt == 128 ? launch_dispatch<128>(kind, metric, p, grid, smem, stream)
+                     : (nt == 64 ? launch_dispatch<64>(kind, metric, p, grid, smem, stream) : launch_dispatch<256>(kind, metric, p, grid, smem, stream));
 }
 
 qb_status qb_hnsw_read_stats(qb_hnsw* g, cudaStream_t stream) {

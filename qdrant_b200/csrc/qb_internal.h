@@ -29,6 +29,7 @@ struct QbSearchCtx {
     // profiling
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool in_use = false;
+    unsigned int* d_done = nullptr;      // arrival counter of the single-query in-kernel top-k (zeroed once, the kernel resets it)
 };
 
 struct qb_storage {

@@ -27,10 +27,10 @@ blob = g.export_plain()
 st = qb.DenseVectorStorage(base, qb.Distance.Cosine)
 hg = qb.HnswGraph(st, blob, m, m0)
 variants = {}
-for nt in (256, 128):
+for nt in (256, 128, 64):
     for nopf in (0, 1):
         qb.set_option("hnsw_threads", nt); qb.set_option("hnsw_no_prefetch", nopf)
-        hg.search(queries[:256], 10, ef, entry, lvl)
+        hg.search(queries, 10, ef, entry, lvl)      # same batch once untimed: scratch (visited bitmaps) is sized on first use
         t0 = time.perf_counter(); hg.search(queries, 10, ef, entry, lvl); dt = time.perf_counter() - t0
         variants[f"threads{nt}_{'noprefetch' if nopf else 'prefetch'}"] = nq / dt
 qb.set_option("hnsw_threads", 0); qb.set_option("hnsw_no_prefetch", 0)
