@@ -7,6 +7,8 @@
 //     FilteredScorer          lib/segment/src/index/hnsw_index/point_scorer.rs:53-58,160-304
 //     BatchFilteredSearcher   point_scorer.rs:312-472
 //     ScoredPointOffset       lib/common/common/src/types.rs:12-31
+//     GraphLayers::search     lib/segment/src/index/hnsw_index/graph_layers.rs:530-561   (HnswGraph: whole batches on the device)
+//     SegmentsSearcher task + BatchResultAggregator   segments_searcher.rs:255, search_result_aggregator.rs:50-117   (SegmentShard)
 // Same names, argument meaning and error behaviour: construction may fail (OperationError -> std::runtime_error),
 // scoring is infallible apart from device failures (which throw, the analogue of the reference's `expect`).
 #pragma once
@@ -191,6 +193,59 @@ private:
     const VectorStorage& st_;
     uint32_t top_;
     const uint64_t* deleted_;
+};
+
+// GraphLayers::search (index/hnsw_index/graph_layers.rs:530-561) for a batch of queries, traversal and scoring on the device.
+// The graph is the segment's links.bin in GraphLinksFormat::Plain (graph_links/view.rs:121-135).
+class HnswGraph {
+public:
+    HnswGraph(const VectorStorage& storage, const uint8_t* links_bin, uint64_t n_bytes, uint32_t m, uint32_t m0) {
+        check(qb_hnsw_create_plain(storage.raw(), links_bin, n_bytes, m, m0, &h_));
+    }
+    ~HnswGraph() { qb_hnsw_destroy(h_); }
+    HnswGraph(const HnswGraph&) = delete;
+    // entry_point / entry_level = GraphLayers::get_entry_point(filters, custom_entry_points); deleted = the filter as a bitmap (bit = 1: skip)
+    std::vector<std::vector<ScoredPointOffset>> search(const float* queries, uint32_t n_queries, uint32_t top, uint32_t ef, PointOffsetType entry_point,
+                                                       uint32_t entry_level, const uint64_t* deleted = nullptr) const {
+        std::vector<ScoredPointOffset> flat((size_t)n_queries * top);
+        std::vector<uint32_t> counts(n_queries);
+        check(qb_hnsw_search_batch(h_, queries, n_queries, top, ef, entry_point, entry_level, deleted, nullptr, flat.data(), counts.data(), nullptr));
+        std::vector<std::vector<ScoredPointOffset>> out(n_queries);
+        for (uint32_t q = 0; q < n_queries; ++q) out[q].assign(flat.begin() + (size_t)q * top, flat.begin() + (size_t)q * top + counts[q]);
+        return out;
+    }
+
+private:
+    qb_hnsw* h_ = nullptr;
+};
+
+// One shard (segment on one GPU) of a sharded search: SegmentsSearcher's blocking task per segment (segments_searcher.rs:255) calls
+// search() with the same queries on every shard; the BatchResultAggregator step (search_result_aggregator.rs:50-117) happens on the
+// devices and every call returns the merged top-k.  Wire the shards of one process with ShardedSegments::connect.
+class SegmentShard {
+public:
+    SegmentShard(const VectorStorage& storage, int device, int rank, int world, uint32_t max_queries, uint32_t max_top) : st_(storage) {
+        check(qb_comm_create(device, rank, world, max_queries, max_top, &c_));
+    }
+    ~SegmentShard() { qb_comm_destroy(c_); }
+    SegmentShard(const SegmentShard&) = delete;
+    static void connect(const std::vector<SegmentShard*>& shards) {
+        std::vector<qb_comm*> cs;
+        for (auto* s : shards) cs.push_back(s->c_);
+        check(qb_comm_connect_local(cs.data(), (int32_t)cs.size()));
+    }
+    std::vector<std::vector<ScoredPointOffset>> search(const float* queries, uint32_t n_queries, uint32_t top) const {
+        std::vector<ScoredPointOffset> flat((size_t)n_queries * top);
+        std::vector<uint32_t> counts(n_queries);
+        check(qb_multi_search_batch(c_, st_.raw(), queries, n_queries, top, nullptr, nullptr, flat.data(), counts.data(), nullptr));
+        std::vector<std::vector<ScoredPointOffset>> out(n_queries);
+        for (uint32_t q = 0; q < n_queries; ++q) out[q].assign(flat.begin() + (size_t)q * top, flat.begin() + (size_t)q * top + counts[q]);
+        return out;
+    }
+
+private:
+    const VectorStorage& st_;
+    qb_comm* c_ = nullptr;
 };
 
 }  // namespace qdrant_b200
