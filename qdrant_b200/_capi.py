@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqdrant_b200.so")
+LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(_HERE, "lib", "libqdrant_b200.so")   # QB_LIB_PATH: experiment builds (build.py --variant)
 
 QB_OK, QB_ERR_INVALID, QB_ERR_CUDA, QB_ERR_UNSUPPORTED, QB_ERR_OOM, QB_ERR_CANCELLED, QB_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6
 

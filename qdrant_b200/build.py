@@ -42,6 +42,32 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experiment builds: libqdrant_b200_<name>.so with extra -D flags (build-time knobs), selected at run time with QB_LIB_PATH.
+    Not part of the product build."""
+    out = os.path.join(OUT_DIR, f"libqdrant_b200_{name}.so")
+    vdir = os.path.join(OUT_DIR, "variant_" + name)
+    os.makedirs(vdir, exist_ok=True)
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(vdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [NVCC] + [f for f in FLAGS if f not in ("-shared",)] + defines + ["-c", src, "-o", obj]
+        cmd = [c for i, c in enumerate(cmd) if c != "-cudart" and (i == 0 or cmd[i - 1] != "-cudart")]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(o)
+            raise RuntimeError("nvcc failed")
+    r = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", out] + objs + ["-lpthread", "-ldl", "-lrt"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
@@ -85,5 +111,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(path)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -450,6 +450,8 @@ extern "C" qb_status qb_storage_set_deleted(qb_storage* s, const uint64_t* bitma
     const uint64_t need = ceil_div_u64(s->count, 64);
     QB_CHECK(n_words >= need, QB_ERR_INVALID, "set_deleted: bitmap has %llu words, need %llu", (unsigned long long)n_words, (unsigned long long)need);
     if (!s->d_deleted) QB_CUDA(cudaMalloc(&s->d_deleted, std::max<uint64_t>(need, 1) * 8));
+    // searches in flight on this storage's (non-blocking) streams may be reading the flags: a rare control call, so simply wait for them
+    QB_CUDA(cudaDeviceSynchronize());
     QB_CUDA(cudaMemcpy(s->d_deleted, bitmap_words, need * 8, cudaMemcpyHostToDevice));
     return QB_OK;
 }

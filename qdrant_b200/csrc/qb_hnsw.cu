@@ -35,6 +35,9 @@ using namespace qbs;
 
 namespace {
 
+#ifndef QB_HNSW_LINK_PREFETCH
+#define QB_HNSW_LINK_PREFETCH 1      // build-time experiment knob
+#endif
 constexpr uint32_t HNSW_MAX_LINKS = 64;      // links scored per hop (m0 <= 64)
 constexpr uint32_t HNSW_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t HNSW_MAX_EF = 4096;
@@ -284,7 +287,11 @@ __global__ void __launch_bounds__(NT) hnsw_search_kernel(const HnswParams p) {
                     uint32_t lo = 0, hi = len;   // first index with keys[idx] < k (keys are distinct and descending)
                     while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] > k) lo = mid + 1; else hi = mid; }
                     r += lo;
-                    if (r < ef) { nk[r] = k; nf[r] = 0; }
+                    if (r < ef) {
+                        nk[r] = k; nf[r] = 0;
+                        // every point that enters `nearest` is a future candidate: pull its level-0 link row (one 128-byte line at m0 = 32) into L2 now
+                        if (QB_HNSW_LINK_PREFETCH && p.prefetch) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.links0 + (size_t)qb_key_id(k) * p.m0));
+                    }
                 }
             }
             __syncthreads();

@@ -56,9 +56,15 @@ constexpr int A_STAGE_BYTES = MMA_M * KB;    // 16 KB
 constexpr int STAGES_1 = 4;                  // cta_group::1 ring
 constexpr int STAGES_2 = 7;                  // cta_group::2 ring
 constexpr int N_MAX = 256;
-constexpr int EPI_WARPS = 16;                // 4 per TMEM lane quarter
+#ifndef QB_EPI_WARPS
+#define QB_EPI_WARPS 16
+#endif
+#ifndef QB_MMA_PF
+#define QB_MMA_PF 3
+#endif
+constexpr int EPI_WARPS = QB_EPI_WARPS;      // a multiple of 4: EPI_WARPS / 4 per TMEM lane quarter (build-time experiment knob)
 constexpr int EPI_PARTS = EPI_WARPS / 4;     // 16-column chunks are dealt round-robin to the warps of a quarter
-constexpr uint32_t MAX_CHUNKS_PER_WARP = N_MAX / 16 / EPI_PARTS;
+constexpr uint32_t MAX_CHUNKS_PER_WARP = (N_MAX / 16 + EPI_PARTS - 1) / EPI_PARTS;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr int WARP_TMA = EPI_WARPS;
 constexpr int WARP_MMA = EPI_WARPS + 1;
@@ -406,7 +412,7 @@ sq8_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint64_t pol_keep = qb_policy_evict_last();
         const uint64_t pol_stream = qb_policy_evict_first();
         uint64_t it = 0;
-        constexpr uint64_t PF = 3;  // L2 prefetch distance in tiles: hides the HBM latency that the smem ring cannot
+        constexpr uint64_t PF = QB_MMA_PF;  // L2 prefetch distance in tiles: hides the HBM latency that the smem ring cannot
         for (uint64_t ti = 0; ti < my_tiles; ++ti) {
             const int32_t row0 = (int32_t)((worker + ti * p.n_workers) * TILE_M + row_in_tile0);
             if (!(p.debug & 16) && elect_one()) {  // the n_qblocks groups of a worker walk the same tiles: each prefetches its share of the K-blocks
