@@ -407,6 +407,10 @@ def main_ours(args):
         line["fallback_reruns"] = reruns
         if cpu is not None:
             line["cpu_baseline"] = cpu
+    # ---- the same storage, 1024 f32 queries at once (north_star: "batched multi-query x segment scoring on tensor cores"): bf16 tcgen05
+    # prefilter + exact rescoring.  Reported as configs.f32_batch of the default line.
+    if rank == 0 and world == 1 and getattr(args, "with_f32_batch", False):
+        line["_f32_batch"] = f32_batch_on(st, args, dev)
     # orderly teardown: torch tensors / streams first, then the storage (the process group outlives this config)
     searcher.close()
     del searcher, d_all_q
@@ -414,6 +418,70 @@ def main_ours(args):
     st.close()
     torch.cuda.empty_cache()
     return line if rank == 0 else None
+
+
+def f32_batch_on(st, args, dev):
+    """1024-query f32 batches over the C2 storage: device-timed steps, host-API steps, tensor-core == CUDA-core lists, no fallback rerun."""
+    import torch
+
+    from qdrant_b200 import scorer as qb
+    from qdrant_b200._capi import check, lib, vp
+
+    nq, top = args.batch, TOP
+    queries = np.random.default_rng(46).standard_normal((nq, args.dim)).astype(np.float32)
+    d_q = torch.from_numpy(queries).to(dev)
+    d_out = torch.empty((nq, top), dtype=torch.int64, device=dev); d_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.ExternalStream(st.stream_ptr(), device=dev)
+
+    def step():
+        check(lib().qb_search_batch_device(st._h, vp(d_q.data_ptr()), nq, top, vp(d_out.data_ptr()), vp(d_cnt.data_ptr())))
+
+    for _ in range(3):
+        step()                                   # the first one builds the bf16 shadow plane
+    torch.cuda.synchronize()
+    st.search_stats(reset=True); st.profile_read(reset=True); st.profile(True)
+    launches0 = int(lib().qb_kernel_launch_count())
+    K = 5
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = int(lib().qb_kernel_launch_count()) - launches0
+    n_prof, prof_ms = st.profile_read(reset=True)
+    st.profile(False)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        res = st.search_batch(queries, top)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+    searches, reruns = st.search_stats(reset=True)
+    assert reruns == 0, f"f32 batch: {reruns} fallback reruns"
+    qb.set_option("disable_mma", 1)
+    try:
+        res_cc = st.search_batch(queries[:32], top)
+    finally:
+        qb.set_option("disable_mma", 0)
+    for a_, b_ in zip(res[:32], res_cc):
+        assert np.array_equal(a_, b_), "f32 batch: tensor-core prefilter path and CUDA-core path disagree"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]); peak_src = "measured (MEASURED_PEAKS.json bf16_tflops)"
+    except Exception:
+        peak, peak_src = 2250.0, "fallback (nominal dense bf16)"
+    n = st.count
+    flops = 2.0 * nq * n * args.dim
+    kern_ms = prof_ms / max(n_prof, 1)
+    ach = flops / (kern_ms / 1e3) / 1e12 if n_prof else None
+    return {"metric": f"queries/sec, {n}x{args.dim} f32 cosine brute-force top-{top}, batch={nq}, bf16 tensor-core prefilter + exact rescoring", "value": nq * K / (dev_ms / 1e3),
+            "unit": "queries/s", "n_gpus": 1, "steps": K, "warmup": 3, "ms_per_step": dev_ms / K, "higher_is_better": True, "dtype": "f32 (bf16 prefilter, f32 exact rescoring)",
+            "data": "synthetic", "config": {"workload": f"{n}x{args.dim} f32 cosine, batch={nq}", "rows": n, "dim": args.dim, "batch": nq},
+            "e2e": {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4, "d2h_bytes_per_step": nq * top * 8 + nq * 4, "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "sq8_mma_kernel<1,1> (tcgen05.mma kind::f16 prefilter) + f32_rescore_kernel, main pass", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src, "avg_launch_ms": kern_ms, "launches_timed": n_prof,
+                         "algorithmic_flops_per_launch": flops},
+            "parity": {"checked": True, "tensor_core_equals_cuda_core": "bit-exact on 32 queries x all rows", "fallback_reruns": reruns}}
 
 
 # ------------------------------------------------------------------------------------------------ C3: batched SQ8 (1 GPU)
@@ -825,8 +893,12 @@ def main_all(args):
     import torch.distributed as dist
 
     world, rank, _, _ = dist_ctx()
+    if args.config == "all":
+        args.with_f32_batch = True
     line = main_ours(args) if args.config in ("all", "c2") else None
     extras = {}
+    if line is not None and "_f32_batch" in line:
+        extras["f32_batch"] = line.pop("_f32_batch")
     if args.config == "all":
         small = args.rows != N_ROWS     # debug sizes: shrink the other configs along
         sub = argparse.Namespace(**vars(args))

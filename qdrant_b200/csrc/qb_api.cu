@@ -65,6 +65,8 @@ QbOptions& qb_opt() {
         v.sample_rows = (uint64_t)num("QB_SAMPLE_ROWS", 0);
         v.verbose = getenv("QB_VERBOSE") != nullptr;
         v.pq_queries_per_pass = (int)num("QB_PQ_QUERIES", 0);
+        v.mma_seg_cap = (uint32_t)num("QB_MMA_SEG_CAP", 0);
+        v.hnsw_threads = (int)num("QB_HNSW_THREADS", 0);
         return v;
     }();
     return o;
@@ -83,6 +85,7 @@ extern "C" qb_status qb_set_option(const char* name, int64_t value) {
     else if (n == "verbose") o.verbose = value != 0;
     else if (n == "pq_queries_per_pass") o.pq_queries_per_pass = (int)value;
     else if (n == "hnsw_threads") o.hnsw_threads = (int)value;
+    else if (n == "mma_seg_cap") o.mma_seg_cap = (uint32_t)value;
     else if (n == "hnsw_no_prefetch") o.hnsw_no_prefetch = value != 0;
     else { qb_set_error("set_option: unknown option '%s'", name); return QB_ERR_INVALID; }
     return QB_OK;
