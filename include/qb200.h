@@ -321,10 +321,17 @@ QB_API void qb_comm_destroy(qb_comm* c);
 QB_API qb_status qb_multi_search_batch(qb_comm* c, qb_storage* shard, const float* queries, uint32_t n_queries, uint32_t top,
                                        const uint64_t* deleted_bitmap, const volatile int32_t* is_stopped, qb_scored_point* out,
                                        uint32_t* out_counts, qb_hw_counters* counters /* optional */);
-/* same with queries / outputs resident in HBM, enqueued on qb_storage_stream(shard) without host synchronisation on the exact
- * single-pass paths; dev_local / dev_local_counts (n_queries x top, n_queries) receive the shard's own lists */
+/* same with queries / outputs resident in HBM, no host synchronisation on the exact single-pass paths.
+ *   dev_local / dev_local_counts != NULL: they receive the shard's own lists (n_queries x top, n_queries); scan, exchange and merge are all
+ *     enqueued on qb_storage_stream(shard).
+ *   dev_local == NULL (both): PIPELINED — the scan runs on qb_storage_stream(shard), the exchange + merge on qb_comm_stream(c), and the next
+ *     call's scan does not wait for this call's merge (a window of two steps, ring of four exchange slots): consecutive independent query
+ *     batches overlap across GPUs instead of meeting at a barrier per batch.  dev_out / dev_counts of a call are complete once
+ *     qb_comm_stream(c) has drained; successive calls write them in order. */
 QB_API qb_status qb_multi_search_batch_device(qb_comm* c, qb_storage* shard, const float* dev_queries, uint32_t n_queries, uint32_t top,
                                               qb_scored_point* dev_local, uint32_t* dev_local_counts, qb_scored_point* dev_out, uint32_t* dev_counts);
+/* cudaStream_t the pipelined exchange + merge kernels run on */
+QB_API void* qb_comm_stream(qb_comm* c);
 
 /* ---------------------------------------------------------------- HNSW graph search on the device ---- */
 /* GraphLayers::search (lib/segment/src/index/hnsw_index/graph_layers.rs:530-561) for a BATCH of queries with the

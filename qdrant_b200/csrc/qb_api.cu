@@ -1742,12 +1742,17 @@ extern "C" qb_status qb_multi_search_batch(qb_comm* cm, qb_storage* s, const flo
 // lists (n_queries x top) and must stay valid until the stream has run the exchange.
 extern "C" qb_status qb_multi_search_batch_device(qb_comm* cm, qb_storage* s, const float* dev_queries, uint32_t n_queries, uint32_t top, qb_scored_point* dev_local,
                                                   uint32_t* dev_local_counts, qb_scored_point* dev_out, uint32_t* dev_counts) {
-    QB_CHECK(cm && s && dev_queries && dev_local && dev_local_counts && dev_out && dev_counts, QB_ERR_INVALID, "multi_search_batch_device: null argument");
+    QB_CHECK(cm && s && dev_queries && dev_out && dev_counts && (!dev_local == !dev_local_counts), QB_ERR_INVALID, "multi_search_batch_device: null argument");
     QB_CHECK(cm->device == s->device, QB_ERR_INVALID, "multi_search_batch_device: communicator and shard on different devices");
     if (n_queries == 0) return QB_OK;
-    QB_TRY(qb_search_batch_device(s, dev_queries, n_queries, top, dev_local, dev_local_counts));
     QbSearchCtx* c = nullptr;
     QB_TRY(qb_ctx_device(s, &c));
     std::lock_guard<std::mutex> clk(cm->mu);
+    if (!dev_local) {
+        // pipelined: this step's exchange + merge runs on the communicator's stream while the next step's scan already streams rows
+        return qb_comm_pipelined_step(cm, c->stream, n_queries, top, dev_out, dev_counts,
+                                      [&](qb_scored_point* d_loc, uint32_t* d_loc_cnt) { return qb_search_batch_device(s, dev_queries, n_queries, top, d_loc, d_loc_cnt); });
+    }
+    QB_TRY(qb_search_batch_device(s, dev_queries, n_queries, top, dev_local, dev_local_counts));
     return qb_comm_exchange_merge(cm, dev_local, dev_local_counts, n_queries, top, dev_out, dev_counts, c->stream);
 }

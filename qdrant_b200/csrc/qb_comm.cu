@@ -12,11 +12,19 @@
 //        stores through NVLink / NVSwitch), __threadfence_system(), then raises flag [parity][my rank][query] = seq on the peer;
 //     2. spins (bounded) until its OWN buffer shows flag == seq from every rank for that query, merges the `world` sorted lists
 //        (<= world x top keys: one bitonic sort in shared memory, keys = (score desc, id asc) as everywhere) and writes the result.
-//   No NCCL call, no host round trip, no extra launch: the transfer overlaps the other queries' merges, and a step is
-//   preprocess + scan + select + this kernel.  `parity` double-buffers consecutive steps: a rank can run at most one step ahead of
-//   a peer (its next exchange needs the peer's flags of that step), so two slots suffice; `seq` increases by one per call and all
-//   ranks must call in the same order (it is a collective, like the aggregator it replaces sees every segment's list).
+//   No NCCL call, no host round trip: the transfer overlaps the other queries' merges, and a step is preprocess + scan + this kernel.
+//   `seq` increases by one per call and all ranks must call in the same order (it is a collective, like the aggregator it replaces
+//   sees every segment's list).
+//
+// Waiting for the slowest of N GPUs once per query is what limits strong scaling of a 0.6 ms scan (max-of-8 of the scan times, not
+// their mean, sets the step).  The device-resident entry point therefore PIPELINES independent steps: the exchange + merge kernel of step
+// i runs on the communicator's own high-priority stream (it needs one small CTA and co-resides with the scan), while the scan of step
+// i + 1 starts at once on the storage's stream.  Flow control: a rank starts scan(i) only after its own merge(i - 2) has completed
+// (window W = 2) and lists travel through a ring of R = 4 slots; when X pushes step i, every peer Y has completed merge(i - 2W) — X's
+// merge(i - W) saw Y's push(i - W), Y's scan(i - W) started after Y's merge(i - 2W) — so the slot X overwrites (step i - R, R = 2W) has
+// been consumed.  Results of step i are complete when the communicator's stream has run its merge (qb_comm_stream).
 #include <algorithm>
+#include <functional>
 
 #include "qb_internal.h"
 
@@ -26,14 +34,14 @@ constexpr int XCHG_THREADS = 256;
 constexpr uint32_t XCHG_MAX_KEYS = 4096;   // world * top keys merged per query in shared memory
 
 struct XchgBuf {            // layout of one rank's exchange buffer (all offsets in bytes from the base)
-    uint64_t flags_off;     // u32 [2][world][max_q]
-    uint64_t counts_off;    // u32 [2][world][max_q]
-    uint64_t lists_off;     // qb_scored_point [2][world][max_q][max_top]
+    uint64_t flags_off;     // u32 [QB_XCHG_SLOTS][world][max_q]
+    uint64_t counts_off;    // u32 [QB_XCHG_SLOTS][world][max_q]
+    uint64_t lists_off;     // qb_scored_point [QB_XCHG_SLOTS][world][max_q][max_top]
     uint64_t total;
 };
 __host__ __device__ inline XchgBuf xchg_layout(uint32_t world, uint32_t max_q, uint32_t max_top) {
     XchgBuf b;
-    const uint64_t nf = 2ull * world * max_q;
+    const uint64_t nf = (uint64_t)QB_XCHG_SLOTS * world * max_q;
     b.flags_off = 0;
     b.counts_off = (nf * 4 + 255) & ~255ull;
     b.lists_off = (b.counts_off + nf * 4 + 255) & ~255ull;
@@ -60,7 +68,7 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm vo
 // The grid is capped at what is co-resident (the launcher sizes it), and every CTA pushes ALL its queries before it waits for any:
 // a wait only depends on peers' pushes, pushes depend on nothing, so no schedule of CTAs on either side can deadlock.
 __global__ void __launch_bounds__(XCHG_THREADS) xchg_merge_kernel(const XchgParams p) {
-    __shared__ unsigned long long keys[XCHG_MAX_KEYS];
+    extern __shared__ unsigned long long keys[];     // pow2 >= world * top keys: small, so the CTA co-resides with a running scan
     __shared__ unsigned int s_timeout, s_valid;
     const XchgBuf L = xchg_layout(p.world, p.max_q, p.max_top);
     // ---- 1. push my lists to every rank (own buffer included: one code path)
@@ -173,6 +181,17 @@ extern "C" qb_status qb_comm_create(int32_t device, int32_t rank, int32_t world,
     }
     cudaMemset(c->d_buf, 0, L.total);
     cudaMemset(c->d_error, 0, 256);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        bool ok = cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi) == cudaSuccess;
+        for (uint32_t i = 0; i < QB_XCHG_SLOTS && ok; ++i) {
+            ok = cudaEventCreateWithFlags(&c->ev_scan[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&c->ev_merge[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaMalloc(&c->d_ring[i], (size_t)max_queries * max_top * sizeof(qb_scored_point) + 256) == cudaSuccess &&
+                 cudaMalloc(&c->d_ring_cnt[i], (size_t)max_queries * 4 + 256) == cudaSuccess;
+        }
+        if (!ok) { qb_set_error("comm_create: stream / event / ring allocation failed: %s", cudaGetErrorString(cudaGetLastError())); qb_comm_destroy(c); return QB_ERR_CUDA; }
+    }
     cudaDeviceSynchronize();
     c->peers[rank] = reinterpret_cast<uint8_t*>(c->d_buf);
     c->connected = (world == 1);
@@ -234,6 +253,12 @@ extern "C" void qb_comm_destroy(qb_comm* c) {
     cudaDeviceSynchronize();
     for (int r = 0; r < c->world; ++r) if (c->ipc_opened[r] && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
     cudaFree(c->d_buf); cudaFree(c->d_error); cudaFree(c->d_local); cudaFree(c->d_local_cnt);
+    for (uint32_t i = 0; i < QB_XCHG_SLOTS; ++i) {
+        cudaFree(c->d_ring[i]); cudaFree(c->d_ring_cnt[i]);
+        if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
+        if (c->ev_merge[i]) cudaEventDestroy(c->ev_merge[i]);
+    }
+    if (c->xstream) cudaStreamDestroy(c->xstream);
     cudaGetLastError();
     delete c;
 }
@@ -249,11 +274,30 @@ qb_status qb_comm_exchange_merge(qb_comm* c, const qb_scored_point* d_local, con
     p.world = (uint32_t)c->world; p.rank = (uint32_t)c->rank; p.max_q = c->max_q; p.max_top = c->max_top;
     p.nq = nq; p.top = top;
     c->seq += 1;
-    p.seq = c->seq; p.parity = c->seq & 1u;
+    p.seq = c->seq; p.parity = c->seq % QB_XCHG_SLOTS;
     p.local = d_local; p.local_cnt = d_local_cnt; p.out = d_out; p.out_cnt = d_out_cnt; p.error = c->d_error;
-    const unsigned grid = std::min<unsigned>(nq, (unsigned)c->sm_count);   // one CTA per SM at most: all co-resident (32 KB static smem, 256 threads)
-    xchg_merge_kernel<<<grid, XCHG_THREADS, 0, stream>>>(p);
+    const unsigned grid = std::min<unsigned>(nq, (unsigned)c->sm_count);   // one CTA per SM at most: all co-resident
+    uint32_t p2 = 32;
+    while (p2 < (uint32_t)c->world * top) p2 <<= 1;
+    xchg_merge_kernel<<<grid, XCHG_THREADS, (size_t)p2 * 8, stream>>>(p);
     QB_LAUNCHED();
     QB_CUDA(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" void* qb_comm_stream(qb_comm* c) { return c ? c->xstream : nullptr; }
+
+// Pipelined collective for device-resident queries / results (see the header comment): scan on `scan_stream`, exchange + merge on the
+// communicator's stream.  `launch_scan(d_local, d_local_cnt)` enqueues this shard's fused scan into the given list buffers.
+qb_status qb_comm_pipelined_step(qb_comm* c, cudaStream_t scan_stream, uint32_t nq, uint32_t top, qb_scored_point* d_out, uint32_t* d_out_cnt,
+                                 const std::function<qb_status(qb_scored_point*, uint32_t*)>& launch_scan) {
+    QB_CHECK(nq <= c->max_q && top <= c->max_top, QB_ERR_INVALID, "multi_search: %u queries x top %u exceed the communicator's %u x %u", nq, top, c->max_q, c->max_top);
+    const uint32_t slot = (c->seq + 1) % QB_XCHG_SLOTS;
+    if (c->seq >= 2) QB_CUDA(cudaStreamWaitEvent(scan_stream, c->ev_merge[(c->seq + 1 - 2) % QB_XCHG_SLOTS], 0));   // window: scan(i) after own merge(i - 2)
+    QB_TRY(launch_scan(c->d_ring[slot], c->d_ring_cnt[slot]));
+    QB_CUDA(cudaEventRecord(c->ev_scan[slot], scan_stream));
+    QB_CUDA(cudaStreamWaitEvent(c->xstream, c->ev_scan[slot], 0));
+    QB_TRY(qb_comm_exchange_merge(c, c->d_ring[slot], c->d_ring_cnt[slot], nq, top, d_out, d_out_cnt, c->xstream));   // seq += 1 inside
+    QB_CUDA(cudaEventRecord(c->ev_merge[slot], c->xstream));
     return QB_OK;
 }

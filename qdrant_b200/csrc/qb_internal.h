@@ -1,5 +1,7 @@
 // qb_internal.h — host-side objects behind the opaque C-ABI handles.
 #pragma once
+#include <functional>
+
 #include "qb_common.cuh"
 
 enum QbKind { QB_KIND_DENSE = 0, QB_KIND_SQ8 = 1, QB_KIND_PQ = 2, QB_KIND_BQ = 3 };
@@ -139,6 +141,7 @@ qb_status qb_hnsw_read_stats(qb_hnsw* g, cudaStream_t stream);
 
 // One rank of a sharded search (qb_comm.cu): an exchange buffer every peer maps + the peers' buffers
 constexpr uint32_t QB_MAX_WORLD = 16;
+constexpr uint32_t QB_XCHG_SLOTS = 4;     // ring of exchange slots (window of 2 pipelined steps, see qb_comm.cu)
 struct qb_comm {
     int device = 0, rank = 0, world = 1, sm_count = 148;
     uint32_t max_q = 0, max_top = 0;
@@ -149,8 +152,14 @@ struct qb_comm {
     uint32_t seq = 0;
     unsigned int* d_error = nullptr;
     qb_scored_point* d_local = nullptr; uint32_t* d_local_cnt = nullptr; size_t local_cap = 0;   // this shard's lists (host-facing entry)
+    // pipelined device-resident steps: exchange + merge on its own high-priority stream, this shard's lists in a ring
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_scan[QB_XCHG_SLOTS] = {}, ev_merge[QB_XCHG_SLOTS] = {};
+    qb_scored_point* d_ring[QB_XCHG_SLOTS] = {}; uint32_t* d_ring_cnt[QB_XCHG_SLOTS] = {};
     std::mutex mu;
 };
+qb_status qb_comm_pipelined_step(qb_comm* c, cudaStream_t scan_stream, uint32_t nq, uint32_t top, qb_scored_point* d_out, uint32_t* d_out_cnt,
+                                 const std::function<qb_status(qb_scored_point*, uint32_t*)>& launch_scan);
 qb_status qb_comm_exchange_merge(qb_comm* c, const qb_scored_point* d_local, const uint32_t* d_local_cnt, uint32_t nq, uint32_t top, qb_scored_point* d_out,
                                  uint32_t* d_out_cnt, cudaStream_t stream);
 

@@ -79,6 +79,8 @@ class ShardedSegmentSearcher:
                     print(f"[qdrant_b200] peer-memory exchange unavailable ({why or 'a peer rank failed'}): using the NCCL all-gather exchange", file=sys.stderr)
             dist.barrier()
         self.stream = torch.cuda.ExternalStream(storage.stream_ptr(), device=device)
+        # the pipelined exchange + merge kernels run on the communicator's own stream (qb_comm_stream)
+        self.xstream = torch.cuda.ExternalStream(lib().qb_comm_stream(self.comm), device=device) if self.comm else None
         nq, k, w = self.max_queries, self.top, self.world
         # ScoredPointOffset = 8 bytes -> int64 tensors as opaque 8-byte records
         self.d_queries = torch.empty((nq, storage.dim), dtype=torch.float32, device=device)
@@ -96,9 +98,11 @@ class ShardedSegmentSearcher:
     # ---- device-resident step: queries already in self.d_queries[:nq]; results land in self.d_out / d_out_cnt
     def search_device(self, nq: int) -> None:
         if self.exchange == "peer":
-            # local fused scan + select, then ONE kernel: push this shard's lists into every peer's buffer, wait for theirs, merge
-            check(lib().qb_multi_search_batch_device(self.comm, self.storage._h, vp(self.d_queries.data_ptr()), nq, self.top, vp(self.d_local.data_ptr()),
-                                                     vp(self.d_local_cnt.data_ptr()), vp(self.d_out.data_ptr()), vp(self.d_out_cnt.data_ptr())))
+            # local fused scan + select, then ONE kernel: push this shard's lists into every peer's buffer, wait for theirs, merge.
+            # Pipelined (dev_local = NULL): the exchange + merge runs on self.xstream while the next call's scan already streams rows;
+            # drain() orders self.stream after the merges.
+            check(lib().qb_multi_search_batch_device(self.comm, self.storage._h, vp(self.d_queries.data_ptr()), nq, self.top, None, None,
+                                                     vp(self.d_out.data_ptr()), vp(self.d_out_cnt.data_ptr())))
             return
         with torch.cuda.stream(self.stream):
             check(lib().qb_search_batch_device(self.storage._h, vp(self.d_queries.data_ptr()), nq, self.top,
@@ -155,8 +159,14 @@ class ShardedSegmentSearcher:
         except Exception:
             pass
 
+    def drain(self) -> None:
+        """Order self.stream after every exchange + merge enqueued so far (no host synchronisation)."""
+        if self.xstream is not None:
+            self.stream.wait_stream(self.xstream)
+
     def results_host(self, nq: int):
         """Copy the device results of the last search_device() to the host (synchronises)."""
+        self.drain()
         with torch.cuda.stream(self.stream):
             self.h_out.copy_(self.d_out, non_blocking=True)
             self.h_out_cnt.copy_(self.d_out_cnt, non_blocking=True)

@@ -68,3 +68,67 @@ def test_sharded_equals_single_through_the_c_abi(qb, oracle, world, nq, top, n, 
         lib().qb_comm_destroy(comms[r])
         shards[r].close()
     single.close()
+
+
+@pytest.mark.parametrize("world,nq,top,n,dim", [(2, 1, 10, 150_003, 64), (4, 3, 10, 120_000, 96), (8, 1, 10, 160_000, 128)])
+def test_pipelined_device_steps_equal_single(qb, oracle, world, nq, top, n, dim):
+    """qb_multi_search_batch_device with dev_local = NULL: the exchange + merge of step i runs on the communicator's stream while the
+    scan of step i + 1 is already enqueued (window of two steps, ring of four slots).  Fourteen back-to-back steps without any host
+    synchronisation, every step's merged lists kept in its own buffer, all compared with the unsharded storage."""
+    import torch
+
+    from qdrant_b200._capi import check, lib, vp
+    from qdrant_b200.sharded import shard_ranges
+
+    steps = 14
+    n_dev = torch.cuda.device_count()
+    rng = np.random.default_rng(100 + world)
+    base = oracle.preprocess_rows_f32(oracle.COSINE, rng.standard_normal((n, dim)).astype(np.float32))
+    queries = rng.standard_normal((steps, nq, dim)).astype(np.float32)
+    single = qb.DenseVectorStorage(base, qb.Distance.Cosine)
+    shards, comms = [], (vp * world)()
+    for r, (b, e) in enumerate(shard_ranges(n, world)):
+        st = qb.DenseVectorStorage(base[b:e], qb.Distance.Cosine, device=r % n_dev)
+        check(lib().qb_storage_set_id_base(st._h, b))
+        shards.append(st)
+        h = vp()
+        check(lib().qb_comm_create(r % n_dev, r, world, 64, 16, C.byref(h)))
+        comms[r] = h
+    check(lib().qb_comm_connect_local(comms, world))
+    results = [None] * world
+    errors = []
+
+    def task(r):
+        try:
+            dev = torch.device("cuda", r % n_dev)
+            torch.cuda.set_device(dev)
+            d_q = torch.from_numpy(queries).to(dev)
+            d_out = torch.zeros((steps, nq, top), dtype=torch.int64, device=dev)
+            d_cnt = torch.zeros((steps, nq), dtype=torch.int32, device=dev)
+            torch.cuda.synchronize(dev)
+            for it in range(steps):
+                check(lib().qb_multi_search_batch_device(comms[r], shards[r]._h, vp(d_q[it].data_ptr()), nq, top, None, None,
+                                                         vp(d_out[it].data_ptr()), vp(d_cnt[it].data_ptr())))
+            xs = torch.cuda.ExternalStream(lib().qb_comm_stream(comms[r]), device=dev)
+            xs.synchronize()
+            rec = d_out.cpu().numpy().view(qb.SCORED_POINT_OFFSET).reshape(steps, nq, top)
+            cnt = d_cnt.cpu().numpy()
+            results[r] = [[rec[it, i, : cnt[it, i]].copy() for i in range(nq)] for it in range(steps)]
+        except Exception as ex:   # noqa: BLE001
+            errors.append((r, ex))
+
+    th = [threading.Thread(target=task, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errors, errors
+    for it in range(steps):
+        want = single.search_batch(queries[it], top)
+        for r in range(world):
+            for i in range(nq):
+                np.testing.assert_array_equal(results[r][it][i], want[i], err_msg=f"world {world} rank {r} step {it} query {i}")
+    for r in range(world):
+        lib().qb_comm_destroy(comms[r])
+        shards[r].close()
+    single.close()
