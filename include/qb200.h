@@ -332,6 +332,9 @@ QB_API qb_status qb_multi_search_batch_device(qb_comm* c, qb_storage* shard, con
                                               qb_scored_point* dev_local, uint32_t* dev_local_counts, qb_scored_point* dev_out, uint32_t* dev_counts);
 /* cudaStream_t the pipelined exchange + merge kernels run on */
 QB_API void* qb_comm_stream(qb_comm* c);
+/* synchronise qb_comm_stream(c) and report a failed exchange of the device-resident calls made so far (a peer that never made the matching
+ * call: the waiting rank gives up after ~10 s, leaves that step's results empty and this returns QB_ERR_CUDA) */
+QB_API qb_status qb_comm_check(qb_comm* c);
 
 /* ---------------------------------------------------------------- HNSW graph search on the device ---- */
 /* GraphLayers::search (lib/segment/src/index/hnsw_index/graph_layers.rs:530-561) for a BATCH of queries with the

@@ -87,6 +87,7 @@ SIGNATURES = {
     "qb_comm_connect_local": (C.c_int32, [C.POINTER(vp), C.c_int32]),
     "qb_comm_destroy": (None, [vp]),
     "qb_comm_stream": (vp, [vp]),
+    "qb_comm_check": (C.c_int32, [vp]),
     "qb_multi_search_batch": (C.c_int32, [vp, vp, f32p, C.c_uint32, C.c_uint32, u64p, i32p, C.POINTER(ScoredPoint), u32p, C.POINTER(HwCounters)]),
     "qb_multi_search_batch_device": (C.c_int32, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "qb_hnsw_create_plain": (C.c_int32, [vp, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(vp)]),

@@ -654,7 +654,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
     const SearchPlan plan = make_plan(n_cand, nq, top, force_direct, mma_ok && (f32_mma || qb_sq8_mma_block(s, nq) != 0) && !(rs_flags & RS_NO_REFINE));
     if (can_flag && plan.direct) *can_flag = false;  // full materialisation: no threshold, no counters, nothing to overflow
     QB_TRY(ensure_dev_elems(&c->d_cand, &c->cand_elems, (size_t)plan.q_chunk * plan.cap));
-    QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)nq));
+    QB_TRY(ensure_dev_elems(&c->d_thr, &c->thr_elems, (size_t)2 * nq));   // [nq] thresholds + [nq] scratch (adjusted thresholds of the PQ prefilter)
     QB_TRY(ensure_dev_elems(&c->d_cnt, &c->cnt_elems, (size_t)nq + 1));
     const size_t enc_bytes = qb_encoded_query_bytes(s);
 
@@ -671,6 +671,7 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         a.emit.id_base = s->id_base;
         a.emit.cand = c->d_cand;
         a.emit.cap = plan.cap;
+        a.d_thr_scratch = c->d_thr + nq + q0;
         cudaEvent_t e0, e1;
         if (plan.direct) {
             a.row_begin = 0; a.row_end = n_cand;

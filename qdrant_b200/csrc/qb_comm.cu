@@ -287,6 +287,24 @@ qb_status qb_comm_exchange_merge(qb_comm* c, const qb_scored_point* d_local, con
 
 extern "C" void* qb_comm_stream(qb_comm* c) { return c ? c->xstream : nullptr; }
 
+// Drain the communicator's stream and report what the asynchronous (device-resident) steps could not: an exchange that gave up
+// waiting for a peer (a rank that never made the matching call) leaves its results empty and sets the error word.
+extern "C" qb_status qb_comm_check(qb_comm* c) {
+    QB_CHECK(c, QB_ERR_INVALID, "comm_check: null communicator");
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != c->device) QB_CUDA(cudaSetDevice(c->device));
+    QB_CUDA(cudaStreamSynchronize(c->xstream));
+    unsigned int err = 0;
+    QB_CUDA(cudaMemcpy(&err, c->d_error, 4, cudaMemcpyDeviceToHost));
+    if (err) {
+        cudaMemset(c->d_error, 0, 4);
+        qb_set_error("sharded search: rank %d timed out waiting for a peer's lists (flags 0x%x); every rank must make the same sequence of calls", c->rank, err);
+        return QB_ERR_CUDA;
+    }
+    return QB_OK;
+}
+
 // Pipelined collective for device-resident queries / results (see the header comment): scan on `scan_stream`, exchange + merge on the
 // communicator's stream.  `launch_scan(d_local, d_local_cnt)` enqueues this shard's fused scan into the given list buffers.
 qb_status qb_comm_pipelined_step(qb_comm* c, cudaStream_t scan_stream, uint32_t nq, uint32_t top, qb_scored_point* d_out, uint32_t* d_out_cnt,

@@ -47,7 +47,7 @@ struct QbOptions {
     int pq_queries_per_pass = 0;   // 0 = automatic
     int hnsw_threads = 0;          // 0 / 128 (default) or 256 threads per traversal CTA
     bool hnsw_no_prefetch = false;
-    uint32_t mma_seg_cap = 0;      // 0 = 512 survivor slots per (query, CTA) segment of the tensor-core scan
+    uint32_t mma_seg_cap = 0;      // 0 = 256 survivor slots per (query, CTA) segment of the tensor-core scan
     uint64_t sample_rows = 0;
 };
 QbOptions& qb_opt();

@@ -187,6 +187,7 @@ struct QbScanArgs {
     uint64_t row_begin, row_end;
     const uint32_t* d_ids;  // optional gather list; then row_begin/row_end index into it
     QbEmit emit;
+    float* d_thr_scratch;   // optional: nq floats a scan may use for adjusted thresholds (PQ prefilter); null = exact kernels only
 };
 qb_status qb_launch_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 

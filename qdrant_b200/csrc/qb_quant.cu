@@ -392,6 +392,169 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ4_THREADS, 1) pq_s
     cluster.sync();   // a CTA's shared memory (slot, barriers) must outlive its peer's last remote access
 }
 
+// ---------------------------------------------------------------- eight queries per pass: bf16 LUT prefilter + exact rescoring
+// The four-query kernel above sits on the shared-memory pipe (random 16-byte gathers, ~10 wavefronts per LDS.128): the only way to more
+// lookups per second is more QUERIES per wavefront.  Eight bf16 table entries fit the same 16 bytes, so one gather serves eight queries —
+// but a bf16 table cannot give the reference's f32 sums.  It does not have to: the scan only has to find every row whose EXACT score
+// reaches the query's threshold.  With  S_q = sum_j max_c |lut_q[j][c]|  the prefilter's score differs from the exact f32 sum by at most
+//   2^-9 S_q (round-to-nearest bf16 of every entry) + 2 * m * 2^-24 S_q (both f32 accumulations, any order)  <  (2^-9 + 2^-15) S_q =: margin_q
+// so the kernel emits every row with  approx >= thr_q - margin_q  (a superset of the rows the exact filter would pass), a second kernel
+// re-scores exactly those survivors with the f32 tables in score_point_sse's order (four lanes, (s0+s2)+(s1+s3)) and rewrites their keys,
+// and the selection runs on exact keys: results are bit-identical to the single-query kernel's.  Non-finite table entries make the
+// margin inf / NaN: every row passes, the candidate buffer overflows and the host's rerun takes the exact path.
+// Layout as above (CTA pair, chunks split, per-warp DSMEM hand-off), except that the approximate sum has no order to keep: one f32 per
+// query crosses the pair (32 bytes per thread instead of 256).
+constexpr int PQ8_THREADS = 512;
+constexpr int PQ8_WARPS = PQ8_THREADS / 32;
+
+__global__ void __launch_bounds__(256) pq8_margin_kernel(const float* __restrict__ luts, uint32_t m, uint32_t K, const float* __restrict__ thr,
+                                                         float* __restrict__ thr_adj) {
+    __shared__ float s_part[8];
+    const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* lut = luts + (size_t)q * m * K;
+    float sum = 0.f;
+    for (uint32_t j = warp; j < m; j += 8) {
+        float mx = 0.f;
+        bool bad = false;
+        for (uint32_t c = lane; c < K; c += 32) { const float v = fabsf(lut[(size_t)j * K + c]); bad |= !(v <= 3.0e38f); mx = fmaxf(mx, v); }
+        for (int o = 16; o; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); bad |= __shfl_xor_sync(0xffffffffu, (int)bad, o) != 0; }
+        sum = __fadd_ru(sum, bad ? __int_as_float(0x7f800000) : mx);      // NaN / inf / beyond bf16's range: no finite margin exists
+    }
+    if (lane == 0) s_part[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float S = 0.f;
+        for (int w = 0; w < 8; ++w) S = __fadd_ru(S, s_part[w]);
+        const float margin = __fadd_ru(__fmul_ru(S, 0x1.04p-9f), 1.0e-37f);   // (2^-9 + 2^-15) S, rounded up, plus the denormal floor
+        thr_adj[q] = __fsub_rd(thr[q], margin);
+    }
+}
+
+__device__ __forceinline__ void pq8_st_async_f4(uint32_t cluster_addr, float4 v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "r"(cluster_bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pq8_pack_bf16(float lo, float hi) {   // round-to-nearest-even bf16 pair, lo in bits [0,16)
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void pq8_acc(float (&acc)[8], const uint4 v) {
+    acc[0] = __fadd_rn(acc[0], __uint_as_float(v.x << 16)); acc[1] = __fadd_rn(acc[1], __uint_as_float(v.x & 0xFFFF0000u));
+    acc[2] = __fadd_rn(acc[2], __uint_as_float(v.y << 16)); acc[3] = __fadd_rn(acc[3], __uint_as_float(v.y & 0xFFFF0000u));
+    acc[4] = __fadd_rn(acc[4], __uint_as_float(v.z << 16)); acc[5] = __fadd_rn(acc[5], __uint_as_float(v.z & 0xFFFF0000u));
+    acc[6] = __fadd_rn(acc[6], __uint_as_float(v.w << 16)); acc[7] = __fadd_rn(acc[7], __uint_as_float(v.w & 0xFFFF0000u));
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ8_THREADS, 1) pq_scan8_kernel(const PqParams p, const QbEmit emit /* thr = thr - margin */) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) float lut_s[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();
+    const uint32_t K = p.n_centroids, mh = p.m >> 1, j0 = rank * mh;
+    uint4* lut8 = reinterpret_cast<uint4*>(lut_s);                   // [mh][K] x 8 bf16 (queries q0 .. q0+7)
+    float4* hand = reinterpret_cast<float4*>(lut8 + (size_t)mh * K); // [2][PQ8_THREADS]   (CTA 1's copy is the one in use)
+    uint64_t* full = reinterpret_cast<uint64_t*>(hand + 2 * PQ8_THREADS);
+    uint64_t* empty = full + PQ8_WARPS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < PQ8_WARPS) { qb_mbar_init(&full[tid], 1); qb_mbar_init(&empty[tid], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cluster.sync();
+    const uint32_t hand_remote = pq4_map_to_cta(hand, 1);
+    const uint32_t full_remote = pq4_map_to_cta(&full[warp], 1);
+    const uint32_t empty_remote = pq4_map_to_cta(&empty[warp], 0);
+    const uint64_t n = p.end - p.begin;
+    const uint64_t n_tiles = (n + PQ8_THREADS - 1) / PQ8_THREADS;
+    const uint32_t cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const size_t lut_elems = (size_t)p.m * K;
+    uint32_t it = 0;
+    for (uint32_t q0 = 0; q0 < p.nq; q0 += 8) {
+        const float* l0 = p.luts + (size_t)q0 * lut_elems + (size_t)j0 * K;
+        size_t qo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qo[i] = (q0 + i < p.nq) ? (size_t)i * lut_elems : 0;   // missing queries of the last group: query q0 again (never emitted)
+        __syncthreads();
+        for (uint32_t i = tid; i < mh * K; i += PQ8_THREADS) {
+            uint4 v;
+            v.x = pq8_pack_bf16(l0[qo[0] + i], l0[qo[1] + i]); v.y = pq8_pack_bf16(l0[qo[2] + i], l0[qo[3] + i]);
+            v.z = pq8_pack_bf16(l0[qo[4] + i], l0[qo[5] + i]); v.w = pq8_pack_bf16(l0[qo[6] + i], l0[qo[7] + i]);
+            lut8[i] = v;
+        }
+        __syncthreads();
+        for (uint64_t t = cid; t < n_tiles; t += n_clusters, ++it) {
+            const uint64_t ci = t * PQ8_THREADS + tid;
+            const bool valid = ci < n;
+            const uint64_t cand = p.begin + (valid ? ci : 0);
+            const uint8_t* code = p.codes + (size_t)cand * p.stride + j0;
+            uint4 cw[3];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) cw[w] = (w * 16u < mh) ? *reinterpret_cast<const uint4*>(code + w * 16) : make_uint4(0, 0, 0, 0);
+            float a[8], b[8];                                        // two independent chains per query (the order is free here)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                if (w * 16u >= mh) break;
+                const uint32_t wd[4] = {cw[w].x, cw[w].y, cw[w].z, cw[w].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4* l = lut8 + (size_t)(w * 16 + 4 * k) * K;
+                    const uint4 v0 = l[wd[k] & 255u], v1 = l[K + ((wd[k] >> 8) & 255u)], v2 = l[2 * K + ((wd[k] >> 16) & 255u)], v3 = l[3 * K + (wd[k] >> 24)];
+                    pq8_acc(a, v0); pq8_acc(b, v1); pq8_acc(a, v2); pq8_acc(b, v3);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = __fadd_rn(a[i], b[i]);
+            if (rank == 0) {
+                if (it > 0) pq4_wait_cluster(&empty[warp], (it - 1) & 1u);
+                pq8_st_async_f4(hand_remote + (0 * PQ8_THREADS + tid) * 16u, make_float4(a[0], a[1], a[2], a[3]), full_remote);
+                pq8_st_async_f4(hand_remote + (1 * PQ8_THREADS + tid) * 16u, make_float4(a[4], a[5], a[6], a[7]), full_remote);
+            } else {
+                if (lane == 0) qb_mbar_arrive_expect_tx(&full[warp], 32u * 32u);
+                pq4_wait_cluster(&full[warp], it & 1u);
+                const float4 h0 = hand[0 * PQ8_THREADS + tid], h1 = hand[1 * PQ8_THREADS + tid];
+                __syncwarp();
+                if (lane == 0) pq4_remote_arrive(empty_remote);
+                if (valid) {
+                    const uint32_t row = (uint32_t)cand;
+                    const float r[8] = {__fadd_rn(a[0], h0.x), __fadd_rn(a[1], h0.y), __fadd_rn(a[2], h0.z), __fadd_rn(a[3], h0.w),
+                                        __fadd_rn(a[4], h1.x), __fadd_rn(a[5], h1.y), __fadd_rn(a[6], h1.z), __fadd_rn(a[7], h1.w)};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (q0 + i < p.nq) qb_emit(emit, q0 + i, cand, row, r[i]);
+                }
+            }
+        }
+    }
+    cluster.sync();
+}
+
+// exact f32 score of every survivor of the prefilter, in score_point_sse's order; the candidate's key is rewritten in place
+__global__ void __launch_bounds__(128) pq_rescore_kernel(const PqParams p, const QbEmit emit) {
+    const uint32_t q = blockIdx.y;
+    const unsigned long long cnt = min((unsigned long long)emit.cnt[q], emit.cap);
+    const uint32_t K = p.n_centroids, m4 = p.m & ~3u;
+    const float* lut = p.luts + (size_t)q * p.m * K;
+    for (unsigned long long pos = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; pos < cnt; pos += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long* slot = emit.cand + (unsigned long long)q * emit.cap + pos;
+        const uint32_t id = qb_key_id(*slot);
+        const uint8_t* code = p.codes + (size_t)(id - emit.id_base) * p.stride;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        uint32_t j = 0;
+        for (; j < m4; j += 4) {
+            const float* l = lut + (size_t)j * K;
+            s0 = __fadd_rn(s0, l[code[j]]);
+            s1 = __fadd_rn(s1, l[K + code[j + 1]]);
+            s2 = __fadd_rn(s2, l[2 * K + code[j + 2]]);
+            s3 = __fadd_rn(s3, l[3 * K + code[j + 3]]);
+        }
+        float sum = __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
+        for (; j < p.m; ++j) sum = __fadd_rn(sum, lut[(size_t)j * K + code[j]]);
+        *slot = qb_pack_key(sum, id);
+    }
+}
+
 // score_internal (encoded_vectors_pq.rs:574-618): decode both codes through the centroids; single pair
 __global__ void pq_score_internal_kernel(const uint8_t* __restrict__ codes, uint32_t stride, uint32_t m, const uint32_t* __restrict__ div,
                                          const float* __restrict__ centroids, uint32_t dim, int qdist, int invert, uint32_t a, uint32_t b,
@@ -643,13 +806,34 @@ qb_status qb_pq_build_luts(const qb_storage* s, const float* d_q_pre, uint32_t q
     return QB_OK;
 }
 
-static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cudaStream_t stream) {
+static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cudaStream_t stream, float* d_thr_adj = nullptr) {
     const uint64_t n = p.end - p.begin;
     if (n == 0 || p.nq == 0) return QB_OK;
     p.codes = s->d_pq_codes; p.stride = s->pq_stride; p.m = s->pq_m; p.n_centroids = s->n_centroids;
     const size_t lut_bytes = (size_t)s->pq_m * s->n_centroids * sizeof(float);
     const int qpp = qb_opt().pq_queries_per_pass;   // 0 = automatic; 1 / 2 / 4 force a kernel (experiments)
     const size_t smem4 = 2 * lut_bytes + (size_t)4 * PQ4_THREADS * 16 + (size_t)2 * PQ4_WARPS * 8;   // interleaved LUT half (4 queries x m/2 chunks) + hand-off slot + barriers
+    const size_t smem8 = 2 * lut_bytes + (size_t)2 * PQ8_THREADS * 16 + (size_t)2 * PQ8_WARPS * 8;   // 8 bf16 tables x m/2 chunks = the same bytes
+    if (p.emit_mode && !e.dense && d_thr_adj && !p.ids && (qpp == 0 || qpp == 8) && p.nq >= 5 && s->pq_m % 32 == 0 && smem8 <= 227 * 1024 && n >= 65536 && s->sm_count >= 2) {
+        // batched filter passes: eight queries per gather through bf16 tables; survivors re-scored exactly (see pq_scan8_kernel)
+        QB_CUDA(cudaFuncSetAttribute(pq_scan8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        pq8_margin_kernel<<<p.nq, 256, 0, stream>>>(p.luts, p.m, p.n_centroids, e.thr, d_thr_adj);
+        QB_LAUNCHED();
+        QbEmit e8 = e;
+        e8.thr = d_thr_adj;
+        const uint64_t block_rows = std::max<uint64_t>(65536, (48ull << 20) / s->pq_stride);
+        const unsigned grid = (unsigned)(s->sm_count & ~1);
+        for (uint64_t b0 = p.begin; b0 < p.end; b0 += block_rows) {
+            PqParams pb = p;
+            pb.begin = b0; pb.end = std::min<uint64_t>(p.end, b0 + block_rows);
+            pq_scan8_kernel<<<grid, PQ8_THREADS, smem8, stream>>>(pb, e8);
+            QB_LAUNCHED();
+        }
+        pq_rescore_kernel<<<dim3(8, p.nq), 128, 0, stream>>>(p, e);
+        QB_LAUNCHED();
+        QB_CUDA(cudaGetLastError());
+        return QB_OK;
+    }
     if (p.emit_mode && !p.ids && (qpp == 0 || qpp == 4) && p.nq >= 3 && s->pq_m % 32 == 0 && smem4 <= 227 * 1024 && n >= 65536 && s->sm_count >= 2) {
         // batched scans: four queries per pass on CTA pairs; row blocks sized to stay in L2 while every query quad visits them
         QB_CUDA(cudaFuncSetAttribute(pq_scan4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
@@ -691,7 +875,7 @@ qb_status qb_pq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stre
     p.begin = a.row_begin; p.end = a.row_end; p.ids = a.d_ids;
     p.luts = reinterpret_cast<const float*>(a.d_q_enc); p.nq = a.nq;
     p.scores = nullptr; p.emit_mode = 1;
-    return pq_launch(s, p, a.emit, stream);
+    return pq_launch(s, p, a.emit, stream, a.d_thr_scratch);
 }
 
 qb_status qb_pq_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream) {

@@ -831,7 +831,7 @@ qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_
     const uint32_t n_seg = two ? 2 * workers : workers;  // CTAs that ever see a given query
     if (!emit.dense && seg_len && !qb_opt().mma_no_segments) {
         uint64_t seg = (emit.cap / n_seg) & ~15ull;
-        const uint64_t seg_max = qb_opt().mma_seg_cap ? qb_opt().mma_seg_cap : 512;   // slots per (query, CTA): the selection scans all of them
+        const uint64_t seg_max = qb_opt().mma_seg_cap ? qb_opt().mma_seg_cap : 256;   // slots per (query, CTA): the selection scans all of them
         if (seg > seg_max) seg = seg_max;
         if (seg >= 64) {
             p.seg_cap = (uint32_t)seg;

@@ -167,6 +167,8 @@ class ShardedSegmentSearcher:
     def results_host(self, nq: int):
         """Copy the device results of the last search_device() to the host (synchronises)."""
         self.drain()
+        if self.comm:
+            check(lib().qb_comm_check(self.comm))      # a step whose exchange timed out must not read as an empty result
         with torch.cuda.stream(self.stream):
             self.h_out.copy_(self.d_out, non_blocking=True)
             self.h_out_cnt.copy_(self.d_out_cnt, non_blocking=True)

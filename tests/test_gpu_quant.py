@@ -162,7 +162,7 @@ def test_pq_batched_four_query_cluster_kernel(qb, oracle, dist, n, dim, chunk, n
     luts = np.stack([pq.encode_query(oracle.preprocess_f32(int(d), q)) for q in queries])
     deleted = rng.random(n) < 0.02
     want = pq.scan(luts, 10, deleted=pack_bitmap(deleted))
-    for qpp in (0, 4, 2, 1):
+    for qpp in (0, 8, 4, 2, 1):
         qb.set_option("pq_queries_per_pass", qpp)
         try:
             got = st.search_batch(queries, 10, point_deleted=deleted)
@@ -171,6 +171,52 @@ def test_pq_batched_four_query_cluster_kernel(qb, oracle, dist, n, dim, chunk, n
         for i in range(nq):
             assert_topk_equal(got[i], want[i], None, f"pq4 {dist} qpp={qpp} q={i}")
     assert st.search_stats()[1] == 0
+    st.close()
+
+
+@pytest.mark.parametrize("case", ["plain", "ties", "wide_range", "nan_centroid", "cancelling"])
+def test_pq_eight_query_prefilter_is_exact(qb, oracle, case):
+    """pq_scan8_kernel scores eight queries per gather through bf16 tables and keeps every row within (2^-9 + 2^-15) * sum_j max|lut_j| of
+    the threshold; pq_rescore_kernel re-scores the survivors in score_point_sse's order.  The result must be the single-query kernel's,
+    bit for bit: partial last group (19 queries), boundary ties, tables whose entries span 12 orders of magnitude, sums that cancel
+    (margin >> score spread: nearly everything survives -> overflow -> exact rerun), and a NaN centroid (no finite margin)."""
+    rng = np.random.default_rng(sum(map(ord, case)))
+    n, dim, chunk, nq, top = 150_000, 128, 4, 19, 10
+    d = qb.Distance.Dot
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    cents = (rng.standard_normal((256, dim)) * 0.3).astype(np.float32)
+    codes = rng.integers(0, 256, (n, dim // chunk), dtype=np.uint8)
+    if case == "ties":
+        codes = codes[rng.integers(0, 40, n)]                 # 40 distinct rows: every score value occurs thousands of times
+    elif case == "wide_range":
+        cents *= (10.0 ** rng.uniform(-6, 6, (1, dim))).astype(np.float32)
+    elif case == "nan_centroid":
+        cents[7, 5] = np.nan
+    elif case == "cancelling":
+        cents[:, :64] *= 1.0e4                                  # huge table entries ...
+        queries[:, 32:64] = -queries[:, :32]                    # ... that cancel pairwise in most rows' sums
+        cents[:, 32:64] = cents[:, :32]
+        codes[:, 8:16] = codes[:, :8]
+    pq = oracle.PQ(dim, chunk, cents, codes, oracle.QD_DOT, False)
+    st = qb.ProductQuantizedVectors(codes, cents, chunk, dim, d)
+    qb.set_option("pq_queries_per_pass", 1)
+    try:
+        want = st.search_batch(queries, top)
+    finally:
+        qb.set_option("pq_queries_per_pass", 0)
+    st.search_stats(reset=True)
+    got = st.search_batch(queries, top)
+    searches, reruns = st.search_stats(reset=True)
+    if case in ("plain", "wide_range"):
+        assert reruns == 0, "the prefilter's margin admitted too many rows on an ordinary table"
+    if case != "nan_centroid":                                  # the oracle's heap order among NaN scores is not the id order
+        luts = np.stack([pq.encode_query(q) for q in queries])
+        ref = pq.scan(luts, top)
+        for i in range(nq):
+            assert_topk_equal(got[i], ref[i], None, f"pq8 {case} vs oracle q={i}")
+    for i in range(nq):
+        np.testing.assert_array_equal(got[i]["idx"], want[i]["idx"], err_msg=f"pq8 {case} q={i}")
+        np.testing.assert_array_equal(got[i]["score"].view(np.uint32), want[i]["score"].view(np.uint32), err_msg=f"pq8 {case} q={i}")
     st.close()
 
 
