@@ -720,7 +720,7 @@ def main_c4(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     searches, reruns = st.search_stats(reset=True)
-    # the timed path (eight queries per gather through bf16 tables + exact rescoring) against the single-query f32 kernel, all rows
+    # the timed path (sixteen queries per gather through u8 tables + exact rescoring) against the single-query f32 kernel, all rows
     from qdrant_b200.scorer import set_option
     fast = st.search_batch(queries[:24], top)
     set_option("pq_queries_per_pass", 1)
@@ -764,9 +764,14 @@ def main_c4(args):
                            "l2": "code plane 600 MB per GPU > 126 MB L2"},
                 "e2e": {"value": nq * K / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top * 8 + nq * 4, "ms_per_step": e2e_ms / K},
                 "gpu_launches": launches, "clocks": clk,
-                "roofline": {"bound": "smem-gather", "kernel": "pq_scan8_kernel (eight queries per 16-byte gather through bf16 tables) + pq_rescore_kernel (exact f32 sums of the survivors)", "achieved": (lookups / (kern_ms / 1e3) / 1e9) if n_prof else None,
+                "roofline": {"bound": "smem-gather", "kernel": "pq16_prep_kernel + pq_scan16_kernel (sixteen queries per 16-byte gather through u8 tables, integer thresholds) + "
+                                                               "pq_rescore_kernel (exact f32 sums of the survivors)", "achieved": (lookups / (kern_ms / 1e3) / 1e9) if n_prof else None,
                              "peak": smem_peak_glookups, "unit": "Glookup/s", "frac": (lookups / (kern_ms / 1e3) / 1e9 / smem_peak_glookups) if n_prof else None, "traffic": None,
-                             "peak_source": "148 SMs x 32 banks x clocks.max.sm (conflict-free 4-B shared-memory gathers); no such figure in MEASURED_PEAKS.json",
+                             "peak_source": "148 SMs x 32 banks x clocks.max.sm = one 4-byte table entry per bank per clock (the exact kernels' conflict-free gather rate, the "
+                                            "denominator of rounds 1-2; no such figure in MEASURED_PEAKS.json).  A (row, query, chunk) lookup of the batched kernel moves ONE byte "
+                                            "(sixteen queries share a 16-byte gather), so frac > 1 is possible; see frac_of_16B_gather_peak and profiles/ncu_pq16_kernel_r02.txt "
+                                            "(shared-memory pipe 88 % busy, 9.6 wavefronts per LDS.128 on random codes where 4 is conflict-free)",
+                             "frac_of_16B_gather_peak": (lookups / (kern_ms / 1e3) / 1e9 / (148 * 8 * 16 * 1.965)) if n_prof else None,
                              "avg_launch_ms": kern_ms, "launches_timed": n_prof, "hbm_gb_per_s": (float(nq) * n_local * m / (kern_ms / 1e3) / 1e9) if n_prof else None}}
         line["parity"] = parity
         if cpu:

@@ -672,6 +672,10 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         a.emit.cand = c->d_cand;
         a.emit.cap = plan.cap;
         a.d_thr_scratch = c->d_thr + nq + q0;
+        if (s->kind == QB_KIND_PQ && !d_ids && !plan.direct) {
+            const size_t need = qb_pq_scratch_bytes(s, qn);
+            if (need) { QB_TRY(qb_ensure_device(&c->d_mma, &c->mma_bytes, need)); a.d_scratch = c->d_mma; a.scratch_bytes = c->mma_bytes; }
+        }
         cudaEvent_t e0, e1;
         if (plan.direct) {
             a.row_begin = 0; a.row_end = n_cand;

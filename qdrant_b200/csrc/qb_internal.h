@@ -188,7 +188,9 @@ struct QbScanArgs {
     const uint32_t* d_ids;  // optional gather list; then row_begin/row_end index into it
     QbEmit emit;
     float* d_thr_scratch;   // optional: nq floats a scan may use for adjusted thresholds (PQ prefilter); null = exact kernels only
+    void* d_scratch; size_t scratch_bytes;   // optional per-call scratch (PQ: interleaved u8 tables of the sixteen-query prefilter)
 };
+size_t qb_pq_scratch_bytes(const qb_storage* s, uint32_t nq);
 qb_status qb_launch_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 
 // score listed ids for ONE encoded query into d_scores (RawScorer::score_points)

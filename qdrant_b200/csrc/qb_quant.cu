@@ -530,6 +530,188 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ8_THREADS, 1) pq_s
     cluster.sync();
 }
 
+// ---------------------------------------------------------------- sixteen queries per pass: u8 tables, integer prefilter
+// One step further along the same line: SIXTEEN one-byte table entries per 16-byte gather.  Per query the tables are quantised with one
+// step for all chunks, u[j][c] = rint((lut[j][c] - min_j) / step), step = max_j(max_c lut[j][c] - min_j) / 255, so that
+//   | step * sum_j u[j][code_j] + sum_j min_j  -  sum_j lut[j][code_j] |  <=  m * step * (1/2 + 2^-14)          (real arithmetic)
+// and a row whose EXACT f32 score reaches thr_q has  sum_j u >= T_q := floor((thr_q - sum_j min_j - margin_q) / step) - 1  with
+// margin_q = m * step * (1/2 + 2^-14) + 4 m 2^-24 sum_j max_c |lut[j][c]|  (quantisation + every f32 rounding on either side, all
+// evaluated in double on the device).  The hot loop is integer only: per gather two PRMTs spread the sixteen bytes over eight registers
+// of two u16 lanes (sums <= 96 * 255 fit), the accumulators START at 0x8000 - T_q, so "passes" is bit 15 of a lane and the whole
+// 16-query test is an OR and an AND.  Survivors are appended without a score and re-scored exactly (pq_rescore_kernel) as above.
+// The interleaved u8 tables (nq x m x 256 bytes) and the biases are built once per scan by pq16_prep_kernel; a CTA copies its half
+// (192 KB, contiguous) per query group.  Codes of the next row tile are fetched while the current one is gathered.
+constexpr int PQ16_THREADS = 512;
+constexpr int PQ16_WARPS = PQ16_THREADS / 32;
+
+// one block per (padded) query: tables -> interleaved u8 planes tab16[group][j][c][16], bias[q] = 0x8000 - T_q (u16 in a u32)
+__global__ void __launch_bounds__(256) pq16_prep_kernel(const float* __restrict__ luts, uint32_t nq, uint32_t m, uint32_t K, const float* __restrict__ thr,
+                                                        uint8_t* __restrict__ tab16, uint32_t* __restrict__ bias) {
+    __shared__ float s_min[128], s_rng[8], s_abs[8];
+    __shared__ double s_base[8];
+    __shared__ int s_bad;
+    const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* dst = tab16 + ((size_t)(q >> 4) * m * K) * 16 + (q & 15);
+    if (q >= nq) {                                                   // padding of the last group: never passes
+        for (uint32_t i = threadIdx.x; i < m * K; i += blockDim.x) dst[(size_t)i * 16] = 0;
+        if (threadIdx.x == 0) bias[q] = 0u;
+        return;
+    }
+    const float* lut = luts + (size_t)q * m * K;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    float rng_w = 0.f, abs_w = 0.f;
+    double base_w = 0.0;
+    for (uint32_t j = warp; j < m; j += 8) {
+        float mn = __int_as_float(0x7f800000), mx = -mn, ab = 0.f;
+        bool bad = false;
+        for (uint32_t c = lane; c < K; c += 32) { const float v = lut[(size_t)j * K + c]; bad |= !(fabsf(v) <= 3.0e38f); mn = fminf(mn, v); mx = fmaxf(mx, v); ab = fmaxf(ab, fabsf(v)); }
+        for (int o = 16; o; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); ab = fmaxf(ab, __shfl_xor_sync(0xffffffffu, ab, o));
+            bad |= __shfl_xor_sync(0xffffffffu, (int)bad, o) != 0;
+        }
+        if (bad && lane == 0) s_bad = 1;
+        if (lane == 0 && j < 128) s_min[j] = mn;
+        rng_w = fmaxf(rng_w, mx - mn); abs_w += ab; base_w += (double)mn;
+    }
+    if (lane == 0) { s_rng[warp] = rng_w; s_abs[warp] = abs_w; s_base[warp] = base_w; }
+    __syncthreads();
+    float rng = 0.f;
+    double A = 0.0, base = 0.0;
+    for (int w = 0; w < 8; ++w) { rng = fmaxf(rng, s_rng[w]); A += (double)s_abs[w] * 1.0001; base += s_base[w]; }
+    const bool bad = s_bad != 0 || !(rng <= 3.0e38f) || !(A <= 3.0e38);      // a sum of m entries must stay finite, too
+    const float step = bad ? 1.f : fmaxf(rng / 255.f, 1.0e-30f);
+    const float inv = 1.f / step;
+    for (uint32_t i = threadIdx.x; i < m * K; i += blockDim.x) {
+        const float t = __fmul_rn(__fsub_rn(lut[i], s_min[i / K]), inv);
+        dst[(size_t)i * 16] = bad ? (uint8_t)0 : (uint8_t)fminf(fmaxf(rintf(t), 0.f), 255.f);
+    }
+    if (threadIdx.x == 0) {
+        uint32_t b;
+        const float th = thr[q];
+        if (bad || !(fabsf(th) <= 3.0e38f)) {
+            b = (th == __int_as_float(0x7f800000) && !bad) ? 0u : 0x8000u;    // +inf threshold: nothing finite reaches it; NaN / -inf / bad tables: everything passes
+        } else {
+            const double margin = (double)m * (double)step * (0.5 + 1.0 / 16384.0) + 4.0 * (double)m * 5.9604644775390625e-8 * A;
+            const double T = floor(((double)th - base - margin) / (double)step) - 1.0;
+            b = T <= 0.0 ? 0x8000u : (T >= 32768.0 ? 0u : 0x8000u - (uint32_t)T);
+        }
+        bias[q] = b;
+    }
+}
+
+__device__ __forceinline__ void pq16_st_async_u4(uint32_t cluster_addr, uint4 v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "r"(cluster_bar)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PQ16_THREADS, 1) pq_scan16_kernel(const PqParams p, const QbEmit emit, const uint8_t* __restrict__ tab16,
+                                                                                              const uint32_t* __restrict__ bias) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) float lut_s[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank();
+    const uint32_t K = p.n_centroids, mh = p.m >> 1, j0 = rank * mh;
+    uint4* lut16 = reinterpret_cast<uint4*>(lut_s);                    // [mh][K] x 16 u8 (queries q0 .. q0+15)
+    float4* hand = reinterpret_cast<float4*>(lut16 + (size_t)mh * K);  // [2][PQ16_THREADS]   (CTA 1's copy is the one in use)
+    uint64_t* full = reinterpret_cast<uint64_t*>(hand + 2 * PQ16_THREADS);
+    uint64_t* empty = full + PQ16_WARPS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < PQ16_WARPS) { qb_mbar_init(&full[tid], 1); qb_mbar_init(&empty[tid], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    cluster.sync();
+    const uint32_t hand_remote = pq4_map_to_cta(hand, 1);
+    const uint32_t full_remote = pq4_map_to_cta(&full[warp], 1);
+    const uint32_t empty_remote = pq4_map_to_cta(&empty[warp], 0);
+    const uint64_t n = p.end - p.begin;
+    const uint64_t n_tiles = (n + PQ16_THREADS - 1) / PQ16_THREADS;
+    const uint32_t cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    uint32_t it = 0;
+    for (uint32_t q0 = 0; q0 < p.nq; q0 += 16) {
+        const uint4* src = reinterpret_cast<const uint4*>(tab16) + ((size_t)(q0 >> 4) * p.m + j0) * K;
+        __syncthreads();
+        for (uint32_t i = tid; i < mh * K; i += PQ16_THREADS) lut16[i] = src[i];
+        uint32_t init[8];                                            // accumulator layout: word 2k = queries (4k, 4k+2), word 2k+1 = (4k+1, 4k+3)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            init[2 * k] = rank ? 0u : (bias[q0 + 4 * k] | (bias[q0 + 4 * k + 2] << 16));
+            init[2 * k + 1] = rank ? 0u : (bias[q0 + 4 * k + 1] | (bias[q0 + 4 * k + 3] << 16));
+        }
+        __syncthreads();
+        uint4 cw[3], cn[3];
+        {
+            const uint64_t ci = (uint64_t)cid * PQ16_THREADS + tid;
+            const uint8_t* code = p.codes + (size_t)(p.begin + (ci < n ? ci : 0)) * p.stride + j0;
+#pragma unroll
+            for (int w = 0; w < 3; ++w) cn[w] = (w * 16u < mh && cid < n_tiles) ? *reinterpret_cast<const uint4*>(code + w * 16) : make_uint4(0, 0, 0, 0);
+        }
+        for (uint64_t t = cid; t < n_tiles; t += n_clusters, ++it) {
+            const uint64_t ci = t * PQ16_THREADS + tid;
+            const bool valid = ci < n;
+            const uint64_t cand = p.begin + (valid ? ci : 0);
+#pragma unroll
+            for (int w = 0; w < 3; ++w) cw[w] = cn[w];
+            if (t + n_clusters < n_tiles) {                          // next tile's codes: in flight while this tile gathers
+                const uint64_t cj = (t + n_clusters) * PQ16_THREADS + tid;
+                const uint8_t* code = p.codes + (size_t)(p.begin + (cj < n ? cj : 0)) * p.stride + j0;
+#pragma unroll
+                for (int w = 0; w < 3; ++w) cn[w] = (w * 16u < mh) ? *reinterpret_cast<const uint4*>(code + w * 16) : make_uint4(0, 0, 0, 0);
+            }
+            uint32_t a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = init[i];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                if (w * 16u >= mh) break;
+                const uint32_t wd[4] = {cw[w].x, cw[w].y, cw[w].z, cw[w].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4* l = lut16 + (size_t)(w * 16 + 4 * k) * K;
+                    const uint4 v[4] = {l[wd[k] & 255u], l[K + ((wd[k] >> 8) & 255u)], l[2 * K + ((wd[k] >> 16) & 255u)], l[3 * K + (wd[k] >> 24)]};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        a[0] += __byte_perm(v[x].x, 0, 0x4240); a[1] += __byte_perm(v[x].x, 0, 0x4341);
+                        a[2] += __byte_perm(v[x].y, 0, 0x4240); a[3] += __byte_perm(v[x].y, 0, 0x4341);
+                        a[4] += __byte_perm(v[x].z, 0, 0x4240); a[5] += __byte_perm(v[x].z, 0, 0x4341);
+                        a[6] += __byte_perm(v[x].w, 0, 0x4240); a[7] += __byte_perm(v[x].w, 0, 0x4341);
+                    }
+                }
+            }
+            if (rank == 0) {
+                if (it > 0) pq4_wait_cluster(&empty[warp], (it - 1) & 1u);
+                pq16_st_async_u4(hand_remote + (0 * PQ16_THREADS + tid) * 16u, make_uint4(a[0], a[1], a[2], a[3]), full_remote);
+                pq16_st_async_u4(hand_remote + (1 * PQ16_THREADS + tid) * 16u, make_uint4(a[4], a[5], a[6], a[7]), full_remote);
+            } else {
+                if (lane == 0) qb_mbar_arrive_expect_tx(&full[warp], 32u * 32u);
+                pq4_wait_cluster(&full[warp], it & 1u);
+                const uint4 h0 = reinterpret_cast<const uint4*>(hand)[0 * PQ16_THREADS + tid], h1 = reinterpret_cast<const uint4*>(hand)[1 * PQ16_THREADS + tid];
+                __syncwarp();
+                if (lane == 0) pq4_remote_arrive(empty_remote);
+                a[0] += h0.x; a[1] += h0.y; a[2] += h0.z; a[3] += h0.w; a[4] += h1.x; a[5] += h1.y; a[6] += h1.z; a[7] += h1.w;
+                const uint32_t any = (a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) & 0x80008000u;
+                if (any && valid) {
+                    const uint32_t row = (uint32_t)cand;
+                    if (!qb_is_deleted(emit, row)) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t q = q0 + 4 * (i >> 1) + (i & 1) + 2 * h;
+                                if ((a[i] >> (15 + 16 * h)) & 1u) {
+                                    const unsigned int pos = atomicAdd(&emit.cnt[q], 1u);
+                                    if (pos < emit.cap) emit.cand[(unsigned long long)q * emit.cap + pos] = qb_pack_key(0.f, row + emit.id_base);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cluster.sync();
+}
+
 // exact f32 score of every survivor of the prefilter, in score_point_sse's order; the candidate's key is rewritten in place
 __global__ void __launch_bounds__(128) pq_rescore_kernel(const PqParams p, const QbEmit emit) {
     const uint32_t q = blockIdx.y;
@@ -806,13 +988,38 @@ qb_status qb_pq_build_luts(const qb_storage* s, const float* d_q_pre, uint32_t q
     return QB_OK;
 }
 
-static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cudaStream_t stream, float* d_thr_adj = nullptr) {
+static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cudaStream_t stream, float* d_thr_adj = nullptr, void* scratch = nullptr,
+                           size_t scratch_bytes = 0) {
     const uint64_t n = p.end - p.begin;
     if (n == 0 || p.nq == 0) return QB_OK;
     p.codes = s->d_pq_codes; p.stride = s->pq_stride; p.m = s->pq_m; p.n_centroids = s->n_centroids;
     const size_t lut_bytes = (size_t)s->pq_m * s->n_centroids * sizeof(float);
     const int qpp = qb_opt().pq_queries_per_pass;   // 0 = automatic; 1 / 2 / 4 force a kernel (experiments)
     const size_t smem4 = 2 * lut_bytes + (size_t)4 * PQ4_THREADS * 16 + (size_t)2 * PQ4_WARPS * 8;   // interleaved LUT half (4 queries x m/2 chunks) + hand-off slot + barriers
+    const uint32_t nq16 = (p.nq + 15u) & ~15u;
+    const size_t tab_bytes = (size_t)nq16 * s->pq_m * s->n_centroids;
+    const size_t smem16 = 2 * lut_bytes + (size_t)2 * PQ16_THREADS * 16 + (size_t)2 * PQ16_WARPS * 8;   // 16 u8 tables x m/2 chunks = the same bytes again
+    if (p.emit_mode && !e.dense && scratch && scratch_bytes >= tab_bytes + (size_t)nq16 * 4 + 256 && !p.ids && (qpp == 0 || qpp == 16) && p.nq >= 9 && s->pq_m % 32 == 0 &&
+        s->pq_m <= 128 && s->n_centroids == 256 && smem16 <= 227 * 1024 && n >= 65536 && s->sm_count >= 2) {
+        // batched filter passes: sixteen queries per gather through u8 tables, integer thresholds; survivors re-scored exactly (pq_scan16_kernel)
+        QB_CUDA(cudaFuncSetAttribute(pq_scan16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+        uint8_t* tab16 = reinterpret_cast<uint8_t*>(scratch);
+        uint32_t* bias = reinterpret_cast<uint32_t*>(tab16 + ((tab_bytes + 255) & ~(size_t)255));
+        pq16_prep_kernel<<<nq16, 256, 0, stream>>>(p.luts, p.nq, p.m, p.n_centroids, e.thr, tab16, bias);
+        QB_LAUNCHED();
+        const uint64_t block_rows = std::max<uint64_t>(65536, (48ull << 20) / s->pq_stride);
+        const unsigned grid = (unsigned)(s->sm_count & ~1);
+        for (uint64_t b0 = p.begin; b0 < p.end; b0 += block_rows) {
+            PqParams pb = p;
+            pb.begin = b0; pb.end = std::min<uint64_t>(p.end, b0 + block_rows);
+            pq_scan16_kernel<<<grid, PQ16_THREADS, smem16, stream>>>(pb, e, tab16, bias);
+            QB_LAUNCHED();
+        }
+        pq_rescore_kernel<<<dim3(8, p.nq), 128, 0, stream>>>(p, e);
+        QB_LAUNCHED();
+        QB_CUDA(cudaGetLastError());
+        return QB_OK;
+    }
     const size_t smem8 = 2 * lut_bytes + (size_t)2 * PQ8_THREADS * 16 + (size_t)2 * PQ8_WARPS * 8;   // 8 bf16 tables x m/2 chunks = the same bytes
     if (p.emit_mode && !e.dense && d_thr_adj && !p.ids && (qpp == 0 || qpp == 8) && p.nq >= 5 && s->pq_m % 32 == 0 && smem8 <= 227 * 1024 && n >= 65536 && s->sm_count >= 2) {
         // batched filter passes: eight queries per gather through bf16 tables; survivors re-scored exactly (see pq_scan8_kernel)
@@ -870,12 +1077,19 @@ static qb_status pq_launch(const qb_storage* s, PqParams& p, const QbEmit& e, cu
     return QB_OK;
 }
 
+// bytes of per-call scratch the sixteen-query prefilter wants for a batch of nq queries (interleaved u8 tables + biases)
+size_t qb_pq_scratch_bytes(const qb_storage* s, uint32_t nq) {
+    if (s->kind != QB_KIND_PQ || nq < 9) return 0;
+    const size_t nq16 = ((size_t)nq + 15) & ~(size_t)15;
+    return nq16 * s->pq_m * s->n_centroids + nq16 * 4 + 512;
+}
+
 qb_status qb_pq_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream) {
     PqParams p{};
     p.begin = a.row_begin; p.end = a.row_end; p.ids = a.d_ids;
     p.luts = reinterpret_cast<const float*>(a.d_q_enc); p.nq = a.nq;
     p.scores = nullptr; p.emit_mode = 1;
-    return pq_launch(s, p, a.emit, stream, a.d_thr_scratch);
+    return pq_launch(s, p, a.emit, stream, a.d_thr_scratch, a.d_scratch, a.scratch_bytes);
 }
 
 qb_status qb_pq_score_points(const qb_storage* s, const void* d_q_enc, const uint32_t* d_ids, uint64_t n, float* d_scores, cudaStream_t stream) {

@@ -144,7 +144,8 @@ def test_pq_search_batch(qb, oracle):
     st.close()
 
 
-@pytest.mark.parametrize("dist,n,dim,chunk,nq", [("Dot", 70_000, 128, 4, 5), ("Euclid", 66_000, 128, 2, 8), ("Cosine", 70_001, 1536, 16, 7), ("Manhattan", 131_000, 64, 2, 3)])
+@pytest.mark.parametrize("dist,n,dim,chunk,nq", [("Dot", 70_000, 128, 4, 5), ("Euclid", 66_000, 128, 2, 8), ("Cosine", 70_001, 1536, 16, 7), ("Manhattan", 131_000, 64, 2, 3),
+                                                 ("Euclid", 140_000, 256, 2, 20), ("Cosine", 70_001, 1536, 16, 33)])
 def test_pq_batched_four_query_cluster_kernel(qb, oracle, dist, n, dim, chunk, nq):
     """pq_scan4_kernel (m % 32 == 0: CTA pair, float4-interleaved LUT halves, partial sums handed over through distributed shared
     memory) == oracle score_point_sse order, bit-exact, for every queries-per-pass variant, with deletions and several row blocks."""
@@ -162,7 +163,7 @@ def test_pq_batched_four_query_cluster_kernel(qb, oracle, dist, n, dim, chunk, n
     luts = np.stack([pq.encode_query(oracle.preprocess_f32(int(d), q)) for q in queries])
     deleted = rng.random(n) < 0.02
     want = pq.scan(luts, 10, deleted=pack_bitmap(deleted))
-    for qpp in (0, 8, 4, 2, 1):
+    for qpp in (0, 16, 8, 4, 2, 1):
         qb.set_option("pq_queries_per_pass", qpp)
         try:
             got = st.search_batch(queries, 10, point_deleted=deleted)
@@ -174,10 +175,12 @@ def test_pq_batched_four_query_cluster_kernel(qb, oracle, dist, n, dim, chunk, n
     st.close()
 
 
-@pytest.mark.parametrize("case", ["plain", "ties", "wide_range", "nan_centroid", "cancelling"])
-def test_pq_eight_query_prefilter_is_exact(qb, oracle, case):
+@pytest.mark.parametrize("qpp", [16, 8])
+@pytest.mark.parametrize("case", ["plain", "ties", "wide_range", "nan_centroid", "cancelling", "flat_tables"])
+def test_pq_prefilter_kernels_are_exact(qb, oracle, case, qpp):
     """pq_scan8_kernel scores eight queries per gather through bf16 tables and keeps every row within (2^-9 + 2^-15) * sum_j max|lut_j| of
-    the threshold; pq_rescore_kernel re-scores the survivors in score_point_sse's order.  The result must be the single-query kernel's,
+    the threshold; pq_scan16_kernel sixteen per gather through u8 tables with an integer threshold (quantisation step * m / 2 + roundings);
+    pq_rescore_kernel re-scores the survivors in score_point_sse's order.  The result must be the single-query kernel's,
     bit for bit: partial last group (19 queries), boundary ties, tables whose entries span 12 orders of magnitude, sums that cancel
     (margin >> score spread: nearly everything survives -> overflow -> exact rerun), and a NaN centroid (no finite margin)."""
     rng = np.random.default_rng(sum(map(ord, case)))
@@ -192,6 +195,8 @@ def test_pq_eight_query_prefilter_is_exact(qb, oracle, case):
         cents *= (10.0 ** rng.uniform(-6, 6, (1, dim))).astype(np.float32)
     elif case == "nan_centroid":
         cents[7, 5] = np.nan
+    elif case == "flat_tables":
+        cents[:] = cents[0]                                     # every centroid the same: all rows score alike, quantisation step 0
     elif case == "cancelling":
         cents[:, :64] *= 1.0e4                                  # huge table entries ...
         queries[:, 32:64] = -queries[:, :32]                    # ... that cancel pairwise in most rows' sums
@@ -205,7 +210,11 @@ def test_pq_eight_query_prefilter_is_exact(qb, oracle, case):
     finally:
         qb.set_option("pq_queries_per_pass", 0)
     st.search_stats(reset=True)
-    got = st.search_batch(queries, top)
+    qb.set_option("pq_queries_per_pass", qpp)
+    try:
+        got = st.search_batch(queries, top)
+    finally:
+        qb.set_option("pq_queries_per_pass", 0)
     searches, reruns = st.search_stats(reset=True)
     if case in ("plain", "wide_range"):
         assert reruns == 0, "the prefilter's margin admitted too many rows on an ordinary table"
@@ -213,10 +222,10 @@ def test_pq_eight_query_prefilter_is_exact(qb, oracle, case):
         luts = np.stack([pq.encode_query(q) for q in queries])
         ref = pq.scan(luts, top)
         for i in range(nq):
-            assert_topk_equal(got[i], ref[i], None, f"pq8 {case} vs oracle q={i}")
+            assert_topk_equal(got[i], ref[i], None, f"pq{qpp} {case} vs oracle q={i}")
     for i in range(nq):
-        np.testing.assert_array_equal(got[i]["idx"], want[i]["idx"], err_msg=f"pq8 {case} q={i}")
-        np.testing.assert_array_equal(got[i]["score"].view(np.uint32), want[i]["score"].view(np.uint32), err_msg=f"pq8 {case} q={i}")
+        np.testing.assert_array_equal(got[i]["idx"], want[i]["idx"], err_msg=f"pq{qpp} {case} q={i}")
+        np.testing.assert_array_equal(got[i]["score"].view(np.uint32), want[i]["score"].view(np.uint32), err_msg=f"pq{qpp} {case} q={i}")
     st.close()
 
 
