@@ -58,6 +58,7 @@ QbOptions& qb_opt() {
         QbOptions v;
         auto num = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? strtoll(e, nullptr, 10) : dflt; };
         v.disable_localk = getenv("QB_DISABLE_LOCALK") != nullptr;
+        v.disable_prefilter = getenv("QB_DISABLE_PREFILTER") != nullptr;
         v.disable_mma = getenv("QB_DISABLE_MMA") != nullptr;
         v.mma_1cta = getenv("QB_MMA_1CTA") != nullptr;
         v.mma_no_segments = getenv("QB_MMA_NO_SEGMENTS") != nullptr;
@@ -77,6 +78,7 @@ extern "C" qb_status qb_set_option(const char* name, int64_t value) {
     QbOptions& o = qb_opt();
     const std::string n(name);
     if (n == "disable_localk") o.disable_localk = value != 0;
+    else if (n == "disable_prefilter") o.disable_prefilter = value != 0;
     else if (n == "disable_mma") o.disable_mma = value != 0;
     else if (n == "mma_1cta") o.mma_1cta = value != 0;
     else if (n == "mma_no_segments") o.mma_no_segments = value != 0;
@@ -204,7 +206,7 @@ static void ctx_destroy(QbSearchCtx* c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_queries_raw); cudaFree(c->d_queries_enc); cudaFree(c->d_q_off); cudaFree(c->d_thr); cudaFree(c->d_cnt); cudaFree(c->d_done);
-    cudaFree(c->d_cand); cudaFree(c->d_out); cudaFree(c->d_out_counts); cudaFree(c->d_deleted2); cudaFree(c->d_ids); cudaFree(c->d_mma);
+    cudaFree(c->d_cand); cudaFree(c->d_out); cudaFree(c->d_out_counts); cudaFree(c->d_deleted2); cudaFree(c->d_ids); cudaFree(c->d_mma); cudaFree(c->d_pf);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -432,7 +434,7 @@ extern "C" void qb_storage_destroy(qb_storage* s) {
     for (auto& pr : s->prof_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : s->prof_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(s->d_rows); cudaFree(s->d_bf16); cudaFree(s->d_bf16_meta); cudaFree(s->d_codes); cudaFree(s->d_voff); cudaFree(s->d_pq_div); cudaFree(s->d_centroids); cudaFree(s->d_pq_codes);
-    cudaFree(s->d_bq_rows); cudaFree(s->d_mean_std); cudaFree(s->d_deleted);
+    cudaFree(s->d_bq_rows); cudaFree(s->d_mean_std); cudaFree(s->d_deleted); cudaFree(s->d_pf_fallbacks);
     cudaGetLastError();
     delete s;
 }
@@ -609,6 +611,21 @@ static void profile_begin(qb_storage* s, QbSearchCtx* c, cudaStream_t stream, cu
     if (!*e0) { cudaEventCreate(e0); cudaEventCreate(e1); }
     cudaEventRecord(*e0, stream);
 }
+// the same pair without recording: the callee brackets its dominant kernel itself
+static void profile_acquire(qb_storage* s, cudaEvent_t* e0, cudaEvent_t* e1) {
+    *e0 = *e1 = nullptr;
+    if (!s->profile) return;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->prof_free.empty()) { *e0 = s->prof_free.back().first; *e1 = s->prof_free.back().second; s->prof_free.pop_back(); }
+    }
+    if (!*e0) { cudaEventCreate(e0); cudaEventCreate(e1); }
+}
+static void profile_commit(qb_storage* s, cudaEvent_t e0, cudaEvent_t e1) {
+    if (!e0) return;
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->prof_pending.emplace_back(e0, e1);
+}
 static void profile_end(qb_storage* s, cudaStream_t stream, cudaEvent_t e0, cudaEvent_t e1) {
     if (!e0) return;
     cudaEventRecord(e1, stream);
@@ -638,6 +655,20 @@ static qb_status run_search(qb_storage* s, QbSearchCtx* c, uint32_t nq, uint32_t
         a.emit.final_out = d_out; a.emit.final_count = d_counts; a.emit.done_counter = c->d_done;
         uint64_t n_slots = 0;
         cudaEvent_t e0, e1;
+        // dot / cosine on a large storage: the scan reads the bf16 shadow plane (half the bytes), survivors are re-scored exactly and a
+        // device-side flag falls back to the exact scan below when the prefilter's candidate list overflowed (qb_prefilter.cu)
+        if (qb_f32_prefilter_usable(s, n_cand, top, stream)) {
+            if (!c->d_pf) { QB_CUDA(cudaMalloc(&c->d_pf, qb_f32_prefilter_scratch_bytes())); QB_CUDA(cudaMemsetAsync(c->d_pf, 0, 256, stream)); }
+            {
+                std::lock_guard<std::mutex> lk(s->mu);
+                if (!s->d_pf_fallbacks) { QB_CUDA(cudaMalloc(&s->d_pf_fallbacks, 256)); QB_CUDA(cudaMemsetAsync(s->d_pf_fallbacks, 0, 256, stream)); }
+            }
+            profile_acquire(s, &e0, &e1);
+            QB_TRY(qb_f32_prefilter_search(s, a, top, c->d_pf, s->d_pf_fallbacks, d_out, d_counts, e0, e1, stream));
+            profile_commit(s, e0, e1);
+            if (can_flag) *can_flag = false;
+            return QB_OK;
+        }
         profile_begin(s, c, stream, &e0, &e1);
         QB_TRY(qb_dense_f32_scan_localk(s, a, top, &n_slots, stream));
         if (n_slots != 0 && n_slots <= 4096) {
@@ -1563,8 +1594,16 @@ extern "C" qb_status qb_profile_read(qb_storage* s, uint64_t* launches, double* 
 
 extern "C" qb_status qb_search_stats(qb_storage* s, uint64_t* searches, uint64_t* reruns, int32_t reset) {
     QB_CHECK(s, QB_ERR_INVALID, "search_stats: null storage");
+    // single-query prefilter searches fall back on the device (no host round trip): their count lives in device memory
+    unsigned int dev_fallbacks = 0;
+    if (s->d_pf_fallbacks) {
+        QB_TRY(use_device(s->device));
+        QB_CUDA(cudaDeviceSynchronize());
+        QB_CUDA(cudaMemcpy(&dev_fallbacks, s->d_pf_fallbacks, 4, cudaMemcpyDeviceToHost));
+        if (reset) QB_CUDA(cudaMemset(s->d_pf_fallbacks, 0, 4));
+    }
     if (searches) *searches = s->n_searches.load();
-    if (reruns) *reruns = s->n_reruns.load();
+    if (reruns) *reruns = s->n_reruns.load() + dev_fallbacks;
     if (reset) { s->n_searches = 0; s->n_reruns = 0; }
     return QB_OK;
 }

@@ -47,6 +47,7 @@ struct QbOptions {
     int pq_queries_per_pass = 0;   // 0 = automatic
     int hnsw_threads = 0;          // 0 / 128 (default) or 256 threads per traversal CTA
     bool hnsw_no_prefetch = false;
+    bool disable_prefilter = false;   // single-query dense f32 searches: always the exact f32 scan (no bf16 shadow plane, qb_prefilter.cu)
     uint32_t mma_seg_cap = 0;      // 0 = 256 survivor slots per (query, CTA) segment of the tensor-core scan
     uint64_t sample_rows = 0;
 };
@@ -109,6 +110,7 @@ struct QbEmit {
     uint32_t local_k;               // per-CTA top-k mode of the dense streaming kernel: entries kept per warp / written per CTA
     // per-CTA top-k mode: the LAST CTA to finish merges the per-CTA lists and writes the query's final top-k here (no select launch)
     qb_scored_point* final_out; uint32_t* final_count; unsigned int* done_counter;
+    const unsigned int* run_if;     // per-CTA top-k mode: when set, the scan runs only if *run_if != 0 (device-side fallback of qb_prefilter.cu)
 };
 
 #ifdef __CUDACC__

@@ -113,6 +113,7 @@ __device__ __noinline__ LkState lk_drain(LkState st, const unsigned long long* q
 template <int METRIC, bool LOCALK>
 __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(const StreamParams p, const QbEmit emit) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (LOCALK && emit.run_if && *emit.run_if == 0u) return;      // conditional launch (uniform): the prefilter path answered already
     float* q_s = reinterpret_cast<float*>(smem);
     uint8_t* slots = smem + p.q_smem_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(slots + (size_t)p.n_slots * p.slot_bytes);

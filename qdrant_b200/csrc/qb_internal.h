@@ -25,6 +25,7 @@ struct QbSearchCtx {
     uint32_t* d_out_counts = nullptr; size_t out_counts_elems = 0;
     uint32_t* d_deleted2 = nullptr;  size_t deleted2_words = 0;
     uint32_t* d_ids = nullptr;       size_t ids_elems = 0;
+    void* d_pf = nullptr;            // single-query bf16 prefilter: counters, sample top-k, candidate rows (qb_prefilter.cu)
     void* d_mma = nullptr;           size_t mma_bytes = 0;           // batched SQ8: sorted query codes / permutation / chunk thresholds
     // pinned host staging
     void* h_stage = nullptr;         size_t h_stage_bytes = 0;
@@ -87,6 +88,7 @@ struct qb_storage {
     // ---- contexts / profiling
     std::mutex mu;
     std::vector<QbSearchCtx*> ctxs;       // pool for the host-facing searches (one per concurrent call)
+    unsigned int* d_pf_fallbacks = nullptr;   // device-side count of prefilter searches answered by the exact fallback scan
     QbSearchCtx* dev_ctx = nullptr;       // reserved for qb_storage_stream / the *_device entry points; never handed out by the pool
     std::atomic<uint64_t> n_searches{0}, n_reruns{0};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
@@ -191,6 +193,12 @@ struct QbScanArgs {
     void* d_scratch; size_t scratch_bytes;   // optional per-call scratch (PQ: interleaved u8 tables of the sixteen-query prefilter)
 };
 size_t qb_pq_scratch_bytes(const qb_storage* s, uint32_t nq);
+// single-query dense f32 searches through the bf16 shadow plane (qb_prefilter.cu)
+qb_status qb_f32_shadow_ensure(qb_storage* s, cudaStream_t stream);
+bool qb_f32_prefilter_usable(qb_storage* s, uint64_t n_rows, uint32_t top, cudaStream_t stream);
+size_t qb_f32_prefilter_scratch_bytes();
+qb_status qb_f32_prefilter_search(qb_storage* s, const QbScanArgs& a, uint32_t top, void* d_scratch, unsigned int* d_n_fallbacks, qb_scored_point* d_out, uint32_t* d_out_cnt,
+                                  cudaEvent_t prof0, cudaEvent_t prof1, cudaStream_t stream);
 qb_status qb_launch_scan(const qb_storage* s, const QbScanArgs& a, cudaStream_t stream);
 
 // score listed ids for ONE encoded query into d_scores (RawScorer::score_points)

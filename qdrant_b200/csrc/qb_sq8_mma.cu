@@ -866,7 +866,7 @@ qb_status qb_sq8_mma_scan(const qb_storage* s, const uint8_t* d_q_codes, uint32_
 // ---------------------------------------------------------------------------------------------- dense f32 batches (F16 prefilter + exact rescoring)
 // bf16 shadow plane of a dense f32 storage, built on first use (and rebuilt after rows were rewritten): +50 % HBM for the storage, the
 // price of reading 2 bytes per element instead of 4 on every batched pass and of feeding the tensor cores.
-static qb_status f32_shadow_ensure(qb_storage* s, cudaStream_t stream) {
+qb_status qb_f32_shadow_ensure(qb_storage* s, cudaStream_t stream) {
     std::lock_guard<std::mutex> lk(s->mu);          // concurrent first batches build it once
     if (s->bf16_ready) return QB_OK;
     const uint32_t row_h = (uint32_t)round_up_u64(s->dim, 8);
@@ -895,7 +895,7 @@ uint32_t qb_f32_mma_block(qb_storage* s, uint32_t nq, cudaStream_t stream) {
     if (s->kind != QB_KIND_DENSE || s->dtype != QB_DT_F32) return 0;
     if (s->distance != QB_DIST_DOT && s->distance != QB_DIST_COSINE) return 0;   // the approximation bounds a dot product
     if (nq < 32 || s->count < 65536 || s->dim < 32 || qb_opt().disable_mma) return 0;
-    if (f32_shadow_ensure(s, stream) != QB_OK) { cudaGetLastError(); return 0; }  // e.g. no room for the shadow plane: stay on the exact kernels
+    if (qb_f32_shadow_ensure(s, stream) != QB_OK) { cudaGetLastError(); return 0; }  // e.g. no room for the shadow plane: stay on the exact kernels
     if (!s->bf16_usable) return 0;                                                // NaN / inf rows: only the exact kernels honour OrderedFloat
     const uint32_t k_bytes = (uint32_t)round_up_u64(s->dim, 8) * 2;
     if (!qb_opt().mma_1cta && !(s->sm_count & 1))

@@ -244,3 +244,74 @@ def test_f32_batch_with_nan_rows_and_nan_queries_stays_exact(qb, oracle):
     got = st.search_batch(queries[:4].copy() * 0 + rng.standard_normal((4, dim)).astype(np.float32), 5)
     assert all(g["idx"][0] == 777 and np.isnan(g["score"][0]) for g in got)
     st.close()
+
+
+# ------------------------------------------------------------------------------------------------ single query through the bf16 shadow plane
+@pytest.mark.parametrize("dist,n,dim,top", [("Cosine", 600_000, 64, 10), ("Dot", 560_001, 200, 16), ("Cosine", 530_000, 264, 1), ("Dot", 524_288, 520, 10),
+                                            ("Cosine", 540_000, 1000, 10)])
+def test_single_query_prefilter_is_exact(qb, oracle, dist, n, dim, top):
+    """Single-query top-k on >= 2^19 rows (dot / cosine): the scan streams the bf16 shadow plane, keeps every row within eps_q of the exact
+    sample threshold, re-scores the survivors in the AVX order — identical, bit for bit, to the exact f32 scan (option disable_prefilter)
+    and to the oracle; no fallback on ordinary data; deletions and id_base honoured."""
+    d = getattr(qb.Distance, dist)
+    rng = np.random.default_rng(dim + top)
+    base = (rng.standard_normal((n, dim), dtype=np.float32) * (1.0 if dist == "Cosine" else rng.uniform(0.2, 3.0, (n, 1)).astype(np.float32)))
+    if d == qb.Distance.Cosine:
+        base = oracle.preprocess_rows_f32(oracle.COSINE, base)
+    queries = rng.standard_normal((5, dim)).astype(np.float32)
+    queries[1] = base[n - 7] * 2.0                    # best match in the very last rows
+    queries[2] = base[3] * 0.5                        # ... and inside the exactly-scored sample prefix
+    deleted = rng.random(n) < 0.02
+    st = qb.DenseVectorStorage(base, d)
+    from qdrant_b200._capi import check, lib
+    check(lib().qb_storage_set_id_base(st._h, 1000))
+    st.search_stats(reset=True)
+    got = [st.search_batch(q, top, point_deleted=deleted)[0] for q in queries]
+    searches, reruns = st.search_stats(reset=True)
+    assert (searches, reruns) == (5, 0), (searches, reruns)
+    qb.set_option("disable_prefilter", 1)
+    try:
+        exact = [st.search_batch(q, top, point_deleted=deleted)[0] for q in queries]
+    finally:
+        qb.set_option("disable_prefilter", 0)
+    for a, b in zip(got, exact):
+        np.testing.assert_array_equal(a["idx"], b["idx"])
+        np.testing.assert_array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32))
+    qp = np.stack([oracle.preprocess_f32(int(d), q) for q in queries[:2]])
+    want = oracle.scan_f32(int(d), base, qp, top, deleted=pack_bitmap(deleted))
+    for i in range(2):
+        g = got[i].copy()
+        g["idx"] -= 1000
+        assert_topk_equal(g, want[i], None, f"prefilter {dist} dim={dim} q={i}")
+    st.close()
+
+
+def test_single_query_prefilter_falls_back_on_the_device(qb, oracle):
+    """Cases the prefilter cannot decide go to the exact scan WITHOUT a host round trip (the finish kernel raises a device flag, the
+    always-enqueued exact scan runs): mass ties (more tied rows than candidate slots), a NaN query, a sample prefix that is almost
+    entirely deleted.  Results == exact path; the fallbacks are counted by qb_search_stats."""
+    rng = np.random.default_rng(9)
+    n, dim = 600_000, 96
+    base = rng.standard_normal((n, dim), dtype=np.float32)
+    base[100_000:110_000] = base[99_999]              # 10 001 identical rows, and they are the best match of query 0
+    st = qb.DenseVectorStorage(base, qb.Distance.Dot)
+    q_ties = base[99_999] * 4.0
+    q_nan = rng.standard_normal(dim).astype(np.float32); q_nan[5] = np.nan
+    q_plain = rng.standard_normal(dim).astype(np.float32)
+    del_prefix = np.zeros(n, bool); del_prefix[:200_000] = True; del_prefix[:4] = False    # 4 live rows in the sample < top
+    cases = [(q_ties, None), (q_nan, None), (q_plain, del_prefix), (q_plain, None)]
+    st.search_stats(reset=True)
+    got = [st.search_batch(q, 10, point_deleted=dl)[0] for q, dl in cases]
+    searches, reruns = st.search_stats(reset=True)
+    assert searches == 4 and reruns == 3, (searches, reruns)
+    qb.set_option("disable_prefilter", 1)
+    try:
+        exact = [st.search_batch(q, 10, point_deleted=dl)[0] for q, dl in cases]
+    finally:
+        qb.set_option("disable_prefilter", 0)
+    for i, (a, b) in enumerate(zip(got, exact)):
+        np.testing.assert_array_equal(a["idx"], b["idx"], err_msg=f"case {i}")
+        np.testing.assert_array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32), err_msg=f"case {i}")
+    assert list(got[0]["idx"]) == list(range(99_999, 100_009))          # ties broken by ascending id
+    assert np.isnan(got[1]["score"]).all()
+    st.close()
