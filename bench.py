@@ -377,6 +377,7 @@ def main_ours(args):
     # single-query searches on >= 2^19 rows stream the bf16 shadow plane and re-score the survivors exactly (qb_prefilter.cu): the timed path
     # must return what the exact f32 scan returns, bit for bit, on the whole shard
     prefilter = n_local >= (1 << 19) and not os.environ.get("QB_DISABLE_PREFILTER")
+    plane_q8 = prefilter and os.environ.get("QB_PREFILTER_PLANE", "0") != "1" and args.dim <= 1024   # int8 codes + per-row scale, else bf16
     if prefilter:
         from qdrant_b200.scorer import set_option
         fast = [st.search_batch(queries[i], TOP)[0] for i in range(3)]
@@ -403,7 +404,7 @@ def main_ours(args):
         achieved = algo_bytes / (kern_ms / 1e3) / 1e9 if n_prof else None
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's main pass from the committed `ncu --set full` capture; it
         # was taken on the 10M x 768 single-GPU workload, so it is only quoted for that shape
-        traffic, traffic_src = ncu_traffic("ncu_bf16_filter_kernel_r02.txt" if prefilter else "ncu_stream_kernel_r01_localk.txt") if (n_local == 10_000_000 and args.dim == 768) else (None, None)
+        traffic, traffic_src = ncu_traffic(("ncu_q8_filter_kernel_r02.txt" if plane_q8 else "ncu_bf16_filter_kernel_r02.txt") if prefilter else "ncu_stream_kernel_r01_localk.txt") if (n_local == 10_000_000 and args.dim == 768) else (None, None)
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -414,17 +415,19 @@ def main_ours(args):
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": launches,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": ("dense_bf16_filter_kernel (the scan reads the bf16 shadow plane: 2 bytes per element; exact f32 sample scan before, exact "
-                                                    "rescoring of the survivors after)") if prefilter else "dense_f32_stream_kernel (main pass)",
+            "roofline": {"bound": "hbm", "kernel": (("dense_q8_filter_kernel (the scan reads the int8 shadow plane: 1 byte per element + a 4-byte scale per row; "
+                                                     if plane_q8 else "dense_bf16_filter_kernel (the scan reads the bf16 shadow plane: 2 bytes per element; ") +
+                                                    "exact f32 sample scan before, exact rescoring of the survivors after)") if prefilter else "dense_f32_stream_kernel (main pass)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms, "launches_timed": n_prof},
         }
         if prefilter and n_prof:
             # algorithmic bytes (dim x 4 per row) / time exceeds the HBM peak because the kernel moves half of them
-            line["roofline"]["bytes_moved_per_launch"] = algo_bytes // 2
-            line["roofline"]["hbm_frac_of_bytes_moved"] = algo_bytes / 2 / (kern_ms / 1e3) / 1e9 / peak
-            line["roofline"]["note"] = ("achieved = algorithmic f32 bytes / kernel time; the kernel itself streams the bf16 plane (bytes_moved_per_launch) at "
+            moved = n_local * (((args.dim + 15) // 16) * 16 + 4) if plane_q8 else algo_bytes // 2
+            line["roofline"]["bytes_moved_per_launch"] = moved
+            line["roofline"]["hbm_frac_of_bytes_moved"] = moved / (kern_ms / 1e3) / 1e9 / peak
+            line["roofline"]["note"] = ("achieved = algorithmic f32 bytes / kernel time; the kernel itself streams the shadow plane (bytes_moved_per_launch) at "
                                         "hbm_frac_of_bytes_moved of the measured copy peak; results are bit-identical to the f32 scan (parity.prefilter_equals_exact_scan)")
         line["parity"] = parity
         line["fallback_reruns"] = reruns

@@ -59,6 +59,7 @@ QbOptions& qb_opt() {
         auto num = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? strtoll(e, nullptr, 10) : dflt; };
         v.disable_localk = getenv("QB_DISABLE_LOCALK") != nullptr;
         v.disable_prefilter = getenv("QB_DISABLE_PREFILTER") != nullptr;
+        v.prefilter_plane = (int)num("QB_PREFILTER_PLANE", 0);
         v.disable_mma = getenv("QB_DISABLE_MMA") != nullptr;
         v.mma_1cta = getenv("QB_MMA_1CTA") != nullptr;
         v.mma_no_segments = getenv("QB_MMA_NO_SEGMENTS") != nullptr;
@@ -79,6 +80,7 @@ extern "C" qb_status qb_set_option(const char* name, int64_t value) {
     const std::string n(name);
     if (n == "disable_localk") o.disable_localk = value != 0;
     else if (n == "disable_prefilter") o.disable_prefilter = value != 0;
+    else if (n == "prefilter_plane") o.prefilter_plane = (int)value;
     else if (n == "disable_mma") o.disable_mma = value != 0;
     else if (n == "mma_1cta") o.mma_1cta = value != 0;
     else if (n == "mma_no_segments") o.mma_no_segments = value != 0;
@@ -261,6 +263,7 @@ extern "C" qb_status qb_storage_write_rows(qb_storage* s, uint64_t first_row, ui
     QB_CUDA(cudaMemcpy2D(reinterpret_cast<uint8_t*>(s->d_rows) + first_row * s->row_stride, s->row_stride, host_rows, row_stride_bytes, rb, n_rows,
                          cudaMemcpyHostToDevice));
     s->bf16_ready = false;   // the bf16 shadow (if any) no longer mirrors the rows
+    s->q8_ready = false;
     return QB_OK;
 }
 
@@ -274,6 +277,7 @@ extern "C" qb_status qb_storage_write_rows_device(qb_storage* s, uint64_t first_
     QB_CUDA(cudaMemcpy2D(reinterpret_cast<uint8_t*>(s->d_rows) + first_row * s->row_stride, s->row_stride, dev_rows, row_stride_bytes, rb, n_rows,
                          cudaMemcpyDeviceToDevice));
     s->bf16_ready = false;
+    s->q8_ready = false;
     return QB_OK;
 }
 
@@ -433,7 +437,7 @@ extern "C" void qb_storage_destroy(qb_storage* s) {
     ctx_destroy(s->dev_ctx);
     for (auto& pr : s->prof_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : s->prof_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    cudaFree(s->d_rows); cudaFree(s->d_bf16); cudaFree(s->d_bf16_meta); cudaFree(s->d_codes); cudaFree(s->d_voff); cudaFree(s->d_pq_div); cudaFree(s->d_centroids); cudaFree(s->d_pq_codes);
+    cudaFree(s->d_rows); cudaFree(s->d_bf16); cudaFree(s->d_bf16_meta); cudaFree(s->d_q8); cudaFree(s->d_q8_scale); cudaFree(s->d_q8_meta); cudaFree(s->d_codes); cudaFree(s->d_voff); cudaFree(s->d_pq_div); cudaFree(s->d_centroids); cudaFree(s->d_pq_codes);
     cudaFree(s->d_bq_rows); cudaFree(s->d_mean_std); cudaFree(s->d_deleted); cudaFree(s->d_pf_fallbacks);
     cudaGetLastError();
     delete s;

@@ -249,10 +249,12 @@ def test_f32_batch_with_nan_rows_and_nan_queries_stays_exact(qb, oracle):
 # ------------------------------------------------------------------------------------------------ single query through the bf16 shadow plane
 @pytest.mark.parametrize("dist,n,dim,top", [("Cosine", 600_000, 64, 10), ("Dot", 560_001, 200, 16), ("Cosine", 530_000, 264, 1), ("Dot", 524_288, 520, 10),
                                             ("Cosine", 540_000, 1000, 10)])
-def test_single_query_prefilter_is_exact(qb, oracle, dist, n, dim, top):
-    """Single-query top-k on >= 2^19 rows (dot / cosine): the scan streams the bf16 shadow plane, keeps every row within eps_q of the exact
-    sample threshold, re-scores the survivors in the AVX order — identical, bit for bit, to the exact f32 scan (option disable_prefilter)
-    and to the oracle; no fallback on ordinary data; deletions and id_base honoured."""
+@pytest.mark.parametrize("plane", [0, 1])
+def test_single_query_prefilter_is_exact(qb, oracle, dist, n, dim, top, plane):
+    """Single-query top-k on >= 2^19 rows (dot / cosine): the scan streams a shadow plane — int8 codes with a per-row scale (plane 0) or
+    bf16 (plane 1) —, keeps every row whose error bound reaches the exact sample threshold, re-scores the survivors in the AVX order —
+    identical, bit for bit, to the exact f32 scan (option disable_prefilter) and to the oracle; no fallback on ordinary data; deletions and
+    id_base honoured; all-zero and denormal rows in the storage."""
     d = getattr(qb.Distance, dist)
     rng = np.random.default_rng(dim + top)
     base = (rng.standard_normal((n, dim), dtype=np.float32) * (1.0 if dist == "Cosine" else rng.uniform(0.2, 3.0, (n, 1)).astype(np.float32)))
@@ -261,12 +263,20 @@ def test_single_query_prefilter_is_exact(qb, oracle, dist, n, dim, top):
     queries = rng.standard_normal((5, dim)).astype(np.float32)
     queries[1] = base[n - 7] * 2.0                    # best match in the very last rows
     queries[2] = base[3] * 0.5                        # ... and inside the exactly-scored sample prefix
+    if dist == "Dot":
+        base[1000:1010] = 0.0
+        base[2000:2010] *= np.float32(1e-38)          # denormal rows
+        queries[3, ::2] = 0.0
     deleted = rng.random(n) < 0.02
+    qb.set_option("prefilter_plane", plane)
     st = qb.DenseVectorStorage(base, d)
     from qdrant_b200._capi import check, lib
     check(lib().qb_storage_set_id_base(st._h, 1000))
     st.search_stats(reset=True)
-    got = [st.search_batch(q, top, point_deleted=deleted)[0] for q in queries]
+    try:
+        got = [st.search_batch(q, top, point_deleted=deleted)[0] for q in queries]
+    finally:
+        qb.set_option("prefilter_plane", 0)
     searches, reruns = st.search_stats(reset=True)
     assert (searches, reruns) == (5, 0), (searches, reruns)
     qb.set_option("disable_prefilter", 1)
@@ -293,7 +303,7 @@ def test_single_query_prefilter_falls_back_on_the_device(qb, oracle):
     rng = np.random.default_rng(9)
     n, dim = 600_000, 96
     base = rng.standard_normal((n, dim), dtype=np.float32)
-    base[100_000:110_000] = base[99_999]              # 10 001 identical rows, and they are the best match of query 0
+    base[100_000:120_000] = base[99_999]              # 20 001 identical rows (more than the candidate list holds), the best match of query 0
     st = qb.DenseVectorStorage(base, qb.Distance.Dot)
     q_ties = base[99_999] * 4.0
     q_nan = rng.standard_normal(dim).astype(np.float32); q_nan[5] = np.nan
