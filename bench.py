@@ -415,7 +415,7 @@ def main_ours(args):
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": launches,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": (("dense_q8_filter_kernel (the scan reads the int8 shadow plane: 1 byte per element + a 4-byte scale per row; "
+            "roofline": {"bound": "hbm", "kernel": (("dense_q8_filter_kernel (the scan reads the int8 shadow plane: 1 byte per element + 16 bytes per row for its scale; "
                                                      if plane_q8 else "dense_bf16_filter_kernel (the scan reads the bf16 shadow plane: 2 bytes per element; ") +
                                                     "exact f32 sample scan before, exact rescoring of the survivors after)") if prefilter else "dense_f32_stream_kernel (main pass)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -424,7 +424,7 @@ def main_ours(args):
         }
         if prefilter and n_prof:
             # algorithmic bytes (dim x 4 per row) / time exceeds the HBM peak because the kernel moves half of them
-            moved = n_local * (((args.dim + 15) // 16) * 16 + 4) if plane_q8 else algo_bytes // 2
+            moved = n_local * (((args.dim + 15) // 16) * 16 + 16) if plane_q8 else algo_bytes // 2
             line["roofline"]["bytes_moved_per_launch"] = moved
             line["roofline"]["hbm_frac_of_bytes_moved"] = moved / (kern_ms / 1e3) / 1e9 / peak
             line["roofline"]["note"] = ("achieved = algorithmic f32 bytes / kernel time; the kernel itself streams the shadow plane (bytes_moved_per_launch) at "

@@ -50,7 +50,7 @@ struct qb_storage {
     uint16_t* d_bf16 = nullptr;  uint32_t bf16_row_h = 0;  unsigned int* d_bf16_meta = nullptr;   // meta: [0] max |row| (float bits), [1] non-finite flag
     bool bf16_ready = false, bf16_usable = false;
     // int8 shadow (per-row scale) for single-query searches (qb_prefilter.cu): a quarter of the f32 bytes per scan; built on first use
-    int8_t* d_q8 = nullptr;  float* d_q8_scale = nullptr;  uint32_t q8_row_b = 0;  unsigned int* d_q8_meta = nullptr;   // meta as above
+    int8_t* d_q8 = nullptr;  uint32_t q8_row_b = 0;  unsigned int* d_q8_meta = nullptr;   // meta as above
     bool q8_ready = false, q8_usable = false;
     uint32_t row_stride = 0;         // bytes
     uint32_t elem_size = 4;

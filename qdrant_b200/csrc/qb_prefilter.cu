@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_bf16_filter_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------------ int8 shadow plane (a quarter of the bytes)
-// x_i ~ s_r c_i, c_i = rint(x_i / s_r) in [-127, 127], s_r = max_i |x_i| / 127 (one f32 scale per row, a separate array);
+// x_i ~ s_r c_i, c_i = rint(x_i / s_r) in [-127, 127], s_r = max_i |x_i| / 127 (one f32 scale per row, stored right behind the row's codes);
 // the QUERY is split into two int8 levels, q_i ~ s_q (h_i + l_i / 254), so that its own error is negligible and the scan is integer only:
 //   H = sum_i h_i c_i, L = sum_i l_i c_i   (dp4a, exact: dim * 127^2 < 2^24 for dim <= 1040),   approx = s_r s_q (H + L / 254)
 //   | exact - approx |  <=  s_r (1/2 + 2^-13) ||q||_1          (row rounding:   |x_i - s_r c_i| <= s_r (1/2 + 1e-4))
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_bf16_filter_kernel(const 
 // so a row passes iff  s_r * (s_q (H + L / 254) + E_q) >= thr_q - slack_q  with the per-query constant
 // E_q = (1/2 + 2^-13) ||q||_1 + 0.27 s_q dim: one FMA, one multiply and one compare per row after two warp-wide integer sums.
 __global__ void __launch_bounds__(256) f32_to_q8_rows_kernel(const float* __restrict__ rows, uint64_t stride_f, uint32_t dim, uint64_t n, int8_t* __restrict__ out,
-                                                              uint32_t out_stride_b, float* __restrict__ scales, unsigned int* __restrict__ max_norm_bits,
+                                                              uint32_t out_stride_b /* codes + 16: the row's f32 scale follows its codes */, unsigned int* __restrict__ max_norm_bits,
                                                               unsigned int* __restrict__ nonfinite) {
     const int t = threadIdx.x & 7;
     const uint64_t groups = (uint64_t)gridDim.x * (blockDim.x >> 3), g0 = (uint64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
@@ -196,13 +196,13 @@ __global__ void __launch_bounds__(256) f32_to_q8_rows_kernel(const float* __rest
         const bool tiny = !(mx >= 1.0e-30f);                      // zero (or denormal-only) rows: all codes 0, scale = max so that the error bound still holds
         const float sr = tiny ? __fmul_ru(mx, 2.0f) : __fdiv_rn(mx, 127.f);
         const float inv = tiny ? 0.f : __fdiv_rn(127.f, mx);
-        for (uint32_t i = t; i < out_stride_b; i += 8) {
+        for (uint32_t i = t; i < out_stride_b - 16; i += 8) {
             const float v = (i < dim) ? src[i] : 0.f;
             const float c = fminf(fmaxf(rintf(__fmul_rn(v, inv)), -127.f), 127.f);
             if (valid) dst[i] = (int8_t)(int)c;
         }
         if (valid && t == 0) {
-            scales[r] = sr;
+            *reinterpret_cast<float4*>(dst + (out_stride_b - 16)) = make_float4(sr, 0.f, 0.f, 0.f);
             if (bad || !(ss <= 3.0e38f)) atomicOr(nonfinite, 1u);
             else atomicMax(max_norm_bits, __float_as_uint(sqrtf(ss) * 1.000001f));
         }
@@ -210,8 +210,7 @@ __global__ void __launch_bounds__(256) f32_to_q8_rows_kernel(const float* __rest
 }
 
 struct Pf8Params {
-    const uint8_t* rows;        // int8 plane
-    const float* scales;        // per-row scale
+    const uint8_t* rows;        // int8 plane: per row `stride - 16` code bytes, then the row's f32 scale (+ 12 bytes of padding)
     uint32_t stride;            // bytes per row (multiple of 16)
     uint32_t dim;
     uint64_t n_rows;
@@ -226,17 +225,17 @@ struct Pf8Params {
 
 __device__ __forceinline__ uint32_t pack_s8x4(int a, int b, int c, int d) { return (uint32_t)(a & 255) | ((uint32_t)(b & 255) << 8) | ((uint32_t)(c & 255) << 16) | ((uint32_t)(d & 255) << 24); }
 
-// NCH = 8-byte chunks of a row per lane (stride <= NCH * 256)
+// NCH = 8-byte chunks of a row's codes per lane (stride - 16 <= NCH * 256)
 template <int NCH>
 __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf8Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* slots = smem;                                       // [n_slots][slot_bytes]: rows_per_slot rows, then rows_per_slot f32 scales
+    uint8_t* slots = smem;                                       // [n_slots][slot_bytes]
     uint64_t* full = reinterpret_cast<uint64_t*>(slots + (size_t)p.n_slots * p.slot_bytes);
     uint64_t* empty = full + p.n_slots;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t n_tiles = (p.n_rows + p.rows_per_slot - 1) / p.rows_per_slot;
     const uint64_t n_local = (blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t rows_bytes = p.rows_per_slot * p.stride;
+    const uint32_t code_b = p.stride - 16;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_slots; ++s) { qb_mbar_init(&full[s], 1); qb_mbar_init(&empty[s], 1); }
         qb_fence_barrier_init();
@@ -252,10 +251,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
                 const uint64_t r0 = (blockIdx.x + i * gridDim.x) * p.rows_per_slot;
                 const uint64_t left = p.n_rows - r0;
                 const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
-                const uint32_t bytes = nr * p.stride, sbytes = ((nr + 3u) & ~3u) * 4u;   // the scale array is padded: whole 16-byte pieces
-                qb_mbar_arrive_expect_tx(&full[s], bytes + sbytes);
+                const uint32_t bytes = nr * p.stride;
+                qb_mbar_arrive_expect_tx(&full[s], bytes);
                 qb_bulk_g2s(slots + (size_t)s * p.slot_bytes, p.rows + r0 * p.stride, bytes, &full[s], policy);
-                qb_bulk_g2s(slots + (size_t)s * p.slot_bytes + rows_bytes, p.scales + r0, sbytes, &full[s], policy);
             }
         }
         return;
@@ -269,10 +267,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const uint32_t d0 = (uint32_t)(c * 32 + lane) * 8;
-        off[c] = (d0 < p.stride) ? d0 : 0;
+        off[c] = (d0 < code_b) ? d0 : 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float v = (d0 < p.stride && d0 + k < p.dim) ? p.q[d0 + k] : 0.f;
+            const float v = (d0 < code_b && d0 + k < p.dim) ? p.q[d0 + k] : 0.f;
             qv[c][k] = v;
             qbad |= !(fabsf(v) <= 3.0e38f);
             qmax = fmaxf(qmax, fabsf(v)); q1 = __fadd_ru(q1, fabsf(v)); q2 = fmaf(v, v, q2);
@@ -316,7 +314,6 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
         const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
         qb_mbar_wait(&full[s], ph);
         const uint8_t* slot = slots + (size_t)s * p.slot_bytes;
-        const float* sc_s = reinterpret_cast<const float*>(slot + rows_bytes);
         for (uint32_t r = 0; r < nr; r += 2) {
             const bool two = r + 1 < nr;
             const uint8_t* ra = slot + (size_t)r * p.stride;
@@ -336,7 +333,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
             if (lane < 2 && (lane == 0 || two)) {
                 const int H = lane ? hb : ha, L = lane ? lb : la;
                 const float v = fmaf(sq, fmaf((float)L, k254, (float)H), e_q);
-                const float up = __fmul_ru(sc_s[r + lane], v);    // an upper bound of the exact score (up to slack_q)
+                const float up = __fmul_ru(*reinterpret_cast<const float*>((lane ? rb : ra) + code_b), v);    // an upper bound of the exact score (up to slack_q)
                 if (!(up < thr_adj)) {
                     const uint32_t id = (uint32_t)(r0 + r + lane);
                     bool dead = false;
@@ -357,10 +354,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
 template <int NCH>
 qb_status launch_filter_q8(Pf8Params& p, int sm_count, cudaStream_t stream) {
     const uint32_t kMaxSmem = 227 * 1024;
-    uint32_t rps = (12288 / p.stride) & ~3u;
-    if (rps < 4) rps = 4;
+    uint32_t rps = (12288 / p.stride) & ~1u;
+    if (rps < 2) rps = 2;
     p.rows_per_slot = rps;
-    p.slot_bytes = rps * p.stride + rps * 4;                      // rows + scales (both multiples of 16 bytes)
+    p.slot_bytes = rps * p.stride;
     uint32_t n_slots = (kMaxSmem - 2048) / p.slot_bytes;
     if (n_slots > 64) n_slots = 64;
     n_slots = (n_slots / PF_CONSUMER_WARPS) * PF_CONSUMER_WARPS;
@@ -450,23 +447,21 @@ qb_status launch_filter(PfParams& p, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-// int8 shadow plane (+ per-row scales) of a dense f32 storage, built on first use and rebuilt after rows were rewritten: +25 % HBM
+// int8 shadow plane (codes + the row's scale) of a dense f32 storage, built on first use and rebuilt after rows were rewritten: +26 % HBM
 static qb_status q8_shadow_ensure(qb_storage* s, cudaStream_t stream) {
     std::lock_guard<std::mutex> lk(s->mu);
     if (s->q8_ready) return QB_OK;
-    const uint32_t row_b = (uint32_t)round_up_u64(s->dim, 16);
+    const uint32_t row_b = (uint32_t)round_up_u64(s->dim, 16) + 16;      // codes, then the row's f32 scale in its own 16 bytes: one bulk copy per tile
     if (!s->d_q8) {
         QB_CUDA(cudaMalloc(&s->d_q8, std::max<size_t>((size_t)s->count * row_b, 256)));
-        QB_CUDA(cudaMalloc(&s->d_q8_scale, ((size_t)s->count + 8) * 4));
         QB_CUDA(cudaMalloc(&s->d_q8_meta, 256));
-        s->hbm_bytes += (uint64_t)s->count * (row_b + 4);
+        s->hbm_bytes += (uint64_t)s->count * row_b;
     }
     s->q8_row_b = row_b;
     QB_CUDA(cudaMemsetAsync(s->d_q8_meta, 0, 256, stream));
-    QB_CUDA(cudaMemsetAsync(s->d_q8_scale + s->count, 0, 32, stream));
     const uint64_t blocks = std::min<uint64_t>(ceil_div_u64(std::max<uint64_t>(s->count, 1), 32), (uint64_t)s->sm_count * 16);
-    f32_to_q8_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(s->d_rows), s->row_stride / 4, s->dim, s->count, s->d_q8, row_b, s->d_q8_scale,
-                                                                s->d_q8_meta, s->d_q8_meta + 1);
+    f32_to_q8_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(s->d_rows), s->row_stride / 4, s->dim, s->count, s->d_q8, row_b, s->d_q8_meta,
+                                                                s->d_q8_meta + 1);
     QB_LAUNCHED();
     QB_CUDA(cudaGetLastError());
     unsigned int meta[2] = {0, 0};
@@ -509,6 +504,7 @@ qb_status qb_f32_prefilter_search(qb_storage* s, const QbScanArgs& a, uint32_t t
     const uint64_t n = s->count;
     // 1. exact top-k of a prefix
     uint64_t sample = std::min<uint64_t>(131072, std::max<uint64_t>(65536, (n / 64) & ~(uint64_t)3));
+    if (qb_opt().sample_rows) sample = std::min<uint64_t>(n, std::max<uint64_t>(65536, qb_opt().sample_rows & ~(uint64_t)3));   // experiments
     QbScanArgs as = a;
     as.row_begin = 0; as.row_end = sample;
     as.emit.final_out = d_samp; as.emit.final_count = d_samp_cnt; as.emit.run_if = nullptr;
@@ -519,12 +515,12 @@ qb_status qb_f32_prefilter_search(qb_storage* s, const QbScanArgs& a, uint32_t t
     const float* d_q = reinterpret_cast<const float*>(a.d_q_enc);
     if (use_q8_plane(s) && s->q8_ready && s->q8_usable) {
         Pf8Params p8{};
-        p8.rows = reinterpret_cast<const uint8_t*>(s->d_q8); p8.scales = s->d_q8_scale; p8.stride = s->q8_row_b; p8.dim = s->dim; p8.n_rows = n;
+        p8.rows = reinterpret_cast<const uint8_t*>(s->d_q8); p8.stride = s->q8_row_b; p8.dim = s->dim; p8.n_rows = n;
         p8.q = d_q; p8.samp_out = d_samp; p8.samp_cnt = d_samp_cnt; p8.top = top; p8.max_norm_bits = s->d_q8_meta;
         p8.cand = d_cand; p8.cnt = d_cnt; p8.deleted = a.emit.deleted; p8.deleted2 = a.emit.deleted2;
         p8.l2_keep = ((uint64_t)n * p8.stride <= (64ull << 20)) ? 1 : 0;
         if (prof0) cudaEventRecord(prof0, stream);
-        switch ((p8.stride + 255) / 256) {
+        switch ((p8.stride - 16 + 255) / 256) {
             case 1: QB_TRY(launch_filter_q8<1>(p8, s->sm_count, stream)); break;
             case 2: QB_TRY(launch_filter_q8<2>(p8, s->sm_count, stream)); break;
             case 3: QB_TRY(launch_filter_q8<3>(p8, s->sm_count, stream)); break;
