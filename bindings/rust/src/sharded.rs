@@ -42,4 +42,19 @@ impl B200Shard {
         assert!(st == QB_OK, "{}", last_error());
         (0..n_queries).map(|q| out[q * top..q * top + counts[q] as usize].iter().map(|p| ScoredPointOffset { idx: p.idx, score: p.score }).collect()).collect()
     }
+
+    /// Device-resident, PIPELINED step (queries and results stay in HBM): the scan is enqueued on the storage's stream, the exchange + merge
+    /// on the communicator's; the next step's scan does not wait for this step's merge.  `drain()` before reading `dev_out`.
+    pub unsafe fn search_device(&self, dev_queries: *const f32, n_queries: usize, top: usize, dev_out: *mut qb_scored_point, dev_counts: *mut u32) -> OperationResult<()> {
+        let st = qb_multi_search_batch_device(self.comm, self.storage.raw, dev_queries, n_queries as u32, top as u32, std::ptr::null_mut(), std::ptr::null_mut(), dev_out,
+                                              dev_counts);
+        if st != QB_OK { return Err(OperationError::service_error(last_error())); }
+        Ok(())
+    }
+
+    /// Waits for every exchange + merge enqueued so far; a peer that never made the matching call surfaces here as an error.
+    pub fn drain(&self) -> OperationResult<()> {
+        if unsafe { qb_comm_check(self.comm) } != QB_OK { return Err(OperationError::service_error(last_error())); }
+        Ok(())
+    }
 }
