@@ -325,7 +325,7 @@ QB_API qb_status qb_multi_search_batch(qb_comm* c, qb_storage* shard, const floa
  *   dev_local / dev_local_counts != NULL: they receive the shard's own lists (n_queries x top, n_queries); scan, exchange and merge are all
  *     enqueued on qb_storage_stream(shard).
  *   dev_local == NULL (both): PIPELINED — the scan runs on qb_storage_stream(shard), the exchange + merge on qb_comm_stream(c), and the next
- *     call's scan does not wait for this call's merge (a window of two steps, ring of four exchange slots): consecutive independent query
+ *     call's scan does not wait for this call's merge (a window of two steps over rings of four list buffers / exchange slots): consecutive independent query
  *     batches overlap across GPUs instead of meeting at a barrier per batch.  dev_out / dev_counts of a call are complete once
  *     qb_comm_stream(c) has drained; successive calls write them in order. */
 QB_API qb_status qb_multi_search_batch_device(qb_comm* c, qb_storage* shard, const float* dev_queries, uint32_t n_queries, uint32_t top,

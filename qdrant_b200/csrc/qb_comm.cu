@@ -19,10 +19,12 @@
 // Waiting for the slowest of N GPUs once per query is what limits strong scaling of a 0.6 ms scan (max-of-8 of the scan times, not
 // their mean, sets the step).  The device-resident entry point therefore PIPELINES independent steps: the exchange + merge kernel of step
 // i runs on the communicator's own high-priority stream (it needs one small CTA and co-resides with the scan), while the scan of step
-// i + 1 starts at once on the storage's stream.  Flow control: a rank starts scan(i) only after its own merge(i - 2) has completed
-// (window W = 2) and lists travel through a ring of R = 4 slots; when X pushes step i, every peer Y has completed merge(i - 2W) — X's
-// merge(i - W) saw Y's push(i - W), Y's scan(i - W) started after Y's merge(i - 2W) — so the slot X overwrites (step i - R, R = 2W) has
-// been consumed.  Results of step i are complete when the communicator's stream has run its merge (qb_comm_stream).
+// i + 1 starts at once on the storage's stream.  Flow control: a rank starts scan(i) only after its own merge(i - 2) has completed (window
+// W = 2), so at most two steps' lists wait in the shard's local ring (four buffers: a scan never overwrites lists that were not pushed).
+// Remote slots (a ring of four, two would do): the exchange streams are in order — X pushes step i only after its merge(i - 1), which saw
+// Y's push(i - 1), which Y issued after its merge(i - 2) — so a push never overwrites a slot its owner has not merged
+// (tests/test_pipeline_protocol.py model-checks both hazards under random schedules).  Results of step i are complete when the
+// communicator's stream has run its merge (qb_comm_stream).
 #include <algorithm>
 #include <functional>
 
