@@ -60,6 +60,7 @@ QbOptions& qb_opt() {
         v.disable_localk = getenv("QB_DISABLE_LOCALK") != nullptr;
         v.disable_prefilter = getenv("QB_DISABLE_PREFILTER") != nullptr;
         v.prefilter_plane = (int)num("QB_PREFILTER_PLANE", 0);
+        v.prefilter_slot_bytes = (uint32_t)num("QB_PREFILTER_SLOT_BYTES", 0);
         v.disable_mma = getenv("QB_DISABLE_MMA") != nullptr;
         v.mma_1cta = getenv("QB_MMA_1CTA") != nullptr;
         v.mma_no_segments = getenv("QB_MMA_NO_SEGMENTS") != nullptr;
@@ -81,6 +82,7 @@ extern "C" qb_status qb_set_option(const char* name, int64_t value) {
     if (n == "disable_localk") o.disable_localk = value != 0;
     else if (n == "disable_prefilter") o.disable_prefilter = value != 0;
     else if (n == "prefilter_plane") o.prefilter_plane = (int)value;
+    else if (n == "prefilter_slot_bytes") o.prefilter_slot_bytes = (uint32_t)value;
     else if (n == "disable_mma") o.disable_mma = value != 0;
     else if (n == "mma_1cta") o.mma_1cta = value != 0;
     else if (n == "mma_no_segments") o.mma_no_segments = value != 0;

@@ -29,6 +29,7 @@ namespace {
 
 constexpr int PF_CONSUMER_WARPS = 8;
 constexpr int PF_THREADS = 32 * (PF_CONSUMER_WARPS + 1);
+constexpr uint32_t PF_SLOT_BYTES = 12288;  // target bytes per ring slot (a consumer warp holds one slot while the others are in flight)
 constexpr uint32_t PF_CAP = 16384;         // candidate rows per query (a few hundred to a few thousand expected)
 
 struct PfParams {
@@ -354,7 +355,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
 template <int NCH>
 qb_status launch_filter_q8(Pf8Params& p, int sm_count, cudaStream_t stream) {
     const uint32_t kMaxSmem = 227 * 1024;
-    uint32_t rps = (12288 / p.stride) & ~1u;
+    const uint32_t target = qb_opt().prefilter_slot_bytes ? qb_opt().prefilter_slot_bytes : PF_SLOT_BYTES;
+    uint32_t rps = (target / p.stride) & ~1u;
     if (rps < 2) rps = 2;
     p.rows_per_slot = rps;
     p.slot_bytes = rps * p.stride;
@@ -426,7 +428,8 @@ __global__ void __launch_bounds__(256) f32_prefilter_finish_kernel(const uint8_t
 template <int NCH>
 qb_status launch_filter(PfParams& p, int sm_count, cudaStream_t stream) {
     const uint32_t kMaxSmem = 227 * 1024;
-    uint32_t rps = (12288 / p.stride) & ~1u;      // 12-KB slots, sixteen of them: the shape the f32 stream kernel saturates HBM with
+    const uint32_t target = qb_opt().prefilter_slot_bytes ? qb_opt().prefilter_slot_bytes : PF_SLOT_BYTES;
+    uint32_t rps = (target / p.stride) & ~1u;
     if (rps < 2) rps = 2;
     p.rows_per_slot = rps;
     p.slot_bytes = rps * p.stride;
