@@ -83,6 +83,7 @@ extern "C" qb_status qb_set_option(const char* name, int64_t value) {
     else if (n == "disable_prefilter") o.disable_prefilter = value != 0;
     else if (n == "prefilter_plane") o.prefilter_plane = (int)value;
     else if (n == "prefilter_slot_bytes") o.prefilter_slot_bytes = (uint32_t)value;
+    else if (n == "prefilter_producers") o.prefilter_producers = (int)value;
     else if (n == "disable_mma") o.disable_mma = value != 0;
     else if (n == "mma_1cta") o.mma_1cta = value != 0;
     else if (n == "mma_no_segments") o.mma_no_segments = value != 0;

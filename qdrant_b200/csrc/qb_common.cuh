@@ -47,6 +47,7 @@ struct QbOptions {
     int pq_queries_per_pass = 0;   // 0 = automatic
     int hnsw_threads = 0;          // 0 / 128 (default) or 256 threads per traversal CTA
     bool hnsw_no_prefetch = false;
+    int prefilter_producers = 0;       // single-query prefilter: producer warps per CTA (0 = default)
     uint32_t prefilter_slot_bytes = 0; // single-query prefilter: target bytes per ring slot (0 = default)
     int prefilter_plane = 0;          // single-query prefilter: 0 = int8 shadow plane when the storage allows it, 1 = bf16 shadow plane
     bool disable_prefilter = false;   // single-query dense f32 searches: always the exact f32 scan (no bf16 shadow plane, qb_prefilter.cu)

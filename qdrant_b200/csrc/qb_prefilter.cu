@@ -28,9 +28,14 @@ qb_status qb_dense_f32_scan_localk(const qb_storage* s, const QbScanArgs& a, uin
 namespace {
 
 constexpr int PF_CONSUMER_WARPS = 8;
-constexpr int PF_THREADS = 32 * (PF_CONSUMER_WARPS + 1);
+constexpr int PF_MAX_PRODUCERS = 4;
+constexpr int PF_PRODUCERS = 2;             // producer warps (one lane each): a bulk copy costs its issuing thread ~500 clocks (wait for the slot, arm the
+                                            // barrier, issue), so ONE producer caps a CTA at one 12-KB slot per ~500 clocks — below the HBM rate for these planes
+constexpr int PF_THREADS = 32 * (PF_CONSUMER_WARPS + PF_MAX_PRODUCERS);     // launch bound; the launch uses 32 * (consumers + producers)
 constexpr uint32_t PF_SLOT_BYTES = 12288;  // target bytes per ring slot (a consumer warp holds one slot while the others are in flight)
 constexpr uint32_t PF_CAP = 16384;         // candidate rows per query (a few hundred to a few thousand expected)
+
+static int pf_producers() { const int o = qb_opt().prefilter_producers; return (o >= 1 && o <= PF_MAX_PRODUCERS) ? o : PF_PRODUCERS; }
 
 struct PfParams {
     const uint8_t* rows;        // bf16 plane
@@ -68,24 +73,28 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_bf16_filter_kernel(const 
         qb_fence_barrier_init();
     }
     __syncthreads();
-    if (warp == 0) {
+    const int n_prod = (int)(blockDim.x >> 5) - PF_CONSUMER_WARPS;
+    if (warp < n_prod) {
         if (lane == 0) {
             const uint64_t policy = p.l2_keep ? qb_policy_evict_last() : qb_policy_evict_first();
-            for (uint64_t i = 0; i < n_local; ++i) {
-                const uint32_t s = (uint32_t)(i % p.n_slots);
-                const uint32_t ph = (uint32_t)((i / p.n_slots) & 1);
+            // slot / phase / first row advance incrementally: 64-bit divisions in this loop cost more than the copy they issue
+            uint32_t s = (uint32_t)warp, ph = 0;                 // n_slots is a multiple of 8, n_prod of 1 / 2 / 4: s wraps exactly
+            uint64_t r0 = ((uint64_t)blockIdx.x + (uint64_t)warp * gridDim.x) * p.rows_per_slot;
+            const uint64_t r_step = (uint64_t)n_prod * gridDim.x * p.rows_per_slot;
+            for (uint64_t i = warp; i < n_local; i += n_prod, r0 += r_step) {
                 qb_mbar_wait(&empty[s], ph ^ 1u);
-                const uint64_t r0 = (blockIdx.x + i * gridDim.x) * p.rows_per_slot;
                 const uint64_t left = p.n_rows - r0;
                 const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
                 const uint32_t bytes = nr * p.stride;
                 qb_mbar_arrive_expect_tx(&full[s], bytes);
                 qb_bulk_g2s(slots + (size_t)s * p.slot_bytes, p.rows + r0 * p.stride, bytes, &full[s], policy);
+                s += (uint32_t)n_prod;
+                if (s >= p.n_slots) { s -= p.n_slots; ph ^= 1u; }
             }
         }
         return;
     }
-    const int cw = warp - 1;
+    const int cw = warp - n_prod;
     // this lane's slice of the query: dimensions [ (c * 32 + lane) * 8, + 8 ) for c < NCH, zero past dim
     float qr[NCH][8];
     uint32_t off[NCH];
@@ -112,10 +121,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_bf16_filter_kernel(const 
         const float thr = (*p.samp_cnt >= p.top) ? p.samp_out[p.top - 1].score : __int_as_float(0xff800000);
         thr_adj = __fsub_rd(thr, eps);                           // NaN query -> NaN: `approx < NaN` is false, every row passes (-> fallback)
     }
-    for (uint64_t i = cw; i < n_local; i += PF_CONSUMER_WARPS) {
-        const uint32_t s = (uint32_t)(i % p.n_slots);
-        const uint32_t ph = (uint32_t)((i / p.n_slots) & 1);
-        const uint64_t r0 = (blockIdx.x + i * gridDim.x) * p.rows_per_slot;
+    uint32_t s = (uint32_t)cw, ph = 0;                            // as in the producers: no 64-bit division per slot
+    uint64_t r0 = ((uint64_t)blockIdx.x + (uint64_t)cw * gridDim.x) * p.rows_per_slot;
+    const uint64_t r_step = (uint64_t)PF_CONSUMER_WARPS * gridDim.x * p.rows_per_slot;
+    for (uint64_t i = cw; i < n_local; i += PF_CONSUMER_WARPS, r0 += r_step) {
         const uint64_t left = p.n_rows - r0;
         const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
         qb_mbar_wait(&full[s], ph);
@@ -160,6 +169,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_bf16_filter_kernel(const 
         }
         __syncwarp();
         if (lane == 0) qb_mbar_arrive(&empty[s]);
+        s += PF_CONSUMER_WARPS;
+        if (s >= p.n_slots) { s -= p.n_slots; ph ^= 1u; }
     }
 }
 
@@ -242,24 +253,28 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
         qb_fence_barrier_init();
     }
     __syncthreads();
-    if (warp == 0) {
+    const int n_prod = (int)(blockDim.x >> 5) - PF_CONSUMER_WARPS;
+    if (warp < n_prod) {
         if (lane == 0) {
             const uint64_t policy = p.l2_keep ? qb_policy_evict_last() : qb_policy_evict_first();
-            for (uint64_t i = 0; i < n_local; ++i) {
-                const uint32_t s = (uint32_t)(i % p.n_slots);
-                const uint32_t ph = (uint32_t)((i / p.n_slots) & 1);
+            // slot / phase / first row advance incrementally: 64-bit divisions in this loop cost more than the copy they issue
+            uint32_t s = (uint32_t)warp, ph = 0;                 // n_slots is a multiple of 8, n_prod of 1 / 2 / 4: s wraps exactly
+            uint64_t r0 = ((uint64_t)blockIdx.x + (uint64_t)warp * gridDim.x) * p.rows_per_slot;
+            const uint64_t r_step = (uint64_t)n_prod * gridDim.x * p.rows_per_slot;
+            for (uint64_t i = warp; i < n_local; i += n_prod, r0 += r_step) {
                 qb_mbar_wait(&empty[s], ph ^ 1u);
-                const uint64_t r0 = (blockIdx.x + i * gridDim.x) * p.rows_per_slot;
                 const uint64_t left = p.n_rows - r0;
                 const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
                 const uint32_t bytes = nr * p.stride;
                 qb_mbar_arrive_expect_tx(&full[s], bytes);
                 qb_bulk_g2s(slots + (size_t)s * p.slot_bytes, p.rows + r0 * p.stride, bytes, &full[s], policy);
+                s += (uint32_t)n_prod;
+                if (s >= p.n_slots) { s -= p.n_slots; ph ^= 1u; }
             }
         }
         return;
     }
-    const int cw = warp - 1;
+    const int cw = warp - n_prod;
     // query statistics over the whole vector, then this lane's slice quantised to two int8 levels
     float qv[NCH][8];
     uint32_t off[NCH];
@@ -307,10 +322,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
     const float thr = (*p.samp_cnt >= p.top) ? p.samp_out[p.top - 1].score : __int_as_float(0xff800000);
     const float thr_adj = qbad ? __int_as_float(0x7fc00000) : __fsub_rd(thr, slack);
     const float k254 = 1.0f / 254.0f;
-    for (uint64_t i = cw; i < n_local; i += PF_CONSUMER_WARPS) {
-        const uint32_t s = (uint32_t)(i % p.n_slots);
-        const uint32_t ph = (uint32_t)((i / p.n_slots) & 1);
-        const uint64_t r0 = (blockIdx.x + i * gridDim.x) * p.rows_per_slot;
+    uint32_t s = (uint32_t)cw, ph = 0;                            // as in the producers: no 64-bit division per slot
+    uint64_t r0 = ((uint64_t)blockIdx.x + (uint64_t)cw * gridDim.x) * p.rows_per_slot;
+    const uint64_t r_step = (uint64_t)PF_CONSUMER_WARPS * gridDim.x * p.rows_per_slot;
+    for (uint64_t i = cw; i < n_local; i += PF_CONSUMER_WARPS, r0 += r_step) {
         const uint64_t left = p.n_rows - r0;
         const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
         qb_mbar_wait(&full[s], ph);
@@ -349,6 +364,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
         }
         __syncwarp();
         if (lane == 0) qb_mbar_arrive(&empty[s]);
+        s += PF_CONSUMER_WARPS;
+        if (s >= p.n_slots) { s -= p.n_slots; ph ^= 1u; }
     }
 }
 
@@ -369,7 +386,7 @@ qb_status launch_filter_q8(Pf8Params& p, int sm_count, cudaStream_t stream) {
     QB_CUDA(cudaFuncSetAttribute(dense_q8_filter_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     const uint64_t n_tiles = ceil_div_u64(p.n_rows, p.rows_per_slot);
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sm_count);
-    dense_q8_filter_kernel<NCH><<<grid, PF_THREADS, smem, stream>>>(p);
+    dense_q8_filter_kernel<NCH><<<grid, 32 * (PF_CONSUMER_WARPS + pf_producers()), smem, stream>>>(p);
     QB_LAUNCHED();
     QB_CUDA(cudaGetLastError());
     return QB_OK;
@@ -442,7 +459,7 @@ qb_status launch_filter(PfParams& p, int sm_count, cudaStream_t stream) {
     QB_CUDA(cudaFuncSetAttribute(dense_bf16_filter_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     const uint64_t n_tiles = ceil_div_u64(p.n_rows, p.rows_per_slot);
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sm_count);
-    dense_bf16_filter_kernel<NCH><<<grid, PF_THREADS, smem, stream>>>(p);
+    dense_bf16_filter_kernel<NCH><<<grid, 32 * (PF_CONSUMER_WARPS + pf_producers()), smem, stream>>>(p);
     QB_LAUNCHED();
     QB_CUDA(cudaGetLastError());
     return QB_OK;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """prefilter_probe.py [rows] [dim] — single-query searches over one synthetic cosine storage (generated on the device), device-timed, for several
-ring-slot sizes of the shadow-plane filter kernels and both planes; prints one JSON line.  Results of every variant are compared with the exact scan."""
+ring-slot sizes / producer-warp counts of the shadow-plane filter kernels and both planes; prints one JSON line.  Results of every variant are compared with the exact scan."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -50,13 +50,16 @@ out = {"rows": rows, "dim": dim, "exact_f32_scan": run(10)}
 qb.set_option("disable_prefilter", 0)
 for plane, name in ((0, "int8"), (1, "bf16")):
     qb.set_option("prefilter_plane", plane)
-    for slot in (12288, 8192, 6144, 4096, 3072):
-        qb.set_option("prefilter_slot_bytes", slot)
-        got = [st.search_batch(queries[i], 10)[0] for i in range(4)]
-        same = all(np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32)) for a, b in zip(got, exact))
-        r = run()
-        r["identical_to_exact_scan"] = bool(same)
-        out[f"{name}_slot{slot}"] = r
+    for prod in (1, 2, 4):
+        qb.set_option("prefilter_producers", prod)
+        for slot in (12288, 8192, 6144):
+            qb.set_option("prefilter_slot_bytes", slot)
+            got = [st.search_batch(queries[i], 10)[0] for i in range(4)]
+            same = all(np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32)) for a, b in zip(got, exact))
+            r = run()
+            r["identical_to_exact_scan"] = bool(same)
+            out[f"{name}_producers{prod}_slot{slot}"] = r
+qb.set_option("prefilter_producers", 0)
 qb.set_option("prefilter_slot_bytes", 0); qb.set_option("prefilter_plane", 0)
 out["fallbacks"] = int(st.search_stats()[1])
 print(json.dumps(out))
