@@ -145,17 +145,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(con
     if (warp == 0) {
         if (lane == 0) {
             const uint64_t policy = p.l2_keep ? qb_policy_evict_last() : qb_policy_evict_first();
-            for (uint64_t i = 0; i < n_local; ++i) {
-                const uint32_t s = (uint32_t)(i % p.n_slots);
-                const uint32_t ph = (uint32_t)((i / p.n_slots) & 1);
+            // slot, phase and first row advance incrementally: a 64-bit division per copy costs the issuing thread more than the copy
+            uint32_t s = 0, ph = 0;
+            uint64_t r0 = p.row_begin + (uint64_t)blockIdx.x * p.rows_per_slot;
+            const uint64_t r_step = (uint64_t)gridDim.x * p.rows_per_slot;
+            for (uint64_t i = 0; i < n_local; ++i, r0 += r_step) {
                 qb_mbar_wait(&empty[s], ph ^ 1u);
-                const uint64_t g = blockIdx.x + i * gridDim.x;
-                const uint64_t r0 = p.row_begin + g * p.rows_per_slot;
                 const uint64_t left = p.row_end - r0;
                 const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
                 const uint32_t bytes = nr * p.stride;
                 qb_mbar_arrive_expect_tx(&full[s], bytes);
                 qb_bulk_g2s(slots + (size_t)s * p.slot_bytes, p.rows + r0 * p.stride, bytes, &full[s], policy);
+                if (++s == p.n_slots) { s = 0; ph ^= 1u; }
             }
         }
     } else {
@@ -168,11 +169,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dense_f32_stream_kernel(con
         float wthr = __int_as_float(0xff800000);  // score of wmin once the list is full
         unsigned long long* lk_queue = reinterpret_cast<unsigned long long*>(empty + p.n_slots) + STREAM_CONSUMER_WARPS * QB_LOCALK_SLOTS;  // [8][4]
         unsigned int* lk_count = reinterpret_cast<unsigned int*>(lk_queue + STREAM_CONSUMER_WARPS * 4);                                   // [8]
-        for (uint64_t i = cw; i < n_local; i += STREAM_CONSUMER_WARPS) {
-            const uint32_t s = (uint32_t)(i % p.n_slots);
-            const uint32_t ph = (uint32_t)((i / p.n_slots) & 1);
-            const uint64_t g = blockIdx.x + i * gridDim.x;
-            const uint64_t r0 = p.row_begin + g * p.rows_per_slot;
+        uint32_t s = (uint32_t)cw, ph = 0;                        // n_slots is a multiple of STREAM_CONSUMER_WARPS: s wraps exactly
+        uint64_t r0 = p.row_begin + ((uint64_t)blockIdx.x + (uint64_t)cw * gridDim.x) * p.rows_per_slot;
+        const uint64_t r_step = (uint64_t)STREAM_CONSUMER_WARPS * gridDim.x * p.rows_per_slot;
+        for (uint64_t i = cw; i < n_local; i += STREAM_CONSUMER_WARPS, r0 += r_step, s += STREAM_CONSUMER_WARPS) {
+            if (s >= p.n_slots) { s -= p.n_slots; ph ^= 1u; }
             const uint64_t left = p.row_end - r0;
             const uint32_t nr = (uint32_t)(left < p.rows_per_slot ? left : p.rows_per_slot);
             qb_mbar_wait(&full[s], ph);
