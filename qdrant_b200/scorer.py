@@ -219,9 +219,9 @@ class RawScorer:
             self._h = None
 
     def __del__(self):
-        if sys.is_finalizing():  # the CUDA runtime / library may already be torn down at interpreter exit
-            return
         try:
+            if sys is None or sys.is_finalizing():  # the CUDA runtime / library may already be torn down at interpreter exit
+                return
             self.close()
         except Exception:
             pass
@@ -344,9 +344,9 @@ class _Storage:
             self._h = vp()
 
     def __del__(self):
-        if sys.is_finalizing():
-            return
         try:
+            if sys is None or sys.is_finalizing():     # interpreter shutdown: module globals may already be gone
+                return
             self.close()
         except Exception:
             pass
@@ -743,9 +743,9 @@ class HnswGraph:
             self._h = vp()
 
     def __del__(self):
-        if sys.is_finalizing():
-            return
         try:
+            if sys is None or sys.is_finalizing():     # interpreter shutdown: module globals may already be gone
+                return
             self.close()
         except Exception:
             pass

@@ -18,7 +18,8 @@ def qb():
     return scorer
 
 
-@pytest.mark.parametrize("world,nq,top,n,dim", [(2, 1, 10, 150_003, 64), (3, 5, 10, 90_001, 96), (4, 40, 7, 70_000, 32), (8, 1, 10, 80_000, 128)])
+@pytest.mark.parametrize("world,nq,top,n,dim", [(2, 1, 10, 150_003, 64), (3, 5, 10, 90_001, 96), (4, 40, 7, 70_000, 32), (8, 1, 10, 80_000, 128),
+                                                (2, 1, 10, 1_200_001, 64)])   # the last one: shards of >= 2^19 rows answer through the shadow-plane scan
 def test_sharded_equals_single_through_the_c_abi(qb, oracle, world, nq, top, n, dim):
     import torch
 
@@ -72,7 +73,7 @@ def test_sharded_equals_single_through_the_c_abi(qb, oracle, world, nq, top, n, 
     single.close()
 
 
-@pytest.mark.parametrize("world,nq,top,n,dim", [(2, 1, 10, 150_003, 64), (4, 3, 10, 120_000, 96), (8, 1, 10, 160_000, 128)])
+@pytest.mark.parametrize("world,nq,top,n,dim", [(2, 1, 10, 150_003, 64), (4, 3, 10, 120_000, 96), (8, 1, 10, 160_000, 128), (2, 1, 10, 1_200_001, 64)])
 def test_pipelined_device_steps_equal_single(qb, oracle, world, nq, top, n, dim):
     """qb_multi_search_batch_device with dev_local = NULL: the exchange + merge of step i runs on the communicator's stream while the
     scan of step i + 1 is already enqueued (window of two steps, ring of four slots).  Fourteen back-to-back steps without any host
