@@ -6,15 +6,19 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A step = one query (BASELINE configs[1]: single-query streaming scan) answered over the WHOLE data set: every rank
-scans its shard (10M/N rows, strong scaling), local top-10 lists are all-gathered over NCCL/NVLink and merged.
+scans its shard (10M/N rows, strong scaling); the shards' top-10 lists cross GPUs through peer-mapped buffers inside the merge
+kernel (qb_comm.cu; consecutive steps are pipelined across GPUs), every rank ends up with the merged list.
   value  : queries/s with the query already resident in HBM (CUDA events on the launch stream, max over ranks)
-  e2e    : the same through the public host API — qb_search_batch (N=1) / ShardedSegmentSearcher.search (N>1): host
+  e2e    : the same through the public host API — qb_search_batch (N=1) / qb_multi_search_batch (N>1): host
            query in (H2D inside), host top-k out (D2H inside), wall clock, max over ranks.  The data set itself is
            resident state of the storage (uploaded once, like the reference's vectors in RAM), not a per-step input.
-  roofline: the dominant kernel (dense_f32_stream_kernel, main pass) timed live with CUDA events on its stream;
-           achieved = rows_per_rank*768*4 B / avg launch time, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline: the oracle's restatement of the reference's AVX2+FMA path (peek_top_iter loop) on this box's cores,
-           on a bounded sample of the same rows, extrapolated to 10M rows.
+  roofline: the dominant kernel timed live with CUDA events on its stream (qb_profile_enable).  Shards of >= 2^19 rows are
+           scanned through the int8 shadow plane (dense_q8_filter_kernel, qb_prefilter.cu) with exact rescoring — results
+           bit-identical to the f32 scan, asserted inside the run; achieved = ALGORITHMIC bytes (rows_per_rank*768*4)
+           / avg launch time against MEASURED_PEAKS.json hbm_gbs, so it exceeds the peak; bytes_moved_per_launch /
+           hbm_frac_of_bytes_moved describe the kernel's own traffic.  QB_DISABLE_PREFILTER=1 measures the f32 scan itself.
+  cpu_baseline: the oracle's restatement of the reference's AVX2+FMA path (peek_top_iter loop) on this box's cores: the FULL
+           10M rows per query when RAM allows (pinned threads, one first-touched segment each, oracle/mt.c).
 `--impl reference` times only that CPU path and prints the same JSON shape.
 
 The default run (`--config all`) prints ONE JSON line: the C2 headline fields above plus `configs.{c3,c4,c5}` — the other
