@@ -527,10 +527,10 @@ qb_status qb_dense_f32_scan_fold(const qb_storage* s, const QbScanArgs& a, int k
 
 // Single-query scan with per-CTA top-k lists (top <= 16): writes *n_slots candidate keys (zeros = empty) to a.emit.cand.
 // *n_slots = 0 when the shape does not suit the streaming kernel (the caller then takes the generic path).
-qb_status qb_dense_f32_scan_localk(const qb_storage* s, const QbScanArgs& a, uint32_t top, uint64_t* n_slots, cudaStream_t stream) {
+qb_status qb_dense_f32_scan_localk(const qb_storage* s, const QbScanArgs& a, uint32_t top, uint64_t* n_slots, cudaStream_t stream, uint64_t min_rows) {
     *n_slots = 0;
     const uint64_t n = a.row_end - a.row_begin;
-    if (a.d_ids || a.nq != 1 || top > (uint32_t)QB_LOCALK_SLOTS || s->dim < 32 || n < 65536) return QB_OK;
+    if (a.d_ids || a.nq != 1 || top > (uint32_t)QB_LOCALK_SLOTS || s->dim < 32 || n < min_rows) return QB_OK;
     StreamParams sp{};
     sp.rows = reinterpret_cast<const uint8_t*>(s->d_rows);
     sp.stride = s->row_stride; sp.dim = s->dim;

@@ -8,7 +8,7 @@
 //   + f32 evaluation of either sum, any order:  <=  dim 2^-24 ||q|| ||x|| each
 //   =>  |approx - exact|  <=  eps_q := (2^-9 + dim 2^-22) ||q|| max_rows ||x||  (1 + 2^-10)
 // Four launches per query, no host synchronisation:
-//   1. the EXACT in-kernel-top-k scan (dense_f32_stream_kernel<., LOCALK>) over a prefix of the rows -> thr_q = the k-th best exact score
+//   1. the EXACT in-kernel-top-k scan (dense_f32_stream_kernel<., LOCALK>) over a prefix of the rows (1/64 of them, 2^14..2^17) -> thr_q = the k-th best exact score
 //      of the sample (a lower bound of the final k-th score);
 //   2. dense_bf16_filter_kernel: the whole bf16 plane streams through the same TMA-bulk ring (dim * 2 bytes per row); the query sits in
 //      REGISTERS (a lane always meets the same dimensions); rows with approx >= thr_q - eps_q are appended to a candidate list — a
@@ -23,7 +23,7 @@
 #include "qb_internal.h"
 #include "qb_score.cuh"
 
-qb_status qb_dense_f32_scan_localk(const qb_storage* s, const QbScanArgs& a, uint32_t top, uint64_t* n_slots, cudaStream_t stream);   // qb_dense.cu
+qb_status qb_dense_f32_scan_localk(const qb_storage* s, const QbScanArgs& a, uint32_t top, uint64_t* n_slots, cudaStream_t stream, uint64_t min_rows = 65536);   // qb_dense.cu
 
 namespace {
 
@@ -523,13 +523,14 @@ qb_status qb_f32_prefilter_search(qb_storage* s, const QbScanArgs& a, uint32_t t
     uint32_t* d_cand = reinterpret_cast<uint32_t*>(d_keys + PF_CAP);
     const uint64_t n = s->count;
     // 1. exact top-k of a prefix
-    uint64_t sample = std::min<uint64_t>(131072, std::max<uint64_t>(65536, (n / 64) & ~(uint64_t)3));
-    if (qb_opt().sample_rows) sample = std::min<uint64_t>(n, std::max<uint64_t>(65536, qb_opt().sample_rows & ~(uint64_t)3));   // experiments
+    // 1/64 of the rows, 2^14..2^17: a shard of a sharded search (1.25M rows at N = 8) should not spend a fifth of its step on the sample
+    uint64_t sample = std::min<uint64_t>(131072, std::max<uint64_t>(16384, (n / 64) & ~(uint64_t)3));
+    if (qb_opt().sample_rows) sample = std::min<uint64_t>(n, std::max<uint64_t>(16384, qb_opt().sample_rows & ~(uint64_t)3));   // experiments
     QbScanArgs as = a;
     as.row_begin = 0; as.row_end = sample;
     as.emit.final_out = d_samp; as.emit.final_count = d_samp_cnt; as.emit.run_if = nullptr;
     uint64_t n_slots = 0;
-    QB_TRY(qb_dense_f32_scan_localk(s, as, top, &n_slots, stream));
+    QB_TRY(qb_dense_f32_scan_localk(s, as, top, &n_slots, stream, 4096));
     QB_CHECK(n_slots != 0 && n_slots <= 4096, QB_ERR_CUDA, "prefilter: the sample scan did not launch (%llu slots)", (unsigned long long)n_slots);
     // 2. filter pass over the whole shadow plane
     const float* d_q = reinterpret_cast<const float*>(a.d_q_enc);
