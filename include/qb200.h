@@ -176,7 +176,13 @@ QB_API qb_status qb_scorer_take_counters(qb_scorer* sc, qb_hw_counters* out);
  *   is_stopped     optional cancellation flag, polled between kernel launches
  *   out            n_queries x top; out_counts[q] = number of valid entries (< top when fewer candidates)
  * Ties: ScoredPointOffset orders by score only, so which of several equal-score points survives at the
- * k-th boundary is unspecified in the reference; this library orders by (score desc, id asc). */
+ * k-th boundary is unspecified in the reference; this library orders by (score desc, id asc).
+ * How the scan is carried out never changes the result: large dense f32 storages keep compact shadow planes of their rows
+ * (built on the first search that uses them, rebuilt after qb_storage_write_rows*: + 26 % HBM for the int8 plane of single-query
+ * searches on >= 2^19 rows, + 50 % for the bf16 plane of batches of >= 32 queries; dot / cosine only), batched SQ8 / PQ scans run
+ * prefilter kernels — in every case the rows that can reach the top-k are re-scored with the reference's exact arithmetic before
+ * selection, and a case the prefilter cannot decide falls back to the exact scan (qb_search_stats counts those).
+ * qb_set_option("disable_prefilter" / "disable_mma", 1) keeps a process on the exact kernels and allocates no plane. */
 QB_API qb_status qb_search_batch(qb_storage* s, const float* queries, uint32_t n_queries, uint32_t top,
                           const uint64_t* deleted_bitmap, const uint32_t* id_list, uint64_t n_ids,
                           const volatile int32_t* is_stopped, qb_scored_point* out, uint32_t* out_counts,
