@@ -366,7 +366,8 @@ def main_ours(args):
         assert np.array_equal(got["idx"], want["idx"] + np.uint32(b))
         parity = {"checked": True, "rows_checked_per_rank": rows, "scan_vs_oracle": "bit-exact"}
         if world > 1:
-            searcher.d_queries[:1].copy_(d_all_q[:1])
+            with torch.cuda.stream(stream):
+                searcher.d_queries[:1].copy_(d_all_q[:1], non_blocking=True)      # on the storage's stream: ordered before the scan
             searcher.search_device(1)
             merged = searcher.results_host(1)[0]
             local = st.search_batch(queries[0], TOP)[0]          # this rank's own top-k through the plain C-ABI call (global ids)
@@ -706,6 +707,7 @@ def main_c4(args):
     queries = np.random.default_rng(45).standard_normal((nq, dim)).astype(np.float32)
     searcher = ShardedSegmentSearcher(st, id_base=rank * n_local, top=top, max_queries=nq, device=dev)
     searcher.d_queries.copy_(torch.from_numpy(queries).to(dev))
+    torch.cuda.synchronize()          # the copy ran on torch's stream, the searches run on the storage's
     W, K = max(args.warmup, 3), args.steps
 
     def barrier():
