@@ -412,7 +412,9 @@ def main_ours(args):
         traffic, traffic_src = ncu_traffic(("ncu_q8_filter_kernel_r02.txt" if plane_q8 else "ncu_bf16_filter_kernel_r02.txt") if prefilter else "ncu_stream_kernel_r01_localk.txt") if (n_local == 10_000_000 and args.dim == 768) else (None, None)
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": ("f32 results (exact reference arithmetic); the scan itself runs on an " + ("int8" if plane_q8 else "bf16") + " shadow plane and re-scores the survivors in f32") if prefilter else "f32",
+            "data": "synthetic",
             "config": dict(c2_config(args.rows, args.dim), rows_per_gpu=n_local, parallelism=f"row-sharded x{world}, top-k exchange ({exchange}) + device merge",
                            l2="inputs larger than L2 (shard = %.1f GB >> 126 MB), no flush needed" % (algo_bytes / 1e9)),
             "gb_per_s_scanned": qps * args.rows * args.dim * 4 / 1e9,
