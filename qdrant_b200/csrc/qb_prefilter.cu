@@ -297,8 +297,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) dense_q8_filter_kernel(const Pf
         qmax = fmaxf(qmax, __shfl_xor_sync(0xFFFFFFFFu, qmax, o)); q1 = __fadd_ru(q1, __shfl_xor_sync(0xFFFFFFFFu, q1, o)); q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, o);
         qbad |= __shfl_xor_sync(0xFFFFFFFFu, (int)qbad, o) != 0;
     }
+    qbad |= (qmax > 0.f && qmax < 1.0e-30f);                     // 127 / qmax would overflow: leave such a query to the exact scan
     const float sq = (qmax > 0.f) ? __fdiv_rn(qmax, 127.f) : 0.f;
-    const float inv_sq = (qmax > 0.f) ? __fdiv_rn(127.f, qmax) : 0.f;
+    const float inv_sq = (qmax > 0.f && !qbad) ? __fdiv_rn(127.f, qmax) : 0.f;
     uint32_t hq[NCH][2], lq[NCH][2];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
